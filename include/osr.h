@@ -1,0 +1,173 @@
+/*
+ * osr.h - C ABI of libosr_sm100a.so: the B200-native RoI hot path of Openset-RCNN.
+ *
+ * One shared library, loaded with ctypes (Python host, like the reference) or linked from C/C++.
+ * No torch / pybind types cross this boundary: plain device pointers, sizes, strides, scalars.
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = OK, >0 = cudaError_t of a failed launch / API call,
+ *     <0 = argument or shape error (OSR_E_*).  osr_last_error() returns a thread-local message.
+ *   - the library never allocates or frees device memory and keeps no global mutable state:
+ *     the caller owns all outputs and the workspace (size from the matching *_workspace()).
+ *   - every call is asynchronous on the cudaStream_t passed as `stream` (void*), never syncs,
+ *     never touches the default stream implicitly; all exports are re-entrant.
+ *   - pointers are DEVICE pointers unless the name starts with h_ (host).
+ *   - fp32 everywhere at the boundary (the reference has no AMP); boxes are xyxy absolute pixels.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * Yifei-Y/Openset-RCNN checkout).
+ */
+#ifndef OSR_H_
+#define OSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSR_ABI_VERSION 1
+#define OSR_MAX_LEVELS 8
+
+#define OSR_E_ARG (-1)       /* null pointer / negative size / unsupported value            */
+#define OSR_E_SHAPE (-2)     /* size outside what the kernels support (message says which)  */
+#define OSR_E_WORKSPACE (-3) /* workspace too small                                         */
+
+int osr_version(void);
+const char* osr_last_error(void);
+/* Number of kernel launches issued by this process since the last call to osr_reset_launch_count(). */
+long long osr_launch_count(void);
+void osr_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) CF-RPN proposal stage
+ * Replaces ClsFreeRPN.predict_proposals + _decode_proposals
+ *   openset_rcnn/modeling/proposal_generator/classification_free_rpn.py:558-610
+ * and find_top_rpn_proposals steps 1-3 (top-k, gather, finite check, clip, small-box filter)
+ *   openset_rcnn/modeling/find_top_proposals.py:63-110
+ * Decode is detectron2 Box2BoxTransformLinear(normalize_by_size=True).apply_deltas, applied only
+ * to the selected anchors (select-then-decode is bit-identical: decode is elementwise).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* deltas;    /* element (n, i, c) at deltas[n*delta_stride_n + i*delta_stride_a + c*delta_stride_c] */
+  const float* scores;    /* element (n, i)    at scores[n*score_stride_n + i*score_stride_a]                    */
+  const float* anchors;   /* (num_anchors, 4) contiguous xyxy; NULL => `deltas` already holds decoded xyxy boxes  */
+  int64_t num_anchors;    /* Hi*Wi*A */
+  int64_t delta_stride_n, delta_stride_a, delta_stride_c;
+  int64_t score_stride_n, score_stride_a;
+} osr_rpn_level_t;
+
+/* Kmax = sum over levels of min(num_anchors, pre_nms_topk). */
+int64_t osr_rpn_kmax(const osr_rpn_level_t* h_levels, int num_levels, int pre_nms_topk);
+size_t osr_rpn_select_decode_workspace(const osr_rpn_level_t* h_levels, int num_levels, int num_images,
+                                       int pre_nms_topk);
+/*
+ * Outputs (all (N, Kmax)-padded, valid prefix per image):
+ *   out_boxes  (N, Kmax, 4) fp32  clipped boxes; per image = levels concatenated, each level score-descending,
+ *                                 ties by lower anchor index; non-finite and empty boxes compacted out
+ *   out_scores (N, Kmax)    fp32
+ *   out_level  (N, Kmax)    int32 FPN level id of each kept proposal
+ *   out_index  (N, Kmax)    int32 flat anchor index inside its level (test / debugging aid)
+ *   out_counts (N, L+2)     int32 [kept per level ..., kept total, flags]; flags bit0 = a selected box or score
+ *                                 was non-finite (the reference raises FloatingPointError when training)
+ * image_hw: (N, 2) int32 device array of un-padded (h, w)  (find_top_proposals.py:91,105).
+ */
+int osr_rpn_select_decode(const osr_rpn_level_t* h_levels, int num_levels, int num_images, int pre_nms_topk,
+                          float min_box_size, const int32_t* image_hw, float* out_boxes, float* out_scores,
+                          int32_t* out_level, int32_t* out_index, int32_t* out_counts, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) NMS
+ * Replaces detectron2.layers.batched_nms -> torchvision.ops.nms at
+ *   openset_rcnn/modeling/roi_heads/osrcnn_fast_rcnn.py:135, softmax_classifier.py:93 and :154,
+ *   and the nominal-mode site openset_rcnn/modeling/find_top_proposals.py:112.
+ * Segments are the units inside which suppression applies (image x category).  IoU arithmetic is
+ * the one of torchvision's CUDA kernel: inter / (fma(bw, bh, rn(aw*ah)) - inter) > (float)thr.
+ * ------------------------------------------------------------------------------------------ */
+size_t osr_nms_workspace(int64_t total_boxes, int num_segments, int max_segment_len);
+/*
+ *   boxes (T,4), scores (T), seg_offsets (S+1) int32 device (segment s = [seg_offsets[s], seg_offsets[s+1]))
+ *   max_segment_len: host-side upper bound on any segment length (<= 16384)
+ *   presorted != 0: every segment is already score-descending (stable) - the sort is skipped
+ *   keep_idx   (T) int64: for segment s, keep_idx[seg_offsets[s] + j], j < keep_counts[s], are the kept boxes as
+ *                         indices RELATIVE to the segment start, in score-descending (stable) order
+ *   keep_counts (S) int32
+ */
+int osr_nms_segmented(const float* boxes, const float* scores, const int32_t* seg_offsets, int num_segments,
+                      int max_segment_len, float iou_threshold, int presorted, int64_t* keep_idx,
+                      int32_t* keep_counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) FPN level assignment + multi-level ROIAlignV2 forward / backward
+ * Replaces detectron2 ROIPooler.forward (assign_boxes_to_levels + per-level torchvision roi_align,
+ * aligned=True) called at openset_rcnn/modeling/roi_heads/osrcnn_roi_heads.py:306 (built :108-113),
+ * and its autograd backward (train.py:145).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float* data;                 /* (N, C, H, W) logical; element (n,c,y,x) at data[n*sN + c*sC + y*sH + x*sW] */
+  int64_t sN, sC, sH, sW;      /* element strides: NCHW-contiguous or channels_last both accepted */
+  int32_t H, W;
+  float scale;                 /* 1/stride of the level */
+} osr_feat_level_t;
+
+/*
+ *   rois (M,5) fp32 [image index, x1, y1, x2, y2] (detectron2 convert_boxes_to_pooler_format)
+ *   out  (M, C, P, P) fp32, C-major (box_head.fc1 weight order)
+ *   out_level (M) int32 = clamp(floor(canonical_level + log2(sqrt(area)/canonical_box_size + 1e-8)), min, max) - min
+ *   sampling_ratio 0 = adaptive ceil(roi/P) grid; aligned must be 1 (ROIAlignV2)
+ */
+int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                      int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
+                      int min_level, float* out, int32_t* out_level, void* stream);
+
+size_t osr_roi_align_bwd_workspace(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int M);
+/*
+ *   grad_out (M, C, P, P); rois as above and image-major (all RoIs of image n are contiguous);
+ *   roi_batch_offsets (N+1) int32 device: RoIs of image n = [off[n], off[n+1])
+ *   h_grad_levels[l].data: dense (N,C,H,W) gradient, FULLY written (zeros where untouched); deterministic
+ *   (gather formulation, no atomics, fixed accumulation order).
+ */
+int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
+                      const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
+                      int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) PLN prototype loss (COS distance) forward / backward
+ * Replaces PLN.loss lines 134,137-187 of
+ *   openset_rcnn/modeling/roi_heads/prototype_learning_network.py
+ * (everything after the encoder nn.Linear) and its autograd backward (closed form).
+ * labels are already id-mapped: [0,K) = known class, anything else is ignored (line 146-151).
+ * r_norm = normaliser (the reference uses the number of sampled RoIs R, line 187);
+ * center_weight = 1 (reference) or world_size for the gathered multi-GPU variant.
+ * ------------------------------------------------------------------------------------------ */
+size_t osr_pln_workspace(int R, int D, int K, int reps_per_class);
+/*
+ * saved-for-backward outputs:
+ *   emb_inv_norm (R) fp32, rep_inv_norm (K*rpc) fp32,
+ *   intra_rep (R) int32: rep index of the own-class minimum if the intra hinge is active else -1
+ *   inter_rep (R) int32: rep index of the nearest other-class rep if the inter hinge is active else -1
+ *   center_rep (K*rpc) int32: nearest other-class rep if the separation hinge is active else -1
+ *   loss_terms (4) fp32: [loss, intra_sum, inter_sum, center_sum]
+ */
+int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, int R, int D,
+                     int K, int reps_per_class, float alpha, float beta, float loss_weight, float iou_threshold,
+                     float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
+                     float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/*
+ *   grad_loss (1) device fp32 (upstream gradient of the scalar loss)
+ *   grad_emb (R, D) fully written (zeros for non-foreground rows); grad_reps (K*rpc, D)
+ */
+int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels, const float* emb_inv_norm,
+                     const float* rep_inv_norm, const int32_t* intra_rep, const int32_t* inter_rep,
+                     const int32_t* center_rep, const float* grad_loss, int R, int D, int K, int reps_per_class,
+                     float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSR_H_ */
