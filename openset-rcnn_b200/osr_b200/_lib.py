@@ -89,11 +89,20 @@ def lib() -> C.CDLL:
                         "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
                 h = C.CDLL(LIB_PATH)
                 for name, (res, args) in SIGNATURES.items():
-                    fn = getattr(h, name)
+                    try:
+                        fn = getattr(h, name)
+                    except AttributeError:  # reported by missing_symbols(); calling it raises AttributeError
+                        continue
                     fn.restype = res
                     fn.argtypes = args
                 _lib = h
     return _lib
+
+
+def missing_symbols():
+    """Symbols declared in include/osr.h (SIGNATURES) that the built library does not export."""
+    h = lib()
+    return [name for name in SIGNATURES if not hasattr(h, name)]
 
 
 def check(rc: int, what: str) -> None:
