@@ -167,6 +167,15 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
                      float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * PLN.inference nearest-prototype classification (prototype_learning_network.py:203-226), all images at once:
+ *   pred[i] = class of the nearest prototype of normalize(emb[i]) (min over the reps of a class first),
+ *   mapped through class_id_map (K int64, may be NULL = identity; the reference's self.class_id for GraspNet),
+ *   or unknown_id when the minimum cosine distance is > unk_thr.  min_dist (R) fp32 is also returned.
+ */
+int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, float unk_thr,
+                    int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,500 @@
+// PLN prototype loss (cosine distance) forward + closed-form backward for sm_100a.
+// Replaces prototype_learning_network.py:134,137-187 (F.normalize x2, nonzero (host sync), index, mm, reshape/min,
+// two index_puts, K-iteration Python loop :179-180, three relu/sum chains) and its autograd graph.
+//
+// forward  pln_rows_kernel   : one warp per RoI row; non-foreground rows are skipped without reading emb.
+//                              Prototypes are normalised into shared memory once per CTA (K*D*4 <= 28 KB).
+//                              Per-CTA partial hinge sums go to the workspace (fixed order => deterministic).
+//          pln_final_kernel  : prototype-separation term (K x K, one CTA) + ordered sum of the partials.
+// backward pln_grad_emb_kernel   : one warp per row, d loss/d emb through the normalisation (zeros for inactive rows)
+//          pln_grad_reps_partial : grid (rep, row-segment): ordered compaction of the rows whose active hinge points
+//                                  at this prototype, then a fixed-order sum of their unit embeddings
+//          pln_grad_reps_final   : ordered sum over segments + separation-term gradient + projection.
+// No atomics anywhere: results are run-to-run bit-identical.
+#include "osr_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxD = 256;   // embedding dim handled: D == 256 fast layout (8 floats per lane), checked on host
+constexpr int kMaxReps = 64; // K * reps_per_class
+constexpr int kSeg = 8;      // row segments of the grad_reps partial reduction
+constexpr float kEps = 1e-12f;
+
+struct PlnParams {
+  const float* emb;
+  const float* reps;
+  const int64_t* labels;
+  const float* ious;
+  int R, D, K, rpc, Kr;
+  float alpha, beta, loss_weight, iou_thr, r_norm, center_weight;
+  // outputs / saved
+  float* loss_terms;
+  float* emb_inv_norm;
+  float* rep_inv_norm;
+  int32_t* intra_rep;
+  int32_t* inter_rep;
+  int32_t* center_rep;
+  // workspace
+  float* partial;      // fwd: (num_ctas, 2)   bwd: (kSeg, Kr, D)
+  int num_ctas;
+  // backward only
+  const float* grad_loss;
+  float* grad_emb;
+  float* grad_reps;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Normalise the prototypes into shared memory: rh[j][d] = r[j][d] / max(||r_j||, eps).  One warp per prototype.
+__device__ __forceinline__ void load_unit_reps(const PlnParams& p, float* rh, float* inv_norm_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < p.Kr; j += kWarps) {
+    float ss = 0.f;
+    for (int d = lane; d < p.D; d += 32) {
+      const float v = __ldg(p.reps + (int64_t)j * p.D + d);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), kEps);
+    for (int d = lane; d < p.D; d += 32) rh[j * p.D + d] = __ldg(p.reps + (int64_t)j * p.D + d) / denom;
+    if (inv_norm_out && lane == 0) inv_norm_out[j] = 1.0f / denom;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constant__ PlnParams p) {
+  extern __shared__ __align__(16) float rh[];  // (Kr, D)
+  __shared__ float s_part[kWarps][2];
+  load_unit_reps(p, rh, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float intra_sum = 0.f, inter_sum = 0.f;
+  const int rows_per_cta = osr::ceil_div(p.R, (int)gridDim.x);
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(p.R, row_begin + rows_per_cta);
+  for (int i = row_begin + warp; i < row_end; i += kWarps) {
+    const int64_t y = __ldg(p.labels + i);
+    const float iou = __ldg(p.ious + i);
+    const bool fg = (y >= 0) && (y < p.K) && (iou > p.iou_thr);   // :149-151 (strict >)
+    if (!fg) {
+      if (lane == 0) {
+        p.emb_inv_norm[i] = 0.f;
+        p.intra_rep[i] = -1;
+        p.inter_rep[i] = -1;
+      }
+      continue;
+    }
+    // unit embedding, 8 dims per lane (D == 256) or strided in general
+    float e[kMaxD / 32];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxD / 32; ++q) {
+      const int d = q * 32 + lane;
+      e[q] = (d < p.D) ? __ldg(p.emb + (int64_t)i * p.D + d) : 0.f;
+      ss = fmaf(e[q], e[q], ss);
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), kEps);
+#pragma unroll
+    for (int q = 0; q < kMaxD / 32; ++q) e[q] = e[q] / denom;
+    // distances to all prototypes; min over the reps of each class (:164)
+    float intra = 0.f, inter = 1000.f;   // sentinel 1000 as in :168
+    int intra_j = -1, inter_j = -1;
+    for (int c = 0; c < p.K; ++c) {
+      float best = 0.f;
+      int best_j = -1;
+      for (int r = 0; r < p.rpc; ++r) {
+        const int j = c * p.rpc + r;
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < kMaxD / 32; ++q) {
+          const int d = q * 32 + lane;
+          if (d < p.D) dot = fmaf(e[q], rh[j * p.D + d], dot);
+        }
+        dot = warp_sum(dot);
+        const float dist = 1.0f - dot;
+        if (best_j < 0 || dist < best) {
+          best = dist;
+          best_j = j;
+        }
+      }
+      if (c == (int)y) {
+        intra = best;
+        intra_j = best_j;
+      } else if (best < inter) {
+        inter = best;
+        inter_j = best_j;
+      }
+    }
+    const bool intra_on = (intra - p.alpha) > 0.f;
+    const bool inter_on = (p.beta - inter) > 0.f;
+    if (intra_on) intra_sum += intra - p.alpha;
+    if (inter_on) inter_sum += p.beta - inter;
+    if (lane == 0) {
+      p.emb_inv_norm[i] = 1.0f / denom;
+      p.intra_rep[i] = intra_on ? intra_j : -1;
+      p.inter_rep[i] = inter_on ? inter_j : -1;
+    }
+  }
+  if (lane == 0) {
+    s_part[warp][0] = intra_sum;
+    s_part[warp][1] = inter_sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < kWarps; ++w) {
+      a += s_part[w][0];
+      b += s_part[w][1];
+    }
+    p.partial[2 * blockIdx.x] = a;
+    p.partial[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// prototype-separation term (:171-181) + final ordered reduction (:183-187)
+__global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_constant__ PlnParams p) {
+  extern __shared__ __align__(16) float rh[];
+  __shared__ float s_c[kMaxReps];
+  load_unit_reps(p, rh, p.rep_inv_norm);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < p.Kr; k += kWarps) {
+    float best = 1000.f;
+    int best_j = -1;
+    for (int j = 0; j < p.Kr; ++j) {
+      if (j / p.rpc == k / p.rpc) continue;  // own-class block masked with 1000 (:179-180)
+      float dot = 0.f;
+      for (int d = lane; d < p.D; d += 32) dot = fmaf(rh[k * p.D + d], rh[j * p.D + d], dot);
+      dot = warp_sum(dot);
+      const float dist = 1.0f - dot;
+      if (dist < best) {
+        best = dist;
+        best_j = j;
+      }
+    }
+    const float h = (p.beta + p.alpha) - best;
+    if (lane == 0) {
+      s_c[k] = h > 0.f ? h : 0.f;
+      p.center_rep[k] = (h > 0.f) ? best_j : -1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = 0; i < p.num_ctas; ++i) {
+      a += p.partial[2 * i];
+      b += p.partial[2 * i + 1];
+    }
+    for (int k = 0; k < p.Kr; ++k) c += s_c[k];
+    const float denom = fmaxf(p.r_norm, 1.0f);
+    p.loss_terms[0] = (a + b + p.center_weight * c) * p.loss_weight / denom;
+    p.loss_terms[1] = a;
+    p.loss_terms[2] = b;
+    p.loss_terms[3] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(kThreads) pln_grad_emb_kernel(const __grid_constant__ PlnParams p) {
+  extern __shared__ __align__(16) float rh[];
+  load_unit_reps(p, rh, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float s = __ldg(p.grad_loss) * p.loss_weight / fmaxf(p.r_norm, 1.0f);
+  for (int i = blockIdx.x * kWarps + warp; i < p.R; i += gridDim.x * kWarps) {
+    const int ja = p.intra_rep[i], jb = p.inter_rep[i];
+    float* go = p.grad_emb + (int64_t)i * p.D;
+    if (ja < 0 && jb < 0) {
+      for (int d = lane; d < p.D; d += 32) go[d] = 0.f;
+      continue;
+    }
+    const float inv = p.emb_inv_norm[i];
+    float eh[kMaxD / 32], g[kMaxD / 32];
+    float dot = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxD / 32; ++q) {
+      const int d = q * 32 + lane;
+      eh[q] = 0.f; g[q] = 0.f;
+      if (d < p.D) {
+        eh[q] = __ldg(p.emb + (int64_t)i * p.D + d) * inv;
+        float t = 0.f;
+        if (ja >= 0) t -= rh[ja * p.D + d];   // d/dS of relu(d_y - alpha) = -1, dS/de_hat = r_hat
+        if (jb >= 0) t += rh[jb * p.D + d];   // d/dS of relu(beta - d_c*) = +1
+        g[q] = t;
+        dot = fmaf(eh[q], t, dot);
+      }
+    }
+    dot = warp_sum(dot);
+    const float f = s * inv;
+#pragma unroll
+    for (int q = 0; q < kMaxD / 32; ++q) {
+      const int d = q * 32 + lane;
+      if (d < p.D) go[d] = f * (g[q] - eh[q] * dot);
+    }
+  }
+}
+
+// grid (Kr, kSeg): partial[seg][j][:] = sum over rows of segment seg (in row order) of G[i][j] * e_hat_i
+__global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_constant__ PlnParams p) {
+  __shared__ int s_rows[2048];       // |row+1| with sign = sign of G; segment length <= 2048 enforced by the host loop
+  __shared__ int s_wcnt[kWarps + 1];
+  const int j = blockIdx.x, seg = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg_len = osr::ceil_div(p.R, kSeg);
+  const int r0 = seg * seg_len, r1 = min(p.R, r0 + seg_len);
+  float acc[kMaxD / kThreads > 0 ? kMaxD / kThreads : 1] = {0.f};
+  for (int base = r0; base < r1; base += 2048) {
+    // ordered compaction of matching rows of [base, base+2048): each thread owns 8 consecutive rows
+    int code[8], cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = base + tid * 8 + k;
+      code[k] = 0;
+      if (i < r1) {
+        const int ja = p.intra_rep[i], jb = p.inter_rep[i];
+        // a row can point at j through only one of the two hinges (own class vs other class)
+        if (ja == j) code[k] = -(i + 1);
+        else if (jb == j) code[k] = (i + 1);
+      }
+      cnt += code[k] != 0;
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wcnt[warp] = inc;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int w = 0; w < kWarps; ++w) {
+        int c = s_wcnt[w];
+        s_wcnt[w] = run;
+        run += c;
+      }
+      s_wcnt[kWarps] = run;
+    }
+    __syncthreads();
+    int pos = s_wcnt[warp] + inc - cnt;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (code[k] != 0) s_rows[pos++] = code[k];
+    __syncthreads();
+    const int n = s_wcnt[kWarps];
+    for (int q = 0; q < n; ++q) {
+      const int c = s_rows[q];
+      const int i = (c < 0 ? -c : c) - 1;
+      const float sg = c < 0 ? -1.f : 1.f;
+      const float inv = p.emb_inv_norm[i] * sg;
+      if (tid < p.D) acc[0] = fmaf(__ldg(p.emb + (int64_t)i * p.D + tid), inv, acc[0]);
+    }
+    __syncthreads();
+  }
+  if (tid < p.D) p.partial[((int64_t)seg * p.Kr + j) * p.D + tid] = acc[0];
+}
+
+__global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_constant__ PlnParams p) {
+  extern __shared__ __align__(16) float rh[];
+  __shared__ float s_red[kWarps];
+  load_unit_reps(p, rh, nullptr);
+  __syncthreads();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float s = __ldg(p.grad_loss) * p.loss_weight / fmaxf(p.r_norm, 1.0f);
+  for (int j = 0; j < p.Kr; ++j) {
+    float g = 0.f;
+    if (tid < p.D) {
+      for (int seg = 0; seg < kSeg; ++seg) g += p.partial[((int64_t)seg * p.Kr + j) * p.D + tid];
+      // separation term: (Gamma + Gamma^T) r_hat, Gamma[k][j*_k] = center_weight * [hinge active]
+      const int js = p.center_rep[j];
+      if (js >= 0) g = fmaf(p.center_weight, rh[js * p.D + tid], g);
+      for (int k = 0; k < p.Kr; ++k)
+        if (p.center_rep[k] == j) g = fmaf(p.center_weight, rh[k * p.D + tid], g);
+    }
+    float dot = (tid < p.D) ? rh[j * p.D + tid] * g : 0.f;
+    dot = warp_sum(dot);
+    if (lane == 0) s_red[warp] = dot;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < kWarps; ++w) tot += s_red[w];
+    if (tid < p.D) p.grad_reps[(int64_t)j * p.D + tid] = s * p.rep_inv_norm[j] * (g - rh[j * p.D + tid] * tot);
+    __syncthreads();
+  }
+}
+
+struct NearestParams {
+  PlnParams base;
+  float unk_thr;
+  int64_t unknown_id;
+  const int64_t* class_id_map;
+  int64_t* pred;
+  float* min_dist;
+};
+
+// PLN.inference: nearest prototype + unknown threshold, one warp per row
+__global__ void __launch_bounds__(kThreads) pln_nearest_kernel(const __grid_constant__ NearestParams q) {
+  extern __shared__ __align__(16) float rh[];
+  const PlnParams& p = q.base;
+  load_unit_reps(p, rh, nullptr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = blockIdx.x * kWarps + warp; i < p.R; i += gridDim.x * kWarps) {
+    float e[kMaxD / 32];
+    float ss = 0.f;
+#pragma unroll
+    for (int t = 0; t < kMaxD / 32; ++t) {
+      const int d = t * 32 + lane;
+      e[t] = (d < p.D) ? __ldg(p.emb + (int64_t)i * p.D + d) : 0.f;
+      ss = fmaf(e[t], e[t], ss);
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), kEps);
+#pragma unroll
+    for (int t = 0; t < kMaxD / 32; ++t) e[t] = e[t] / denom;
+    float best = 0.f;
+    int best_c = -1;
+    for (int c = 0; c < p.K; ++c) {
+      for (int r = 0; r < p.rpc; ++r) {
+        const int j = c * p.rpc + r;
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < kMaxD / 32; ++t) {
+          const int d = t * 32 + lane;
+          if (d < p.D) dot = fmaf(e[t], rh[j * p.D + d], dot);
+        }
+        dot = warp_sum(dot);
+        const float dist = 1.0f - dot;
+        if (best_c < 0 || dist < best) {
+          best = dist;
+          best_c = c;
+        }
+      }
+    }
+    if (lane == 0) {
+      int64_t cls = q.class_id_map ? q.class_id_map[best_c] : (int64_t)best_c;
+      if (best > q.unk_thr) cls = q.unknown_id;
+      q.pred[i] = cls;
+      q.min_dist[i] = best;
+    }
+  }
+}
+
+int check_shape(int R, int D, int K, int rpc) {
+  if (R < 0 || D <= 0 || K <= 0 || rpc <= 0) return osr::fail_arg(OSR_E_ARG, "pln: bad R/D/K/reps_per_class");
+  if (D > kMaxD) return osr::fail_arg(OSR_E_SHAPE, "pln: embedding dim %d > %d unsupported", D, kMaxD);
+  if (K * rpc > kMaxReps) return osr::fail_arg(OSR_E_SHAPE, "pln: K*reps_per_class=%d > %d unsupported", K * rpc, kMaxReps);
+  return 0;
+}
+
+int fwd_ctas(int R) { return R < 8 * kWarps ? 1 : (R / (8 * kWarps) > 592 ? 592 : R / (8 * kWarps)); }
+
+}  // namespace
+
+extern "C" {
+
+size_t osr_pln_workspace(int R, int D, int K, int reps_per_class) {
+  const size_t fwd = (size_t)fwd_ctas(R > 0 ? R : 1) * 2 * sizeof(float);
+  const size_t bwd = (size_t)kSeg * K * reps_per_class * D * sizeof(float);
+  return osr::align256(fwd > bwd ? fwd : bwd);
+}
+
+int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, int R, int D,
+                     int K, int reps_per_class, float alpha, float beta, float loss_weight, float iou_threshold,
+                     float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
+                     float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shape(R, D, K, reps_per_class);
+  if (rc) return rc;
+  if (!reps || !loss_terms || !rep_inv_norm || !center_rep || !workspace ||
+      (R > 0 && (!emb || !labels || !ious || !emb_inv_norm || !intra_rep || !inter_rep)))
+    return osr::fail_arg(OSR_E_ARG, "pln_loss_fwd: null pointer argument");
+  if (workspace_bytes < osr_pln_workspace(R, D, K, reps_per_class))
+    return osr::fail_arg(OSR_E_WORKSPACE, "pln_loss_fwd: workspace too small");
+  PlnParams p{};
+  p.emb = emb; p.reps = reps; p.labels = labels; p.ious = ious;
+  p.R = R; p.D = D; p.K = K; p.rpc = reps_per_class; p.Kr = K * reps_per_class;
+  p.alpha = alpha; p.beta = beta; p.loss_weight = loss_weight; p.iou_thr = iou_threshold;
+  p.r_norm = r_norm; p.center_weight = center_weight;
+  p.loss_terms = loss_terms; p.emb_inv_norm = emb_inv_norm; p.rep_inv_norm = rep_inv_norm;
+  p.intra_rep = intra_rep; p.inter_rep = inter_rep; p.center_rep = center_rep;
+  p.partial = static_cast<float*>(workspace);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)p.Kr * D * sizeof(float);
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.num_ctas = 0;
+  if (R > 0) {
+    p.num_ctas = fwd_ctas(R);
+    pln_rows_kernel<<<p.num_ctas, kThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+  }
+  pln_final_kernel<<<1, kThreads, smem, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  return 0;
+}
+
+int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels, const float* emb_inv_norm,
+                     const float* rep_inv_norm, const int32_t* intra_rep, const int32_t* inter_rep,
+                     const int32_t* center_rep, const float* grad_loss, int R, int D, int K, int reps_per_class,
+                     float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  (void)labels;
+  int rc = check_shape(R, D, K, reps_per_class);
+  if (rc) return rc;
+  if (!reps || !rep_inv_norm || !center_rep || !grad_loss || !grad_reps || !workspace ||
+      (R > 0 && (!emb || !emb_inv_norm || !intra_rep || !inter_rep || !grad_emb)))
+    return osr::fail_arg(OSR_E_ARG, "pln_loss_bwd: null pointer argument");
+  if (workspace_bytes < osr_pln_workspace(R, D, K, reps_per_class))
+    return osr::fail_arg(OSR_E_WORKSPACE, "pln_loss_bwd: workspace too small");
+  PlnParams p{};
+  p.emb = emb; p.reps = reps;
+  p.R = R; p.D = D; p.K = K; p.rpc = reps_per_class; p.Kr = K * reps_per_class;
+  p.loss_weight = loss_weight; p.r_norm = r_norm; p.center_weight = center_weight;
+  p.emb_inv_norm = const_cast<float*>(emb_inv_norm); p.rep_inv_norm = const_cast<float*>(rep_inv_norm);
+  p.intra_rep = const_cast<int32_t*>(intra_rep); p.inter_rep = const_cast<int32_t*>(inter_rep);
+  p.center_rep = const_cast<int32_t*>(center_rep);
+  p.grad_loss = grad_loss; p.grad_emb = grad_emb; p.grad_reps = grad_reps;
+  p.partial = static_cast<float*>(workspace);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)p.Kr * D * sizeof(float);
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_emb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (R > 0) {
+    int ctas = osr::ceil_div(R, kWarps * 4);
+    if (ctas > 592) ctas = 592;
+    pln_grad_emb_kernel<<<ctas, kThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+  }
+  pln_grad_reps_partial<<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  pln_grad_reps_final<<<1, kThreads, smem, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  return 0;
+}
+
+int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, float unk_thr,
+                    int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist, void* stream) {
+  int rc = check_shape(R, D, K, reps_per_class);
+  if (rc) return rc;
+  if (R == 0) return 0;
+  if (!emb || !reps || !pred || !min_dist) return osr::fail_arg(OSR_E_ARG, "pln_nearest: null pointer argument");
+  NearestParams q{};
+  q.base.emb = emb; q.base.reps = reps;
+  q.base.R = R; q.base.D = D; q.base.K = K; q.base.rpc = reps_per_class; q.base.Kr = K * reps_per_class;
+  q.unk_thr = unk_thr; q.unknown_id = unknown_id; q.class_id_map = class_id_map; q.pred = pred; q.min_dist = min_dist;
+  const size_t smem = (size_t)q.base.Kr * D * sizeof(float);
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas = osr::ceil_div(R, kWarps * 4);
+  if (ctas > 592) ctas = 592;
+  pln_nearest_kernel<<<ctas, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  OSR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

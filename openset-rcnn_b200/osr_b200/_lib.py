@@ -67,6 +67,9 @@ SIGNATURES = {
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "osr_pln_nearest": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,0 +1,124 @@
+"""GPU parity: PLN loss fwd/bwd + inference kernels vs the oracle (torch ops, fp32).
+Tolerances: loss rtol 1e-5 (fp32 dot products in a different summation order); gradients compared on all rows
+with atol 1e-7 (entries are O(1e-4)) excluding rows whose hinge margin is within 1e-5 of a threshold (a flipped
+hinge is a discontinuity of the gradient, not an error)."""
+import pytest
+import torch
+
+from oracle import pln as opln
+
+pytestmark = pytest.mark.gpu
+
+
+def _kw(K=20, alpha=0.1, beta=0.9, w=0.5):
+    return dict(num_known_classes=K, alpha=alpha, beta=beta, loss_weight=w, iou_threshold=0.5)
+
+
+def _margin_mask(emb, reps, labels, ious, K, alpha, beta):
+    eh = torch.nn.functional.normalize(emb); rh = torch.nn.functional.normalize(reps)
+    d = 1 - eh @ rh.t()
+    fg = (labels >= 0) & (labels < K) & (ious > 0.5)
+    y = labels.clamp(0, K - 1)
+    intra = d.gather(1, y[:, None])[:, 0]
+    dm = d.clone(); dm.scatter_(1, y[:, None], 1000.0)
+    inter = dm.min(1)[0]
+    safe = ((intra - alpha).abs() > 1e-5) & ((beta - inter).abs() > 1e-5)
+    return safe | ~fg
+
+
+@pytest.mark.parametrize("R,K,alpha,beta,w", [(8192, 20, 0.1, 0.9, 0.5), (4096, 28, 0.05, 0.95, 2.0), (37, 20, 0.1, 0.9, 0.5)])
+def test_loss_and_gradients_match_oracle(R, K, alpha, beta, w):
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb
+    pi = synth.make_pln_inputs(R, num_known=K, num_classes=81 if K == 20 else 88, seed=R, device="cuda:0")
+    emb0 = (pi.roi_features @ pi.enc_w.t()).detach()
+    kw = _kw(K, alpha, beta, w)
+    emb_a = emb0.clone().requires_grad_(True); reps_a = pi.reps.clone().requires_grad_(True)
+    la = pln_loss_from_emb(emb_a, reps_a, pi.gt_classes, pi.ious, **kw)
+    (la * 1.7).backward()
+    emb_b = emb0.clone().requires_grad_(True); reps_b = pi.reps.clone().requires_grad_(True)
+    lb = opln.pln_loss_from_emb(emb_b, reps_b, pi.gt_classes, pi.ious, **kw)
+    (lb * 1.7).backward()
+    torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-7)
+    safe = _margin_mask(emb0, pi.reps, pi.gt_classes, pi.ious, K, alpha, beta)
+    assert safe.float().mean() > 0.99
+    torch.testing.assert_close(emb_a.grad[safe], emb_b.grad[safe], rtol=1e-4, atol=1e-7)
+    if bool(safe.all()):
+        torch.testing.assert_close(reps_a.grad, reps_b.grad, rtol=1e-4, atol=1e-6)
+    # CPU oracle too
+    lc = opln.pln_loss_from_emb(emb0.cpu(), pi.reps.cpu(), pi.gt_classes.cpu(), pi.ious.cpu(), **kw)
+    torch.testing.assert_close(la.cpu(), lc, rtol=1e-5, atol=1e-7)
+
+
+def test_no_foreground_rows_only_center_term():
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb
+    pi = synth.make_pln_inputs(64, seed=2, device="cuda:0")
+    labels = torch.full((64,), 81, dtype=torch.int64, device="cuda:0")
+    emb = (pi.roi_features @ pi.enc_w.t()).requires_grad_(True)
+    reps = pi.reps.clone().requires_grad_(True)
+    la = pln_loss_from_emb(emb, reps, labels, pi.ious, **_kw())
+    la.backward()
+    lb = opln.pln_loss_from_emb(emb.detach(), pi.reps, labels, pi.ious, **_kw())
+    torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-8)
+    assert float(emb.grad.abs().max()) == 0.0
+
+
+def test_deterministic():
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb
+    pi = synth.make_pln_inputs(4096, seed=6, device="cuda:0")
+    emb0 = (pi.roi_features @ pi.enc_w.t()).detach()
+    outs = []
+    for _ in range(2):
+        e = emb0.clone().requires_grad_(True); r = pi.reps.clone().requires_grad_(True)
+        l = pln_loss_from_emb(e, r, pi.gt_classes, pi.ious, **_kw())
+        l.backward()
+        outs.append((l.detach().clone(), e.grad.clone(), r.grad.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+def test_module_loss_matches_reference_formulation():
+    from osr_b200 import synth
+    from osr_b200.pln import PLN
+    from osr_b200.structures import Instances
+    torch.manual_seed(0)
+    m = PLN(81, 20, 1024, 256, "COS", 1, 0.1, 0.9, 0.5, opendet_benchmark=True)
+    pi = synth.make_pln_inputs(1024, seed=8, device="cuda:0")
+    props = []
+    for i in range(2):
+        inst = Instances((800, 1333))
+        inst.gt_classes = pi.gt_classes[i * 512:(i + 1) * 512]
+        inst.ious = pi.ious[i * 512:(i + 1) * 512]
+        props.append(inst)
+    emb, rec, loss = m.loss(pi.roi_features, props)
+    e2, r2, l2 = opln.pln_loss(pi.roi_features, m.encoder.weight, m.encoder.bias, m.decoder.weight, m.decoder.bias,
+                               m.representatives, pi.gt_classes, pi.ious, **_kw())
+    torch.testing.assert_close(emb, e2); torch.testing.assert_close(rec, r2)
+    torch.testing.assert_close(loss, l2, rtol=1e-5, atol=1e-7)
+    loss.backward()
+    assert m.encoder.weight.grad is not None and m.representatives.grad is not None
+    assert set(dict(m.named_parameters())) == {"encoder.weight", "encoder.bias", "decoder.weight", "decoder.bias",
+                                               "representatives"}
+
+
+def test_inference_matches_oracle():
+    from osr_b200 import synth
+    from osr_b200.pln import PLN
+    from osr_b200.structures import Instances
+    torch.manual_seed(1)
+    m = PLN(81, 20, 1024, 256, "COS", 1, 0.1, 0.9, 0.5, unk_thr=0.93, opendet_benchmark=True)
+    pi = synth.make_pln_inputs(300, seed=9, device="cuda:0")
+    insts = []
+    for a, b in ((0, 100), (100, 100), (100, 300)):
+        inst = Instances((800, 1333)); inst.features = pi.roi_features[a:b]; insts.append(inst)
+    with torch.no_grad():
+        out = m.inference(insts)
+        for inst, (a, b) in zip(out, ((0, 100), (100, 100), (100, 300))):
+            rec, pred = opln.pln_inference(pi.roi_features[a:b], m.encoder.weight, m.encoder.bias, m.decoder.weight,
+                                           m.decoder.bias, m.representatives, num_known_classes=20, unk_thr=0.93,
+                                           unknown_id=80)
+            assert torch.equal(inst.pred_classes, pred)
+            torch.testing.assert_close(inst.features, rec)
+        assert any((o.pred_classes == 80).any() for o in out if len(o)) and any((o.pred_classes < 20).any() for o in out if len(o))
