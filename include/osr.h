@@ -88,16 +88,20 @@ int osr_rpn_select_decode(const osr_rpn_level_t* h_levels, int num_levels, int n
  * ------------------------------------------------------------------------------------------ */
 size_t osr_nms_workspace(int64_t total_boxes, int num_segments, int max_segment_len);
 /*
- *   boxes (T,4), scores (T), seg_offsets (S+1) int32 device (segment s = [seg_offsets[s], seg_offsets[s+1]))
- *   max_segment_len: host-side upper bound on any segment length (<= 16384)
+ *   boxes (T,4) fp32 xyxy, scores (T) fp32, total_boxes = T (the same T given to osr_nms_workspace)
+ *   seg_begin (S), seg_len (S) int32 DEVICE arrays: segment s = boxes[seg_begin[s] : seg_begin[s] + seg_len[s]]
+ *       (device-resident so that counts produced by osr_rpn_select_decode never visit the host)
+ *   max_segment_len: host-side upper bound on any seg_len (in-kernel sort: <= 16384; presorted: <= 65536)
  *   presorted != 0: every segment is already score-descending (stable) - the sort is skipped
- *   keep_idx   (T) int64: for segment s, keep_idx[seg_offsets[s] + j], j < keep_counts[s], are the kept boxes as
- *                         indices RELATIVE to the segment start, in score-descending (stable) order
+ *   keep_idx   (T) int64: keep_idx[seg_begin[s] + j], j < keep_counts[s] = kept boxes of segment s as indices
+ *                         RELATIVE to seg_begin[s], in score-descending (stable: ties by lower index) order
  *   keep_counts (S) int32
+ *   keep_mask  (T) uint8 or NULL: 1 for kept boxes (indexed like boxes), 0 for suppressed ones inside segments
  */
-int osr_nms_segmented(const float* boxes, const float* scores, const int32_t* seg_offsets, int num_segments,
-                      int max_segment_len, float iou_threshold, int presorted, int64_t* keep_idx,
-                      int32_t* keep_counts, void* workspace, size_t workspace_bytes, void* stream);
+int osr_nms_segmented(const float* boxes, const float* scores, int64_t total_boxes, const int32_t* seg_begin,
+                      const int32_t* seg_len, int num_segments, int max_segment_len, float iou_threshold,
+                      int presorted, int64_t* keep_idx, int32_t* keep_counts, uint8_t* keep_mask, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) FPN level assignment + multi-level ROIAlignV2 forward / backward

@@ -34,6 +34,7 @@ class RpnSelection:
     counts: torch.Tensor   # (N, L+2)     int32 [per level..., total, flags]
     num_levels: int
     kmax: int
+    max_level_k: int = 0  # largest per-level k (host-side bound for the NMS workspace)
 
 
 def _tensor_of(x) -> torch.Tensor:
@@ -102,7 +103,8 @@ def rpn_select_decode(
                                    boxes.data_ptr(), sc.data_ptr(), lvl.data_ptr(), idx.data_ptr(),
                                    counts.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
     _lib.check(rc, "osr_rpn_select_decode")
-    return RpnSelection(boxes, sc, lvl, idx, counts, L, kmax)
+    max_level_k = max(min(int(d.shape[1]), int(pre_nms_topk)) for d in deltas)
+    return RpnSelection(boxes, sc, lvl, idx, counts, L, kmax, max_level_k)
 
 
 def _to_instances(sel: RpnSelection, image_sizes, training: bool, keep=None, keep_counts=None) -> List[Instances]:

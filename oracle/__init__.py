@@ -27,4 +27,4 @@ committed under ``tests/golden/`` with the generating script, and (2) the
 closed-form vectors of SURVEY.md Appendix C.
 """
 
-from . import structures, rpn, nms, roi_align, pln, bytes_model  # noqa: F401
+from . import structures, rpn, nms, roi_align, pln, bytes_model, pipeline  # noqa: F401
