@@ -122,9 +122,13 @@ typedef struct {
  *   out_level (M) int32 = clamp(floor(canonical_level + log2(sqrt(area)/canonical_box_size + 1e-8)), min, max) - min
  *   sampling_ratio 0 = adaptive ceil(roi/P) grid; aligned must be 1 (ROIAlignV2)
  */
+size_t osr_roi_align_fwd_workspace(int M);
+/* workspace (optional, may be NULL): lets the library order the RoIs by (image, level, y band) so that concurrently
+ * processed RoIs share feature rows in L2; results do not depend on it. */
 int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
                       int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
-                      int min_level, float* out, int32_t* out_level, void* stream);
+                      int min_level, float* out, int32_t* out_level, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 size_t osr_roi_align_bwd_workspace(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int M);
 /*

@@ -24,7 +24,9 @@ using namespace osr;
 constexpr int kTH = 16, kTW = 16;       // tile
 constexpr int kThreads = kTH * kTW;     // one thread per tile pixel
 constexpr int kCC = 16;                 // channels accumulated in registers per pass
-constexpr int kNB = 64;                 // RoIs whose tables are resident in shared memory at once
+constexpr int kNB = 32;                 // RoIs whose tables are resident in shared memory at once
+constexpr int kG = 4;                   // RoIs whose grad_out chunk is staged per pipeline stage
+constexpr int kBlk = kCC * kP * kP;     // floats of one (RoI, channel-chunk) block of grad_out = 784 (16-byte multiple)
 constexpr int kWin = 4 * kThreads;      // RoI indices scanned per batch (4 per thread, in order)
 
 struct RoiInfo {
@@ -106,6 +108,7 @@ struct BatchEntry {
 };
 
 struct __align__(16) BwdSmem {
+  float sg[2][kG][kBlk];  // double-buffered staging of grad_out[(roi, c0 .. c0+kCC), 7, 7]
   float wy[kNB][kTH * kP];
   float wx[kNB][kTW * kP];
   uchar2 yi[kNB][kTH];  // (first bin, number of bins) with non-zero weight for each tile row
@@ -114,6 +117,14 @@ struct __align__(16) BwdSmem {
   int warp_cnt[kThreads / 32 + 1];
   int nb, next_pos;
 };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // Scan RoI indices [pos, min(pos + kWin, r1)) in order, keep up to kNB that hit the tile; returns count in S.nb and
 // the next scan position in S.next_pos.
@@ -202,6 +213,50 @@ __device__ __forceinline__ void build_tables(const BwdParams& p, BwdSmem& S, con
   __syncthreads();
 }
 
+// stage grad_out blocks of RoIs [j0, min(j0 + kG, nb)) for channels [c0, c0 + kCC) into S.sg[buf] (async)
+__device__ __forceinline__ void stage_group(const BwdParams& p, BwdSmem& S, int buf, int j0, int nb, int c0, int C,
+                                            bool vec_ok) {
+  const int tid = threadIdx.x;
+  const int nj = min(kG, nb - j0);
+  const int cc = min(kCC, C - c0);
+  if (vec_ok && cc == kCC) {
+    for (int q = tid; q < nj * (kBlk / 4); q += kThreads) {
+      const int jj = q / (kBlk / 4), v = q - jj * (kBlk / 4);
+      const float* src = p.grad_out + ((int64_t)S.e[j0 + jj].m * C + c0) * (kP * kP) + v * 4;
+      cp_async16(&S.sg[buf][jj][v * 4], src);
+    }
+  } else {
+    for (int q = tid; q < nj * kBlk; q += kThreads) {
+      const int jj = q / kBlk, v = q - jj * kBlk;
+      S.sg[buf][jj][v] = (v < cc * kP * kP) ? __ldg(p.grad_out + ((int64_t)S.e[j0 + jj].m * C + c0) * (kP * kP) + v) : 0.f;
+    }
+  }
+  cp_async_commit();
+}
+
+// accumulate the contributions of staged RoIs [j0, j0 + nj) to this thread's pixel, kCC channels
+__device__ __forceinline__ void accumulate_group(const BwdSmem& S, int buf, int j0, int nj, int ty, int tx, float* acc) {
+  for (int jj = 0; jj < nj; ++jj) {
+    const int j = j0 + jj;
+    const uchar2 yi = S.yi[j][ty];
+    const uchar2 xi = S.xi[j][tx];
+    if (yi.y == 0 || xi.y == 0) continue;
+    const float ic = S.e[j].inv_count;
+    const float* g = S.sg[buf][jj];
+    for (int a = 0; a < yi.y; ++a) {
+      const int ph = yi.x + a;
+      const float wy = S.wy[j][ty * kP + ph] * ic;
+      for (int b = 0; b < xi.y; ++b) {
+        const int pw = xi.x + b;
+        const float w = wy * S.wx[j][tx * kP + pw];
+        const float* gp = g + ph * kP + pw;
+#pragma unroll
+        for (int c = 0; c < kCC; ++c) acc[c] = fmaf(w, gp[c * (kP * kP)], acc[c]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -223,12 +278,55 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid
 
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   const int C = p.L.C;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.grad_out) & 15) == 0) && ((C * kP * kP) % 4 == 0);
 
   // first batch; if it covers the whole image's RoI range the tables are built once and reused by every channel pass
   collect_batch(p, S, level, tx0, ty0, r0, r1);
   const bool single = (S.next_pos >= r1);
   if (S.nb > 0) build_tables(p, S, lv, tx0, ty0);
 
+  if (single) {
+    const int nb = S.nb;
+    const int nchunks = ceil_div(C, kCC);
+    if (nb == 0) {  // untouched tile: zero fill
+      if (inside)
+        for (int c = 0; c < C; ++c) gpix[(int64_t)c * lv.sC] = 0.f;
+      return;
+    }
+    const int ngroups = ceil_div(nb, kG);
+    const int total = nchunks * ngroups;
+    float acc[kCC];
+    stage_group(p, S, 0, 0, nb, 0, C, vec_ok);
+    int chunk = 0, grp = 0;
+    for (int st = 0; st < total; ++st) {
+      if (st + 1 < total) {  // prefetch the next (chunk, group) while this one is consumed
+        int nc = chunk, ng = grp + 1;
+        if (ng == ngroups) { ng = 0; ++nc; }
+        stage_group(p, S, (st + 1) & 1, ng * kG, nb, nc * kCC, C, vec_ok);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (grp == 0) {
+#pragma unroll
+        for (int c = 0; c < kCC; ++c) acc[c] = 0.f;
+      }
+      accumulate_group(S, st & 1, grp * kG, min(kG, nb - grp * kG), ty, tx, acc);
+      if (grp == ngroups - 1 && inside) {
+        const int c0 = chunk * kCC;
+#pragma unroll
+        for (int c = 0; c < kCC; ++c)
+          if (c0 + c < C) gpix[(int64_t)(c0 + c) * lv.sC] = acc[c];
+      }
+      __syncthreads();
+      if (++grp == ngroups) { grp = 0; ++chunk; }
+    }
+    return;
+  }
+
+  // dense tile (more RoIs than the resident tables hold, or > kWin RoIs in the image): batches are re-collected for
+  // every channel pass; staging is not overlapped.  Correct for any density, fast enough for the rare case.
   for (int c0 = 0; c0 < C; c0 += kCC) {
     float acc[kCC];
 #pragma unroll
@@ -236,42 +334,30 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid
     int pos = r0;
     bool first = true;
     while (true) {
-      if (!(single || (first && c0 == 0))) {  // tables not resident: (re)collect this batch
+      if (!(first && c0 == 0)) {
         collect_batch(p, S, level, tx0, ty0, pos, r1);
         if (S.nb > 0) build_tables(p, S, lv, tx0, ty0);
       }
       first = false;
       const int nb = S.nb;
       const int next = S.next_pos;
-      for (int j = 0; j < nb; ++j) {
-        const uchar2 yi = S.yi[j][ty];
-        const uchar2 xi = S.xi[j][tx];
-        if (yi.y == 0 || xi.y == 0) continue;
-        const float ic = S.e[j].inv_count;
-        const float* g = p.grad_out + ((int64_t)S.e[j].m * C + c0) * (kP * kP);
-        for (int a = 0; a < yi.y; ++a) {
-          const int ph = yi.x + a;
-          const float wy = S.wy[j][ty * kP + ph] * ic;
-          for (int b = 0; b < xi.y; ++b) {
-            const int pw = xi.x + b;
-            const float w = wy * S.wx[j][tx * kP + pw];
-            const float* gp = g + ph * kP + pw;
-#pragma unroll
-            for (int c = 0; c < kCC; ++c)
-              if (c0 + c < C) acc[c] = fmaf(w, __ldg(gp + c * (kP * kP)), acc[c]);
-          }
-        }
+      for (int j0 = 0; j0 < nb; j0 += kG) {
+        stage_group(p, S, 0, j0, nb, c0, C, vec_ok);
+        cp_async_wait<0>();
+        __syncthreads();
+        accumulate_group(S, 0, j0, min(kG, nb - j0), ty, tx, acc);
+        __syncthreads();
       }
-      if (single || next >= r1) break;
+      if (next >= r1) break;
       pos = next;
-      __syncthreads();  // everyone done with the tables before they are rebuilt
+      __syncthreads();
     }
     if (inside) {
 #pragma unroll
       for (int c = 0; c < kCC; ++c)
         if (c0 + c < C) gpix[(int64_t)(c0 + c) * lv.sC] = acc[c];
     }
-    if (!single) __syncthreads();
+    __syncthreads();
   }
 }
 

@@ -24,23 +24,39 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kWarpTile = 1024;  // floats of warp-private staging
 constexpr int kKC = 4;           // channels per lane in the fast path
 
+constexpr int kMaxRows = kP * kRB;  // footprint rows the shared-row table can describe
+
 struct FwdParams {
   RoiLevels L;
   const float* rois;
   int M;
   float* out;
   int32_t* out_level;
+  const int32_t* order;  // (M) processing order (RoIs sorted by image, level, y band) or nullptr
 };
 
 struct Tables {
   float wy[kP * kRB];
   float wx[kP * kRB];
   int yb[kP], ny[kP], xb[kP], nx[kP];
+  // shared-row form of the y tables: footprint row r (0 = ymin) is loaded ONCE and folded into the (up to 3)
+  // consecutive output bins that contain it.  own_b/own_e[ph] = rows whose FIRST bin is ph.
+  float4 rw[kMaxRows];  // (w for bin ph0, ph0+1, ph0+2, unused)
+  int own_b[kP], own_e[kP];
+  int ymin, hf, shared_ok;
 };
+
+// fold one loaded value into bins PH, PH+1, PH+2 (indices are compile-time after unrolling; guards keep them in range)
+#define OSR_FOLD(K, PH, W, V)                                                                       \
+  do {                                                                                              \
+    U[K][PH] = fmaf((W).x, (V), U[K][PH]);                                                          \
+    if ((PH) + 1 < kP) U[K][(PH) + 1 < kP ? (PH) + 1 : 0] = fmaf((W).y, (V), U[K][(PH) + 1 < kP ? (PH) + 1 : 0]); \
+    if ((PH) + 2 < kP) U[K][(PH) + 2 < kP ? (PH) + 2 : 0] = fmaf((W).z, (V), U[K][(PH) + 2 < kP ? (PH) + 2 : 0]); \
+  } while (0)
 
 template <int LX>
 __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, float* Us, const float* img_base, int C,
-                                         int xmin, int wf, float count, float* out_roi) {
+                                         int xmin, int wf, float inv_count, float* out_roi) {
   constexpr int G = 32 / LX;
   constexpr int CPW = G * kKC;   // channels per warp iteration
   constexpr int LXP = LX + 1;    // padded row stride of the staging tile
@@ -61,18 +77,54 @@ __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, f
     bool cin[kKC];
 #pragma unroll
     for (int k = 0; k < kKC; ++k) cin[k] = xin && (c0 + k < C);
+    if (T.shared_ok) {
+      // every footprint row is loaded once; rows owned by bin ph also feed bins ph+1, ph+2 (static indices)
+      const float* rowp = chan + (int64_t)T.ymin * lv.sH;
 #pragma unroll
-    for (int ph = 0; ph < kP; ++ph) {
-      const int nr = T.ny[ph];
-      const float* rowp = chan + (int64_t)T.yb[ph] * lv.sH;
-      for (int r = 0; r < nr; ++r) {
-        const float w = T.wy[ph * kRB + r];
-        float v[kKC];
+      for (int ph = 0; ph < kP; ++ph) {
+        const int rb = T.own_b[ph], re = T.own_e[ph];
+        int r = rb;
+        for (; r + 1 < re; r += 2) {   // two rows (8 loads) in flight per lane
+          const float4 w0 = T.rw[r], w1 = T.rw[r + 1];
+          const float* p0 = rowp + (int64_t)r * lv.sH;
+          const float* p1 = p0 + lv.sH;
+          float v0[kKC], v1[kKC];
 #pragma unroll
-        for (int k = 0; k < kKC; ++k) v[k] = cin[k] ? __ldg(rowp + (int64_t)k * lv.sC) : 0.f;
+          for (int k = 0; k < kKC; ++k) v0[k] = cin[k] ? __ldg(p0 + (int64_t)k * lv.sC) : 0.f;
 #pragma unroll
-        for (int k = 0; k < kKC; ++k) U[k][ph] = fmaf(w, v[k], U[k][ph]);
-        rowp += lv.sH;
+          for (int k = 0; k < kKC; ++k) v1[k] = cin[k] ? __ldg(p1 + (int64_t)k * lv.sC) : 0.f;
+#pragma unroll
+          for (int k = 0; k < kKC; ++k) {
+            OSR_FOLD(k, ph, w0, v0[k]);
+            OSR_FOLD(k, ph, w1, v1[k]);
+          }
+        }
+        if (r < re) {
+          const float4 w0 = T.rw[r];
+          const float* p0 = rowp + (int64_t)r * lv.sH;
+          float v0[kKC];
+#pragma unroll
+          for (int k = 0; k < kKC; ++k) v0[k] = cin[k] ? __ldg(p0 + (int64_t)k * lv.sC) : 0.f;
+#pragma unroll
+          for (int k = 0; k < kKC; ++k) {
+            OSR_FOLD(k, ph, w0, v0[k]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ph = 0; ph < kP; ++ph) {
+        const int nr = T.ny[ph];
+        const float* rowp = chan + (int64_t)T.yb[ph] * lv.sH;
+        for (int r = 0; r < nr; ++r) {
+          const float w = T.wy[ph * kRB + r];
+          float v[kKC];
+#pragma unroll
+          for (int k = 0; k < kKC; ++k) v[k] = cin[k] ? __ldg(rowp + (int64_t)k * lv.sC) : 0.f;
+#pragma unroll
+          for (int k = 0; k < kKC; ++k) U[k][ph] = fmaf(w, v[k], U[k][ph]);
+          rowp += lv.sH;
+        }
       }
     }
 #pragma unroll
@@ -90,14 +142,14 @@ __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, f
       const float* wp = T.wx + pw * kRB;
       float s = 0.f;
       for (int q = 0; q < nq; ++q) s = fmaf(wp[q], up[q], s);
-      out_roi[(int64_t)cbase * (kP * kP) + o] = s / count;
+      out_roi[(int64_t)cbase * (kP * kP) + o] = s * inv_count;
     }
     __syncwarp();
   }
 }
 
 __device__ __forceinline__ void fwd_wide(const LevelDesc& lv, const Tables& T, float* Us, const float* img_base, int C,
-                                         int xmin, int wf, float count, float* out_roi) {
+                                         int xmin, int wf, float inv_count, float* out_roi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = warp; c < C; c += kWarps) {
     const float* chan = img_base + (int64_t)c * lv.sC + (int64_t)xmin * lv.sW;
@@ -130,17 +182,17 @@ __device__ __forceinline__ void fwd_wide(const LevelDesc& lv, const Tables& T, f
       const float* wp = T.wx + pw * kRB;
       float s = 0.f;
       for (int q = 0; q < nq; ++q) s = fmaf(wp[q], up[q], s);
-      out_roi[(int64_t)c * (kP * kP) + o] = s / count;
+      out_roi[(int64_t)c * (kP * kP) + o] = s * inv_count;
     }
     __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid_constant__ FwdParams p) {
   __shared__ Tables T;
   __shared__ __align__(16) float s_U[kWarps * kWarpTile];
 
-  const int m = blockIdx.x;
+  const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x;
   const float* roi = p.rois + (int64_t)m * 5;
   const float fimg = __ldg(roi), x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
@@ -169,11 +221,12 @@ __global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const __grid_co
     __syncthreads();
   }
   int path = 3;  // 0 fast, 1 wide, 2 generic, 3 zeros
-  int xmin = 0, wf = 0;
+  int xmin = 0, wf = 0, ymin = 0, hf = 0;
   if (!zero) {
     bool overflow = false, anyx = false, anyy = false;
-    int xmax = -1;
+    int xmax = -1, ymax = -1;
     xmin = 1 << 30;
+    ymin = 1 << 30;
 #pragma unroll
     for (int i = 0; i < kP; ++i) {
       const int nx = T.nx[i], ny = T.ny[i];
@@ -183,9 +236,14 @@ __global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const __grid_co
         xmin = min(xmin, T.xb[i]);
         xmax = max(xmax, T.xb[i] + nx - 1);
       }
-      anyy |= ny > 0;
+      if (ny > 0) {
+        anyy = true;
+        ymin = min(ymin, T.yb[i]);
+        ymax = max(ymax, T.yb[i] + ny - 1);
+      }
     }
     wf = xmax - xmin + 1;
+    hf = ymax - ymin + 1;
     if (overflow) path = 2;
     else if (!anyx || !anyy) path = 3;
     else if (wf <= 32) path = 0;
@@ -197,15 +255,59 @@ __global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const __grid_co
     for (int o = tid; o < C * kP * kP; o += kThreads) out_roi[o] = 0.f;
     return;
   }
+  if (path == 0) {
+    // shared-row tables: row r of the footprint -> (first bin containing it, weights for that bin and the next two)
+    int bad = 0;
+    for (int r = tid; r < hf; r += kThreads) {
+      const int y = ymin + r;
+      int ph0 = -1, cnt = 0;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+#pragma unroll
+      for (int ph = 0; ph < kP; ++ph) {
+        const int rr = y - T.yb[ph];
+        if (rr >= 0 && rr < T.ny[ph]) {
+          if (ph0 < 0) ph0 = ph;
+          const int d = ph - ph0;
+          const float wv = T.wy[ph * kRB + rr];
+          if (d == 0) w0 = wv;
+          else if (d == 1) w1 = wv;
+          else if (d == 2) w2 = wv;
+          else bad = 1;
+          ++cnt;
+        }
+      }
+      // rows inside [ymin, ymax] that no bin touches cannot exist (bins tile the RoI), but stay safe:
+      T.rw[r] = make_float4(w0, w1, w2, __int_as_float(ph0 < 0 ? kP - 1 : ph0));
+    }
+    bad = __syncthreads_or(bad);
+    if (tid < kP) {
+      // own range of bin ph = rows whose first bin is ph (rows are ordered, so this is a contiguous range)
+      int b = hf, e = 0;
+      for (int r = 0; r < hf; ++r)
+        if (__float_as_int(T.rw[r].w) == tid) {
+          b = min(b, r);
+          e = r + 1;
+        }
+      T.own_b[tid] = b < e ? b : 0;
+      T.own_e[tid] = b < e ? e : 0;
+    }
+    if (tid == 0) {
+      T.ymin = ymin;
+      T.hf = hf;
+      T.shared_ok = !bad;
+    }
+    __syncthreads();
+  }
   const LevelDesc& lv = p.L.lv[level];
   const float* img_base = lv.data + (int64_t)img * lv.sN;
   float* Us = s_U + (tid >> 5) * kWarpTile;
+  const float inv_count = 1.0f / g.count;
   if (path == 0) {
-    if (wf <= 8) fwd_fast<8>(lv, T, Us, img_base, C, xmin, wf, g.count, out_roi);
-    else if (wf <= 16) fwd_fast<16>(lv, T, Us, img_base, C, xmin, wf, g.count, out_roi);
-    else fwd_fast<32>(lv, T, Us, img_base, C, xmin, wf, g.count, out_roi);
+    if (wf <= 8) fwd_fast<8>(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
+    else if (wf <= 16) fwd_fast<16>(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
+    else fwd_fast<32>(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
   } else if (path == 1) {
-    fwd_wide(lv, T, Us, img_base, C, xmin, wf, g.count, out_roi);
+    fwd_wide(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
   } else {
     // generic: torchvision's per-sample loop, one output element per thread iteration
     for (int o = tid; o < C * kP * kP; o += kThreads) {
@@ -224,6 +326,57 @@ __global__ void __launch_bounds__(kThreads) roi_align_fwd_kernel(const __grid_co
       out_roi[o] = s / g.count;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Processing order: RoIs bucketed by (image, level, y band) with a single-CTA counting sort, so that CTAs that
+// run concurrently read neighbouring feature rows (L2-resident working set instead of a whole image's pyramid).
+// The order only changes scheduling: every RoI still writes its own output rows, results are order-independent.
+constexpr int kSortThreads = 1024;
+constexpr int kYBands = 16;
+constexpr int kMaxBuckets = 8192;
+
+__global__ void __launch_bounds__(kSortThreads) roi_order_kernel(const __grid_constant__ FwdParams p, int32_t* order,
+                                                                int32_t* keys, int ybands) {
+  __shared__ int hist[kMaxBuckets];
+  const int tid = threadIdx.x;
+  const int nb = p.L.num_images * p.L.num_levels * ybands;
+  for (int i = tid; i < nb; i += kSortThreads) hist[i] = 0;
+  __syncthreads();
+  for (int m = tid; m < p.M; m += kSortThreads) {
+    const float* roi = p.rois + (int64_t)m * 5;
+    const float x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
+    int img = (int)__ldg(roi);
+    int level = assign_level(x1, y1, x2, y2, p.L);
+    img = min(max(img, 0), p.L.num_images - 1);
+    level = min(max(level, 0), p.L.num_levels - 1);
+    const LevelDesc& lv = p.L.lv[level];
+    const float yc = 0.5f * (y1 + y2) * lv.scale;
+    int band = (int)(yc * (float)ybands / (float)lv.H);
+    band = min(max(band, 0), ybands - 1);
+    const int key = (img * p.L.num_levels + level) * ybands + band;
+    keys[m] = key;
+    atomicAdd(&hist[key], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the buckets (single warp, nb <= 8192)
+  if (tid < 32) {
+    int run = 0;
+    for (int base = 0; base < nb; base += 32) {
+      const int i = base + tid;
+      const int v = i < nb ? hist[i] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      if (i < nb) hist[i] = run + inc - v;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int m = tid; m < p.M; m += kSortThreads) order[atomicAdd(&hist[keys[m]], 1)] = m;
 }
 
 }  // namespace
@@ -257,10 +410,14 @@ int fill_roi_levels(RoiLevels& L, const osr_feat_level_t* h_levels, int num_leve
 }
 }  // namespace osr
 
-extern "C" int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C,
-                                 const float* rois, int M, int P, int sampling_ratio, int aligned,
-                                 int canonical_box_size, int canonical_level, int min_level, float* out,
-                                 int32_t* out_level, void* stream) {
+extern "C" {
+
+size_t osr_roi_align_fwd_workspace(int M) { return osr::align256((size_t)(M > 0 ? M : 1) * 4) * 2; }
+
+int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                      int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
+                      int min_level, float* out, int32_t* out_level, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   FwdParams p;
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);
@@ -272,7 +429,23 @@ extern "C" int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_level
   p.M = M;
   p.out = out;
   p.out_level = out_level;
-  roi_align_fwd_kernel<<<M, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  p.order = nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // locality ordering (optional: skipped without a workspace, or for tiny problems where it cannot pay)
+  if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && M >= 256) {
+    int ybands = kYBands;
+    while (ybands > 1 && num_images * num_levels * ybands > kMaxBuckets) ybands >>= 1;
+    if (num_images * num_levels * ybands <= kMaxBuckets) {
+      int32_t* order = static_cast<int32_t*>(workspace);
+      int32_t* keys = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + osr::align256((size_t)M * 4));
+      roi_order_kernel<<<1, kSortThreads, 0, s>>>(p, order, keys, ybands);
+      OSR_LAUNCH_CHECK();
+      p.order = order;
+    }
+  }
+  roi_align_fwd_kernel<<<M, kThreads, 0, s>>>(p);
   OSR_LAUNCH_CHECK();
   return 0;
 }
+
+}  // extern "C"

@@ -64,9 +64,10 @@ class _ROIAlignFPN(torch.autograd.Function):
         dev = feats[0].device
         out = torch.empty((M, C, P, P), dtype=torch.float32, device=dev)
         lvl = torch.empty((M,), dtype=torch.int32, device=dev)
+        ws = torch.empty(max(int(lib.osr_roi_align_fwd_workspace(M)), 256), dtype=torch.uint8, device=dev)
         rc = lib.osr_roi_align_fwd(arr, len(feats), N, C, rois.data_ptr(), M, P, sampling_ratio, 1,
                                    canon_size, canon_level, min_level, out.data_ptr(), lvl.data_ptr(),
-                                   _lib.stream_ptr(dev))
+                                   ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "osr_roi_align_fwd")
         ctx.cfg = cfg
         ctx.shapes = [tuple(f.shape) for f in feats]

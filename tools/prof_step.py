@@ -1,0 +1,22 @@
+"""Profiling driver: a few device-resident RoI-path steps, nothing else (for `ncu ... python tools/prof_step.py`)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "openset-rcnn_b200"))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from osr_b200.pipeline import PathConfig, RoiPathStep  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--images", type=int, default=16)
+ap.add_argument("--channels-last", action="store_true")
+a = ap.parse_args()
+path = RoiPathStep(PathConfig(num_images=a.images, channels_last=a.channels_last, seed=3234), "cuda:0")
+for _ in range(a.steps):
+    path.step()
+torch.cuda.synchronize()
+print("done")
