@@ -54,6 +54,10 @@ struct Tables {
     if ((PH) + 2 < kP) U[K][(PH) + 2 < kP ? (PH) + 2 : 0] = fmaf((W).z, (V), U[K][(PH) + 2 < kP ? (PH) + 2 : 0]); \
   } while (0)
 
+// Fast path (footprint at most 32 columns wide).  Instruction-lean on purpose: per-image element offsets are
+// 32-bit (a (C,H,W) pyramid level has < 2^31 elements), loads are unpredicated (out-of-footprint lanes re-read a
+// clamped in-footprint address and their results are never consumed), and every lane owns two fixed (ph, pw)
+// outputs for the whole RoI so stage 2 has no divisions and its x-weights live in registers.
 template <int LX>
 __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, float* Us, const float* img_base, int C,
                                          int xmin, int wf, float inv_count, float* out_roi) {
@@ -63,8 +67,26 @@ __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, f
   static_assert(CPW * kP * LXP <= kWarpTile, "warp tile too small");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = lane / LX, x = lane % LX;
-  const bool xin = x < wf;
-  const float* col = img_base + (int64_t)(xmin + (xin ? x : 0)) * lv.sW;
+  const uint32_t sC = (uint32_t)lv.sC, sH = (uint32_t)lv.sH;
+  const uint32_t off_x = (uint32_t)(xmin + min(x, wf - 1)) * (uint32_t)lv.sW + (uint32_t)T.ymin * sH;
+
+  // stage-2 ownership: outputs o = lane and o = lane + 32 (< 49) of every channel
+  int so[2], snq[2];
+  float sw[2][4];
+  bool sslow = false;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int o = lane + 32 * t;
+    const int oo = o < kP * kP ? o : 0;
+    const int ph = oo / kP, pw = oo - ph * kP;
+    const int nq = (o < kP * kP) ? T.nx[pw] : 0;
+    snq[t] = nq;
+    so[t] = nq > 0 ? ph * LXP + (T.xb[pw] - xmin) : 0;   // taps past nq carry weight 0 and read finite staging data
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sw[t][q] = (q < nq) ? T.wx[pw * kRB + q] : 0.f;
+    sslow |= nq > 4;
+  }
+  sslow = __any_sync(0xffffffffu, sslow);
 
   for (int cbase = warp * CPW; cbase < C; cbase += kWarps * CPW) {
     float U[kKC][kP];
@@ -72,27 +94,24 @@ __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, f
     for (int k = 0; k < kKC; ++k)
 #pragma unroll
       for (int ph = 0; ph < kP; ++ph) U[k][ph] = 0.f;
-    const int c0 = cbase + cg * kKC;
-    const float* chan = col + (int64_t)c0 * lv.sC;
-    bool cin[kKC];
+    uint32_t off_c[kKC];
 #pragma unroll
-    for (int k = 0; k < kKC; ++k) cin[k] = xin && (c0 + k < C);
+    for (int k = 0; k < kKC; ++k) off_c[k] = (uint32_t)min(cbase + cg * kKC + k, C - 1) * sC + off_x;
     if (T.shared_ok) {
       // every footprint row is loaded once; rows owned by bin ph also feed bins ph+1, ph+2 (static indices)
-      const float* rowp = chan + (int64_t)T.ymin * lv.sH;
 #pragma unroll
       for (int ph = 0; ph < kP; ++ph) {
         const int rb = T.own_b[ph], re = T.own_e[ph];
         int r = rb;
+        uint32_t off_r = (uint32_t)rb * sH;
         for (; r + 1 < re; r += 2) {   // two rows (8 loads) in flight per lane
           const float4 w0 = T.rw[r], w1 = T.rw[r + 1];
-          const float* p0 = rowp + (int64_t)r * lv.sH;
-          const float* p1 = p0 + lv.sH;
           float v0[kKC], v1[kKC];
 #pragma unroll
-          for (int k = 0; k < kKC; ++k) v0[k] = cin[k] ? __ldg(p0 + (int64_t)k * lv.sC) : 0.f;
+          for (int k = 0; k < kKC; ++k) v0[k] = __ldg(img_base + (off_c[k] + off_r));
 #pragma unroll
-          for (int k = 0; k < kKC; ++k) v1[k] = cin[k] ? __ldg(p1 + (int64_t)k * lv.sC) : 0.f;
+          for (int k = 0; k < kKC; ++k) v1[k] = __ldg(img_base + (off_c[k] + off_r + sH));
+          off_r += 2 * sH;
 #pragma unroll
           for (int k = 0; k < kKC; ++k) {
             OSR_FOLD(k, ph, w0, v0[k]);
@@ -101,48 +120,75 @@ __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, f
         }
         if (r < re) {
           const float4 w0 = T.rw[r];
-          const float* p0 = rowp + (int64_t)r * lv.sH;
           float v0[kKC];
 #pragma unroll
-          for (int k = 0; k < kKC; ++k) v0[k] = cin[k] ? __ldg(p0 + (int64_t)k * lv.sC) : 0.f;
+          for (int k = 0; k < kKC; ++k) v0[k] = __ldg(img_base + (off_c[k] + off_r));
 #pragma unroll
-          for (int k = 0; k < kKC; ++k) {
-            OSR_FOLD(k, ph, w0, v0[k]);
-          }
+          for (int k = 0; k < kKC; ++k) OSR_FOLD(k, ph, w0, v0[k]);
         }
       }
     } else {
 #pragma unroll
       for (int ph = 0; ph < kP; ++ph) {
         const int nr = T.ny[ph];
-        const float* rowp = chan + (int64_t)T.yb[ph] * lv.sH;
+        uint32_t off_r = (uint32_t)(T.yb[ph] - T.ymin) * sH;
         for (int r = 0; r < nr; ++r) {
           const float w = T.wy[ph * kRB + r];
           float v[kKC];
 #pragma unroll
-          for (int k = 0; k < kKC; ++k) v[k] = cin[k] ? __ldg(rowp + (int64_t)k * lv.sC) : 0.f;
+          for (int k = 0; k < kKC; ++k) v[k] = __ldg(img_base + (off_c[k] + off_r));
 #pragma unroll
           for (int k = 0; k < kKC; ++k) U[k][ph] = fmaf(w, v[k], U[k][ph]);
-          rowp += lv.sH;
+          off_r += sH;
         }
       }
     }
+    {
+      float* ub = Us + (cg * kKC) * (kP * LXP) + x;
 #pragma unroll
-    for (int k = 0; k < kKC; ++k)
+      for (int k = 0; k < kKC; ++k)
 #pragma unroll
-      for (int ph = 0; ph < kP; ++ph) Us[((cg * kKC + k) * kP + ph) * LXP + x] = U[k][ph];
+        for (int ph = 0; ph < kP; ++ph) ub[(k * kP + ph) * LXP] = U[k][ph];
+    }
     __syncwarp();
-    const int nout = min(CPW, C - cbase) * (kP * kP);
-    for (int o = lane; o < nout; o += 32) {
-      const int cl = o / (kP * kP);
-      const int rem = o - cl * (kP * kP);
-      const int ph = rem / kP, pw = rem - ph * kP;
-      const int nq = T.nx[pw];
-      const float* up = Us + (cl * kP + ph) * LXP + (T.xb[pw] - xmin);
-      const float* wp = T.wx + pw * kRB;
-      float s = 0.f;
-      for (int q = 0; q < nq; ++q) s = fmaf(wp[q], up[q], s);
-      out_roi[(int64_t)cbase * (kP * kP) + o] = s * inv_count;
+    const int nch = min(CPW, C - cbase);
+    float* outc = out_roi + (int64_t)cbase * (kP * kP) + lane;
+    if (!sslow) {
+#pragma unroll 4
+      for (int cl = 0; cl < nch; ++cl) {
+        const float* uc = Us + cl * (kP * LXP);
+        {
+          const float* up = uc + so[0];
+          float a = sw[0][0] * up[0];
+          a = fmaf(sw[0][1], up[1], a);
+          a = fmaf(sw[0][2], up[2], a);
+          a = fmaf(sw[0][3], up[3], a);
+          outc[cl * (kP * kP)] = a * inv_count;
+        }
+        if (lane + 32 < kP * kP) {
+          const float* up = uc + so[1];
+          float a = sw[1][0] * up[0];
+          a = fmaf(sw[1][1], up[1], a);
+          a = fmaf(sw[1][2], up[2], a);
+          a = fmaf(sw[1][3], up[3], a);
+          outc[cl * (kP * kP) + 32] = a * inv_count;
+        }
+      }
+    } else {
+      for (int cl = 0; cl < nch; ++cl) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int o = lane + 32 * t;
+          if (o < kP * kP) {
+            const int pw = o % kP;
+            const float* up = Us + cl * (kP * LXP) + so[t];
+            const float* wp = T.wx + pw * kRB;
+            float a = 0.f;
+            for (int q = 0; q < snq[t]; ++q) a = fmaf(wp[q], up[q], a);
+            outc[cl * (kP * kP) + 32 * t] = a * inv_count;
+          }
+        }
+      }
     }
     __syncwarp();
   }
@@ -211,6 +257,8 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid
       T.wy[i] = 0.f;
       T.wx[i] = 0.f;
     }
+    // the staging tiles' pad columns are read (with weight 0) by the fixed 4-tap stage 2: keep them finite
+    for (int i = tid; i < kWarps * kWarpTile; i += kThreads) s_U[i] = 0.f;
     __syncthreads();
     if (tid < kP) {
       T.ny[tid] = build_bin_weights(g.start_h, g.bin_h, g.grid_h, lv0.H, tid, T.wy + tid * kRB, &T.yb[tid]);
