@@ -13,6 +13,9 @@
 //            (M, C, 7, 7) output the box head expects.
 // Wide footprints (33..146 columns) use the same scheme one channel at a time; anything larger, or an
 // output bin spanning more than kRB rows/cols, takes a generic per-sample path (correctness only).
+#include <cuda.h>
+#include <string.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time (no libcuda link dependency)
+
 #include "roi_geometry.cuh"
 
 namespace {
@@ -33,6 +36,17 @@ struct FwdParams {
   float* out;
   int32_t* out_level;
   const int32_t* order;  // (M) processing order (RoIs sorted by image, level, y band) or nullptr
+  int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules (x-contiguous, 16-byte strides/base)
+};
+
+// TMA staging geometry: one box = 32 columns x 8 rows x 8 channels of one image (8 KB), 4-stage ring
+constexpr int kTX = 32, kTR = 8, kTC = 8;
+constexpr int kStageFloats = kTX * kTR * kTC;
+constexpr int kNS = 4;
+static_assert(kTC == kWarps, "one warp per channel of a box");
+
+struct alignas(64) FwdTma {
+  CUtensorMap map[OSR_MAX_LEVELS];
 };
 
 struct Tables {
@@ -194,6 +208,179 @@ __device__ __forceinline__ void fwd_fast(const LevelDesc& lv, const Tables& T, f
   }
 }
 
+// ---- TMA path ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {  // one lane of a CONVERGED warp (TMA is issued from uniform control flow)
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+// One stage = kTC channel planes x kTR rows x kTX columns.  The level is addressed as a 2-D tensor (W, N*C*H): row index
+// of (n, c, y) = (n*C + c)*H + y.  (3-D/4-D tiled loads fault on this driver/toolkit combination - see
+// tools/tma_probe - so a stage is kTC 2-D boxes that complete on the same mbarrier.)  Rows past the plane's end belong
+// to the next plane and are never consumed (r < hf); columns past W are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_stage(float* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int c0,
+                                               int img, int C, int H) {
+  mbar_expect_tx(bar, kStageFloats * 4);
+#pragma unroll
+  for (int k = 0; k < kTC; ++k) {
+    const int c = min(c0 + k, C - 1);  // C % kTC != 0: the extra planes re-read the last channel (results discarded)
+    tma_load_2d(dst + k * (kTR * kTX), map, bar, x, (img * C + c) * H + y);
+  }
+}
+
+// Footprint (<= 32 columns from the 4-column-aligned origin `xmin`) streamed through shared memory by the TMA unit:
+// one elected lane of warp 0 keeps kNS stages in flight, warp w
+// consumes channel w of every box with conflict-free LDS (lane = column), folding rows into the 7 per-bin accumulators;
+// after the last row block of a channel block each warp finishes its channel (stage 2) and stores 49 outputs.
+__device__ __forceinline__ void fwd_tma(const CUtensorMap* map, const Tables& T, float* stages, uint64_t* full_bar,
+                                        uint64_t* empty_bar, float* Us, int C, int H, int img, int xmin, int hf,
+                                        float inv_count, float* out_roi) {
+  constexpr int LXP = kTX + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntr = ceil_div(hf, kTR), ncb = ceil_div(C, kTC);
+  const int total = ntr * ncb;
+  if (tid == 0) {
+    for (int i = 0; i < kNS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the prologue zero-filled the ring with generic-proxy stores; order them before the async-proxy (TMA) writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      const int pre = min(kNS, total);
+      for (int t = 0; t < pre; ++t) {
+        const int cb = t / ntr, rb = t - cb * ntr;
+        tma_load_stage(stages + t * kStageFloats, map, &full_bar[t], xmin, T.ymin + rb * kTR, cb * kTC, img, C, H);
+      }
+    }
+    __syncwarp();
+  }
+  // stage-2 ownership (same scheme as the fast path, staging row stride LXP)
+  int so[2];
+  float sw[2][4];
+  bool sslow = false;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int o = lane + 32 * t;
+    const int oo = o < kP * kP ? o : 0;
+    const int ph = oo / kP, pw = oo - ph * kP;
+    const int nq = (o < kP * kP) ? T.nx[pw] : 0;
+    so[t] = nq > 0 ? ph * LXP + (T.xb[pw] - xmin) : 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sw[t][q] = (q < nq) ? T.wx[pw * kRB + q] : 0.f;
+    sslow |= nq > 4;
+  }
+  sslow = __any_sync(0xffffffffu, sslow);
+
+  float U[1][kP];
+  int cb = 0, rb = 0;
+  for (int t = 0; t < total; ++t) {
+    const int slot = t % kNS;
+    const uint32_t parity = (uint32_t)((t / kNS) & 1);
+    if (rb == 0) {
+#pragma unroll
+      for (int ph = 0; ph < kP; ++ph) U[0][ph] = 0.f;
+    }
+    mbar_wait(&full_bar[slot], parity);
+    const float* tile = stages + slot * kStageFloats + warp * (kTR * kTX) + lane;
+    const int r_lo = rb * kTR, r_hi = min(hf, r_lo + kTR);
+#pragma unroll
+    for (int ph = 0; ph < kP; ++ph) {
+      const int rbeg = max(T.own_b[ph], r_lo), rend = min(T.own_e[ph], r_hi);
+      for (int r = rbeg; r < rend; ++r) {
+        const float4 w0 = T.rw[r];
+        const float v = tile[(r - r_lo) * kTX];
+        OSR_FOLD(0, ph, w0, v);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);
+    if (rb == ntr - 1) {
+      const int c = cb * kTC + warp;
+      if (c < C) {
+#pragma unroll
+        for (int ph = 0; ph < kP; ++ph) Us[ph * LXP + lane] = U[0][ph];
+        __syncwarp();
+        float* outc = out_roi + (int64_t)c * (kP * kP) + lane;
+        if (!sslow) {
+          {
+            const float* up = Us + so[0];
+            float a = sw[0][0] * up[0];
+            a = fmaf(sw[0][1], up[1], a);
+            a = fmaf(sw[0][2], up[2], a);
+            a = fmaf(sw[0][3], up[3], a);
+            outc[0] = a * inv_count;
+          }
+          if (lane + 32 < kP * kP) {
+            const float* up = Us + so[1];
+            float a = sw[1][0] * up[0];
+            a = fmaf(sw[1][1], up[1], a);
+            a = fmaf(sw[1][2], up[2], a);
+            a = fmaf(sw[1][3], up[3], a);
+            outc[32] = a * inv_count;
+          }
+        } else {
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            const int o = lane + 32 * tt;
+            if (o < kP * kP) {
+              const int pw = o % kP;
+              const float* up = Us + so[tt];
+              const float* wp = T.wx + pw * kRB;
+              float a = 0.f;
+              for (int q = 0; q < T.nx[pw]; ++q) a = fmaf(wp[q], up[q], a);
+              outc[32 * tt] = a * inv_count;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // producer: refill this slot with tile t + kNS once every warp has released it
+    if (warp == 0 && t + kNS < total) {
+      if (elect_one()) {
+        mbar_wait(&empty_bar[slot], parity);
+        const int tn = t + kNS;
+        const int ncb2 = tn / ntr, nrb2 = tn - ncb2 * ntr;
+        tma_load_stage(stages + slot * kStageFloats, map, &full_bar[slot], xmin, T.ymin + nrb2 * kTR, ncb2 * kTC, img, C, H);
+      }
+      __syncwarp();
+    }
+    if (++rb == ntr) { rb = 0; ++cb; }
+  }
+}
+
 __device__ __forceinline__ void fwd_wide(const LevelDesc& lv, const Tables& T, float* Us, const float* img_base, int C,
                                          int xmin, int wf, float inv_count, float* out_roi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -234,9 +421,14 @@ __device__ __forceinline__ void fwd_wide(const LevelDesc& lv, const Tables& T, f
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid_constant__ FwdParams p) {
-  __shared__ Tables T;
-  __shared__ __align__(16) float s_U[kWarps * kWarpTile];
+__global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid_constant__ FwdParams p,
+                                                                    const __grid_constant__ FwdTma tm) {
+  // dynamic shared memory: [ s_U (32 KB; LDG paths: warp tiles / TMA path: 4 x 8 KB stage ring) | Us_tma | barriers | T ]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_U = reinterpret_cast<float*>(smem_raw);
+  float* s_Ut = s_U + kWarps * kWarpTile;                                  // kWarps x 7 x 33 floats
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_Ut + kWarps * kP * (kTX + 1) + 8);
+  Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNS);
 
   const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x;
@@ -258,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid
       T.wx[i] = 0.f;
     }
     // the staging tiles' pad columns are read (with weight 0) by the fixed 4-tap stage 2: keep them finite
-    for (int i = tid; i < kWarps * kWarpTile; i += kThreads) s_U[i] = 0.f;
+    for (int i = tid; i < kWarps * kWarpTile + kWarps * kP * (kTX + 1) + 8; i += kThreads) s_U[i] = 0.f;
     __syncthreads();
     if (tid < kP) {
       T.ny[tid] = build_bin_weights(g.start_h, g.bin_h, g.grid_h, lv0.H, tid, T.wy + tid * kRB, &T.yb[tid]);
@@ -350,7 +542,11 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid
   const float* img_base = lv.data + (int64_t)img * lv.sN;
   float* Us = s_U + (tid >> 5) * kWarpTile;
   const float inv_count = 1.0f / g.count;
-  if (path == 0) {
+  // TMA box starts must be 16-byte aligned in x: start at x0 = xmin rounded down to 4 columns
+  if (path == 0 && p.tma_ok[level] && T.shared_ok && ((xmin & 3) + wf <= kTX)) {
+    fwd_tma(&tm.map[level], T, s_U, s_bar, s_bar + kNS, s_Ut + (tid >> 5) * (kP * (kTX + 1)), C, lv.H, img, xmin & ~3, hf,
+            inv_count, out_roi);
+  } else if (path == 0) {
     if (wf <= 8) fwd_fast<8>(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
     else if (wf <= 16) fwd_fast<16>(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
     else fwd_fast<32>(lv, T, Us, img_base, C, xmin, wf, inv_count, out_roi);
@@ -427,6 +623,43 @@ __global__ void __launch_bounds__(kSortThreads) roi_order_kernel(const __grid_co
   for (int m = tid; m < p.M; m += kSortThreads) order[atomicAdd(&hist[keys[m]], 1)] = m;
 }
 
+size_t fwd_smem_bytes() {
+  return (size_t)(kWarps * kWarpTile + kWarps * kP * (kTX + 1) + 8) * 4 + 2 * kNS * 8 + sizeof(Tables) + 16;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 2-D tensor map (x, rows = N*C*H) of one contiguous NCHW pyramid level; returns 1 if the level can be streamed by TMA
+int encode_level_map(CUtensorMap* map, const LevelDesc& lv, int num_images, int C) {
+  if (lv.sW != 1 || lv.sH != lv.W) return 0;                                  // rows contiguous
+  if (lv.sC != (int64_t)lv.H * lv.W || (num_images > 1 && lv.sN != (int64_t)C * lv.H * lv.W)) return 0;  // planes contiguous
+  if ((reinterpret_cast<uintptr_t>(lv.data) & 15) || ((lv.sH * 4) & 15)) return 0;  // 16-byte base and row stride
+  const int64_t rows = (int64_t)(num_images > 0 ? num_images : 1) * C * lv.H;
+  if (rows >= ((int64_t)1 << 31)) return 0;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return 0;
+  cuuint64_t dims[2] = {(cuuint64_t)lv.W, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)lv.sH * 4};
+  cuuint32_t box[2] = {kTX, kTR};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, lv.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 1 : 0;
+}
+
 }  // namespace
 
 namespace osr {
@@ -491,7 +724,12 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
       p.order = order;
     }
   }
-  roi_align_fwd_kernel<<<M, kThreads, 0, s>>>(p);
+  FwdTma tm;
+  memset(&tm, 0, sizeof(tm));
+  for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = encode_level_map(&tm.map[l], p.L.lv[l], num_images, C);
+  const size_t smem = fwd_smem_bytes();
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  roi_align_fwd_kernel<<<M, kThreads, smem, s>>>(p, tm);
   OSR_LAUNCH_CHECK();
   return 0;
 }
