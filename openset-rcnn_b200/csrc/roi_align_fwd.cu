@@ -14,6 +14,7 @@
 // Wide footprints (33..146 columns) use the same scheme one channel at a time; anything larger, or an
 // output bin spanning more than kRB rows/cols, takes a generic per-sample path (correctness only).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time (no libcuda link dependency)
 
 #include "roi_geometry.cuh"
@@ -36,14 +37,20 @@ struct FwdParams {
   float* out;
   int32_t* out_level;
   const int32_t* order;  // (M) processing order (RoIs sorted by image, level, y band) or nullptr
-  int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules (x-contiguous, 16-byte strides/base)
+  int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules AND the TMA path is enabled for this call
+  int ring_floats;             // floats of the staging ring at the start of dynamic shared memory
 };
 
-// TMA staging geometry: one box = 32 columns x 8 rows x 8 channels of one image (8 KB), 4-stage ring
+// TMA staging geometry: a stage holds the WHOLE footprint (<= kTRmax rows x 32 columns) of kTC channels of one image;
+// it is filled by (rows/8) x kTC boxes of 32 x 8 floats that complete on one mbarrier.  2-stage ring.
 constexpr int kTX = 32, kTR = 8, kTC = 8;
-constexpr int kStageFloats = kTX * kTR * kTC;
-constexpr int kNS = 4;
-static_assert(kTC == kWarps, "one warp per channel of a box");
+constexpr int kTRmax = 24;                       // footprints taller than this use the LDG path
+constexpr int kChanFloats = kTRmax * kTX;        // 768 floats per channel plane of a stage
+constexpr int kStageFloats = kTC * kChanFloats;  // 24 KB
+constexpr int kNS = 2;
+constexpr int kRingFloats = kNS * kStageFloats;  // 48 KB (aliases the LDG paths' 32 KB of warp tiles)
+static_assert(kTC == kWarps, "one warp per channel of a stage");
+static_assert(kRingFloats >= kWarps * kWarpTile, "ring must cover the LDG staging tiles");
 
 struct alignas(64) FwdTma {
   CUtensorMap map[OSR_MAX_LEVELS];
@@ -241,31 +248,30 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
-// One stage = kTC channel planes x kTR rows x kTX columns.  The level is addressed as a 2-D tensor (W, N*C*H): row index
-// of (n, c, y) = (n*C + c)*H + y.  (3-D/4-D tiled loads fault on this driver/toolkit combination - see
-// tools/tma_probe - so a stage is kTC 2-D boxes that complete on the same mbarrier.)  Rows past the plane's end belong
-// to the next plane and are never consumed (r < hf); columns past W are zero-filled by the TMA unit.
-__device__ __forceinline__ void tma_load_stage(float* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int c0,
-                                               int img, int C, int H) {
-  mbar_expect_tx(bar, kStageFloats * 4);
+// One stage = kTC channel planes x nrb row blocks.  The level is addressed as a 2-D tensor (W, N*C*H): row index of
+// (n, c, y) = (n*C + c)*H + y.  Rows past the plane's end belong to the next plane and are never consumed (r < hf);
+// columns past W are zero-filled by the TMA unit.  Box starts must be 16-byte aligned in x (x0 % 4 == 0).
+__device__ __forceinline__ void tma_load_stage(float* dst, const CUtensorMap* map, uint64_t* bar, int x0, int y0, int nrb,
+                                               int c0, int img, int C, int H) {
+  mbar_expect_tx(bar, (uint32_t)(kTC * nrb * kTR * kTX * 4));
 #pragma unroll
   for (int k = 0; k < kTC; ++k) {
     const int c = min(c0 + k, C - 1);  // C % kTC != 0: the extra planes re-read the last channel (results discarded)
-    tma_load_2d(dst + k * (kTR * kTX), map, bar, x, (img * C + c) * H + y);
+    const int row0 = (img * C + c) * H + y0;
+    for (int rb = 0; rb < nrb; ++rb) tma_load_2d(dst + k * kChanFloats + rb * (kTR * kTX), map, bar, x0, row0 + rb * kTR);
   }
 }
 
-// Footprint (<= 32 columns from the 4-column-aligned origin `xmin`) streamed through shared memory by the TMA unit:
-// one elected lane of warp 0 keeps kNS stages in flight, warp w
-// consumes channel w of every box with conflict-free LDS (lane = column), folding rows into the 7 per-bin accumulators;
-// after the last row block of a channel block each warp finishes its channel (stage 2) and stores 49 outputs.
+// Footprint (<= 32 columns from the 4-column-aligned origin x0, <= kTRmax rows) streamed through shared memory by the
+// TMA unit: one elected lane of warp 0 keeps both stages in flight; warp w consumes channel w of every stage with
+// conflict-free LDS (lane = column), folding the rows into the 7 per-bin accumulators, then finishes its channel
+// (x contraction through a warp-private tile) and stores its 49 outputs.
 __device__ __forceinline__ void fwd_tma(const CUtensorMap* map, const Tables& T, float* stages, uint64_t* full_bar,
-                                        uint64_t* empty_bar, float* Us, int C, int H, int img, int xmin, int hf,
+                                        uint64_t* empty_bar, float* Us, int C, int H, int img, int x0, int hf,
                                         float inv_count, float* out_roi) {
   constexpr int LXP = kTX + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ntr = ceil_div(hf, kTR), ncb = ceil_div(C, kTC);
-  const int total = ntr * ncb;
+  const int nrb = ceil_div(hf, kTR), ncb = ceil_div(C, kTC);
   if (tid == 0) {
     for (int i = 0; i < kNS; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -278,11 +284,8 @@ __device__ __forceinline__ void fwd_tma(const CUtensorMap* map, const Tables& T,
   __syncthreads();
   if (warp == 0) {
     if (elect_one()) {
-      const int pre = min(kNS, total);
-      for (int t = 0; t < pre; ++t) {
-        const int cb = t / ntr, rb = t - cb * ntr;
-        tma_load_stage(stages + t * kStageFloats, map, &full_bar[t], xmin, T.ymin + rb * kTR, cb * kTC, img, C, H);
-      }
+      for (int t = 0; t < min(kNS, ncb); ++t)
+        tma_load_stage(stages + t * kStageFloats, map, &full_bar[t], x0, T.ymin, nrb, t * kTC, img, C, H);
     }
     __syncwarp();
   }
@@ -296,88 +299,86 @@ __device__ __forceinline__ void fwd_tma(const CUtensorMap* map, const Tables& T,
     const int oo = o < kP * kP ? o : 0;
     const int ph = oo / kP, pw = oo - ph * kP;
     const int nq = (o < kP * kP) ? T.nx[pw] : 0;
-    so[t] = nq > 0 ? ph * LXP + (T.xb[pw] - xmin) : 0;
+    so[t] = nq > 0 ? ph * LXP + (T.xb[pw] - x0) : 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) sw[t][q] = (q < nq) ? T.wx[pw * kRB + q] : 0.f;
     sslow |= nq > 4;
   }
   sslow = __any_sync(0xffffffffu, sslow);
 
-  float U[1][kP];
-  int cb = 0, rb = 0;
-  for (int t = 0; t < total; ++t) {
-    const int slot = t % kNS;
-    const uint32_t parity = (uint32_t)((t / kNS) & 1);
-    if (rb == 0) {
+  for (int cb = 0; cb < ncb; ++cb) {
+    const int slot = cb % kNS;
+    const uint32_t parity = (uint32_t)((cb / kNS) & 1);
+    float U[1][kP];
 #pragma unroll
-      for (int ph = 0; ph < kP; ++ph) U[0][ph] = 0.f;
-    }
+    for (int ph = 0; ph < kP; ++ph) U[0][ph] = 0.f;
     mbar_wait(&full_bar[slot], parity);
-    const float* tile = stages + slot * kStageFloats + warp * (kTR * kTX) + lane;
-    const int r_lo = rb * kTR, r_hi = min(hf, r_lo + kTR);
+    const float* tile = stages + slot * kStageFloats + warp * kChanFloats + lane;
 #pragma unroll
     for (int ph = 0; ph < kP; ++ph) {
-      const int rbeg = max(T.own_b[ph], r_lo), rend = min(T.own_e[ph], r_hi);
-      for (int r = rbeg; r < rend; ++r) {
+      const int rbeg = T.own_b[ph], rend = T.own_e[ph];
+      int r = rbeg;
+      for (; r + 1 < rend; r += 2) {
+        const float4 w0 = T.rw[r], w1 = T.rw[r + 1];
+        const float v0 = tile[r * kTX], v1 = tile[(r + 1) * kTX];
+        OSR_FOLD(0, ph, w0, v0);
+        OSR_FOLD(0, ph, w1, v1);
+      }
+      if (r < rend) {
         const float4 w0 = T.rw[r];
-        const float v = tile[(r - r_lo) * kTX];
-        OSR_FOLD(0, ph, w0, v);
+        const float v0 = tile[r * kTX];
+        OSR_FOLD(0, ph, w0, v0);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);
-    if (rb == ntr - 1) {
-      const int c = cb * kTC + warp;
-      if (c < C) {
-#pragma unroll
-        for (int ph = 0; ph < kP; ++ph) Us[ph * LXP + lane] = U[0][ph];
-        __syncwarp();
-        float* outc = out_roi + (int64_t)c * (kP * kP) + lane;
-        if (!sslow) {
-          {
-            const float* up = Us + so[0];
-            float a = sw[0][0] * up[0];
-            a = fmaf(sw[0][1], up[1], a);
-            a = fmaf(sw[0][2], up[2], a);
-            a = fmaf(sw[0][3], up[3], a);
-            outc[0] = a * inv_count;
-          }
-          if (lane + 32 < kP * kP) {
-            const float* up = Us + so[1];
-            float a = sw[1][0] * up[0];
-            a = fmaf(sw[1][1], up[1], a);
-            a = fmaf(sw[1][2], up[2], a);
-            a = fmaf(sw[1][3], up[3], a);
-            outc[32] = a * inv_count;
-          }
-        } else {
-#pragma unroll
-          for (int tt = 0; tt < 2; ++tt) {
-            const int o = lane + 32 * tt;
-            if (o < kP * kP) {
-              const int pw = o % kP;
-              const float* up = Us + so[tt];
-              const float* wp = T.wx + pw * kRB;
-              float a = 0.f;
-              for (int q = 0; q < T.nx[pw]; ++q) a = fmaf(wp[q], up[q], a);
-              outc[32 * tt] = a * inv_count;
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
-    // producer: refill this slot with tile t + kNS once every warp has released it
-    if (warp == 0 && t + kNS < total) {
+    // producer: refill this slot with channel block cb + kNS once every warp has released it
+    if (warp == 0 && cb + kNS < ncb) {
       if (elect_one()) {
         mbar_wait(&empty_bar[slot], parity);
-        const int tn = t + kNS;
-        const int ncb2 = tn / ntr, nrb2 = tn - ncb2 * ntr;
-        tma_load_stage(stages + slot * kStageFloats, map, &full_bar[slot], xmin, T.ymin + nrb2 * kTR, ncb2 * kTC, img, C, H);
+        tma_load_stage(stages + slot * kStageFloats, map, &full_bar[slot], x0, T.ymin, nrb, (cb + kNS) * kTC, img, C, H);
       }
       __syncwarp();
     }
-    if (++rb == ntr) { rb = 0; ++cb; }
+    const int c = cb * kTC + warp;
+    if (c < C) {
+#pragma unroll
+      for (int ph = 0; ph < kP; ++ph) Us[ph * LXP + lane] = U[0][ph];
+      __syncwarp();
+      float* outc = out_roi + (int64_t)c * (kP * kP) + lane;
+      if (!sslow) {
+        {
+          const float* up = Us + so[0];
+          float a = sw[0][0] * up[0];
+          a = fmaf(sw[0][1], up[1], a);
+          a = fmaf(sw[0][2], up[2], a);
+          a = fmaf(sw[0][3], up[3], a);
+          outc[0] = a * inv_count;
+        }
+        if (lane + 32 < kP * kP) {
+          const float* up = Us + so[1];
+          float a = sw[1][0] * up[0];
+          a = fmaf(sw[1][1], up[1], a);
+          a = fmaf(sw[1][2], up[2], a);
+          a = fmaf(sw[1][3], up[3], a);
+          outc[32] = a * inv_count;
+        }
+      } else {
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+          const int o = lane + 32 * tt;
+          if (o < kP * kP) {
+            const int pw = o % kP;
+            const float* up = Us + so[tt];
+            const float* wp = T.wx + pw * kRB;
+            float a = 0.f;
+            for (int q = 0; q < T.nx[pw]; ++q) a = fmaf(wp[q], up[q], a);
+            outc[32 * tt] = a * inv_count;
+          }
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -421,12 +422,16 @@ __device__ __forceinline__ void fwd_wide(const LevelDesc& lv, const Tables& T, f
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid_constant__ FwdParams p,
-                                                                    const __grid_constant__ FwdTma tm) {
-  // dynamic shared memory: [ s_U (32 KB; LDG paths: warp tiles / TMA path: 4 x 8 KB stage ring) | Us_tma | barriers | T ]
+#ifndef OSR_FWD_MINB
+#define OSR_FWD_MINB 3
+#endif
+template <bool kTma>
+__global__ void __launch_bounds__(kThreads, OSR_FWD_MINB) roi_align_fwd_kernel(const __grid_constant__ FwdParams p,
+                                                                               const __grid_constant__ FwdTma tm) {
+  // dynamic shared memory: [ ring (48 KB; LDG paths use its first 32 KB as warp tiles) | Us_tma | barriers | T ]
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* s_U = reinterpret_cast<float*>(smem_raw);
-  float* s_Ut = s_U + kWarps * kWarpTile;                                  // kWarps x 7 x 33 floats
+  float* s_Ut = s_U + p.ring_floats;                                        // kWarps x 7 x 33 floats
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_Ut + kWarps * kP * (kTX + 1) + 8);
   Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNS);
 
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid
       T.wx[i] = 0.f;
     }
     // the staging tiles' pad columns are read (with weight 0) by the fixed 4-tap stage 2: keep them finite
-    for (int i = tid; i < kWarps * kWarpTile + kWarps * kP * (kTX + 1) + 8; i += kThreads) s_U[i] = 0.f;
+    for (int i = tid; i < p.ring_floats + kWarps * kP * (kTX + 1) + 8; i += kThreads) s_U[i] = 0.f;
     __syncthreads();
     if (tid < kP) {
       T.ny[tid] = build_bin_weights(g.start_h, g.bin_h, g.grid_h, lv0.H, tid, T.wy + tid * kRB, &T.yb[tid]);
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_fwd_kernel(const __grid
   float* Us = s_U + (tid >> 5) * kWarpTile;
   const float inv_count = 1.0f / g.count;
   // TMA box starts must be 16-byte aligned in x: start at x0 = xmin rounded down to 4 columns
-  if (path == 0 && p.tma_ok[level] && T.shared_ok && ((xmin & 3) + wf <= kTX)) {
+  if (kTma && path == 0 && p.tma_ok[level] && T.shared_ok && ((xmin & 3) + wf <= kTX) && hf <= kTRmax) {
     fwd_tma(&tm.map[level], T, s_U, s_bar, s_bar + kNS, s_Ut + (tid >> 5) * (kP * (kTX + 1)), C, lv.H, img, xmin & ~3, hf,
             inv_count, out_roi);
   } else if (path == 0) {
@@ -623,8 +628,8 @@ __global__ void __launch_bounds__(kSortThreads) roi_order_kernel(const __grid_co
   for (int m = tid; m < p.M; m += kSortThreads) order[atomicAdd(&hist[keys[m]], 1)] = m;
 }
 
-size_t fwd_smem_bytes() {
-  return (size_t)(kWarps * kWarpTile + kWarps * kP * (kTX + 1) + 8) * 4 + 2 * kNS * 8 + sizeof(Tables) + 16;
+size_t fwd_smem_bytes(int ring_floats) {
+  return (size_t)(ring_floats + kWarps * kP * (kTX + 1) + 8) * 4 + 2 * kNS * 8 + sizeof(Tables) + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -724,12 +729,23 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
       p.order = order;
     }
   }
+  // TMA staging is opt-in (OSR_ROIALIGN_TMA=1): on NCHW maps a footprint row is only ~50-130 bytes, and the TMA unit's
+  // per-row request rate makes it slower than the LDG path (2.20 ms vs 1.71 ms at cfg2 on B200).
   FwdTma tm;
   memset(&tm, 0, sizeof(tm));
-  for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = encode_level_map(&tm.map[l], p.L.lv[l], num_images, C);
-  const size_t smem = fwd_smem_bytes();
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  roi_align_fwd_kernel<<<M, kThreads, smem, s>>>(p, tm);
+  const char* env = getenv("OSR_ROIALIGN_TMA");
+  const bool use_tma = env && env[0] == '1';
+  for (int l = 0; l < num_levels; ++l)
+    p.tma_ok[l] = use_tma ? encode_level_map(&tm.map[l], p.L.lv[l], num_images, C) : 0;
+  p.ring_floats = use_tma ? kRingFloats : kWarps * kWarpTile;
+  const size_t smem = fwd_smem_bytes(p.ring_floats);
+  if (use_tma) {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_fwd_kernel<true><<<M, kThreads, smem, s>>>(p, tm);
+  } else {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_fwd_kernel<false><<<M, kThreads, smem, s>>>(p, tm);
+  }
   OSR_LAUNCH_CHECK();
   return 0;
 }

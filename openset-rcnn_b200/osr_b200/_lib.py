@@ -10,7 +10,7 @@ import threading
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libosr_sm100a.so")
+LIB_PATH = os.environ.get("OSR_LIB_PATH", os.path.join(_HERE, "libosr_sm100a.so"))  # override = A/B builds only
 OSR_MAX_LEVELS = 8
 
 c_i32p = C.POINTER(C.c_int32)
