@@ -323,29 +323,38 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
 }
 
 // Concatenate the per-level runs of each image (find_top_proposals.py:85-87 cat over levels + :108-110 filter).
+// grid (N, kConcatY): every block derives the level prefix from the counts and moves a strided share of the rows.
+constexpr int kConcatY = 16;
 __global__ void __launch_bounds__(256) rpn_concat_kernel(const __grid_constant__ RpnParams p, float* out_boxes,
                                                           float* out_scores, int32_t* out_level,
                                                           int32_t* out_index) {
   const int n = blockIdx.x;
   const int L = p.num_levels;
   int32_t* cnt = p.counts + n * (L + 2);
-  int off = 0;
+  int off[OSR_MAX_LEVELS + 1];
   int flags = 0;
-  for (int l = 0; l < L; ++l) {
-    const int c = cnt[l];
-    const int64_t src = (int64_t)n * p.kmax + p.koff[l];
-    const int64_t dst = (int64_t)n * p.kmax + off;
-    for (int j = threadIdx.x; j < c; j += blockDim.x) {
-      reinterpret_cast<float4*>(out_boxes)[dst + j] = reinterpret_cast<const float4*>(p.st_boxes)[src + j];
-      out_scores[dst + j] = p.st_scores[src + j];
-      out_index[dst + j] = p.st_index[src + j];
-      out_level[dst + j] = l;
-    }
-    off += c;
-    flags |= p.st_flags[n * L + l];
+  off[0] = 0;
+#pragma unroll
+  for (int l = 0; l < OSR_MAX_LEVELS; ++l) {
+    const int c = l < L ? cnt[l] : 0;
+    off[l + 1] = off[l] + c;
+    if (l < L) flags |= p.st_flags[n * L + l];
   }
-  if (threadIdx.x == 0) {
-    cnt[L] = off;
+  const int total = off[L];
+  const int64_t base = (int64_t)n * p.kmax;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < OSR_MAX_LEVELS; ++k) l += (k < L && i >= off[k]) ? 1 : 0;
+    const int64_t src = base + p.koff[l] + (i - off[l]);
+    reinterpret_cast<float4*>(out_boxes)[base + i] = reinterpret_cast<const float4*>(p.st_boxes)[src];
+    out_scores[base + i] = p.st_scores[src];
+    out_index[base + i] = p.st_index[src];
+    out_level[base + i] = l;
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    // written last in program order by this thread only; other blocks never read cnt[L], cnt[L+1]
+    cnt[L] = total;
     cnt[L + 1] = flags;
   }
 }
@@ -436,7 +445,7 @@ int osr_rpn_select_decode(const osr_rpn_level_t* h_levels, int num_levels, int n
   OSR_CUDA_CHECK(cudaFuncSetAttribute(rpn_select_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rpn_select_decode_kernel<<<num_images * num_levels * kCluster, kThreads, smem, s>>>(p);
   OSR_LAUNCH_CHECK();
-  rpn_concat_kernel<<<num_images, 256, 0, s>>>(p, out_boxes, out_scores, out_level, out_index);
+  rpn_concat_kernel<<<dim3(num_images, kConcatY), 256, 0, s>>>(p, out_boxes, out_scores, out_level, out_index);
   OSR_LAUNCH_CHECK();
   return 0;
 }
