@@ -284,7 +284,7 @@ def run_ours(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "images_per_gpu": N, "global_batch": world * N, "image_hw": list(cfg.image_hw),
+        "config": {"workload": WORKLOAD, "pln_encoder": "bf16 tcgen05, fp32 accumulate (all other arithmetic fp32)", "images_per_gpu": N, "global_batch": world * N, "image_hw": list(cfg.image_hw),
                    "pre_nms_topk_per_level": cfg.pre_nms_topk, "rois_per_image": cfg.rois_per_image,
                    "feature_layout": "channels_last" if cfg.channels_last else "NCHW",
                    "proposal_mode": "as_shipped (find_top_proposals.py:112-120 commented out)",

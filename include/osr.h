@@ -176,6 +176,15 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * PLN encoder on tensor cores: emb[R,E] = x[R,F] . W[E,F]^T + bias   (prototype_learning_network.py:133, nn.Linear)
+ * bf16 operands (x and W are cast from fp32 into the workspace), fp32 accumulation in TMEM (tcgen05.mma), fp32 output.
+ * F must be a multiple of 64, E a multiple of 128 (1024 / 256 in the reference).  bias may be NULL.
+ */
+size_t osr_pln_encode_workspace(int R, int F, int E);
+int osr_pln_encode_fwd(const float* x, const float* W, const float* bias, int R, int F, int E, float* emb,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * PLN.inference nearest-prototype classification (prototype_learning_network.py:203-226), all images at once:
  *   pred[i] = class of the nearest prototype of normalize(emb[i]) (min over the reps of a class first),
  *   mapped through class_id_map (K int64, may be NULL = identity; the reference's self.class_id for GraspNet),

@@ -7,7 +7,7 @@ Training step (BASELINE.json configs[1]):
   S3  ROIPooler forward            osr_roi_align_fwd            (osrcnn_roi_heads.py:306)
   S4  box head FC                  NOT on the path (library GEMM, osrcnn_roi_heads.py:308): a fixed (R,1024) tensor
                                    stands in for its output and a fixed (M,C,7,7) tensor for its input gradient
-  S5  PLN loss forward + backward  encoder nn.Linear + osr_pln_loss_fwd / _bwd (osrcnn_roi_heads.py:315)
+  S5  PLN loss forward + backward  encoder GEMM (osr_pln_encode_fwd, tcgen05 bf16) + osr_pln_loss_fwd / _bwd (osrcnn_roi_heads.py:315)
   S3' ROIPooler backward           osr_roi_align_bwd            (train.py:145)
 """
 from __future__ import annotations
@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 from . import _lib, synth
 from .poolers import ROIPooler
-from .pln import pln_loss_from_emb
+from .pln import pln_encode_tc, pln_loss_from_emb
 from .proposals import rpn_select_decode
 
 
@@ -40,6 +40,7 @@ class PathConfig:
     loss_weight: float = 0.5
     iou_threshold: float = 0.5
     channels_last: bool = False
+    encoder_impl: str = "tcgen05"   # PLN encoder: bf16 tensor cores (fp32 accumulate) | "fp32" = nn.Linear as the reference
     seed: int = 1234
 
 
@@ -133,7 +134,10 @@ class RoiPathStep:
         self._mark(3)
         # S5: encoder (nn.Linear) + prototype loss forward + backward to (emb, representatives)
         pi = self.pln
-        emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+        if cfg.encoder_impl == "tcgen05":
+            emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+        else:
+            emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
         reps = pi.reps.requires_grad_(True)
         loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, num_known_classes=cfg.num_known,
                                  alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,

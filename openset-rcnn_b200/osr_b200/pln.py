@@ -77,6 +77,43 @@ class _PlnLossFn(torch.autograd.Function):
         return grad_emb, grad_reps, None, None, None
 
 
+class _EncodeTcFn(torch.autograd.Function):
+    """emb = x @ W^T + b on tcgen05 tensor cores (bf16 operands, fp32 accumulate).  Backward: the two ordinary GEMMs
+    (grad_x = g @ W, grad_W = g^T @ x) are library calls, like the reference's nn.Linear backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = _lib.lib()
+        _lib.require_cuda(x, weight)
+        xc = x.contiguous().float()
+        wc = weight.contiguous().float()
+        bc = None if bias is None else bias.contiguous().float()
+        R, Fd = xc.shape
+        E = wc.shape[0]
+        emb = torch.empty((R, E), dtype=torch.float32, device=xc.device)
+        ws = torch.empty(max(int(lib.osr_pln_encode_workspace(R, Fd, E)), 256), dtype=torch.uint8, device=xc.device)
+        rc = lib.osr_pln_encode_fwd(xc.data_ptr(), wc.data_ptr(), _lib.ptr(bc), R, Fd, E, emb.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _lib.stream_ptr(xc.device))
+        _lib.check(rc, "osr_pln_encode_fwd")
+        ctx.save_for_backward(xc, wc)
+        ctx.has_bias = bias is not None
+        return emb
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        gx = g @ w if ctx.needs_input_grad[0] else None
+        gw = g.t() @ x if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
+def pln_encode_tc(x, weight, bias=None):
+    """Tensor-core encoder (``PLN.encoder`` forward): bf16 x bf16 -> fp32."""
+    return _EncodeTcFn.apply(x, weight, bias)
+
+
 def pln_loss_from_emb(emb, reps, labels, ious, *, num_known_classes: int, reps_per_class: int = 1,
                       alpha: float = 0.1, beta: float = 0.9, loss_weight: float = 0.5, iou_threshold: float = 0.5,
                       r_norm: Optional[float] = None, center_weight: float = 1.0, emb_grad_scale: float = 1.0):
@@ -110,7 +147,7 @@ class PLN(nn.Module):
                  distance_type: str, reps_per_class: int, alpha: float, beta: float, loss_weight: float,
                  dataset_name: str = "", iou_threshold: float = 0.5, unk_thr: float = 0.23,
                  opendet_benchmark: bool = True, known_class_ids: Optional[Sequence[int]] = None,
-                 device="cuda", gather: bool = False, process_group=None):
+                 device="cuda", gather: bool = False, process_group=None, encoder_impl: str = "fp32"):
         super().__init__()
         if distance_type != "COS":
             raise NotImplementedError(
@@ -130,6 +167,9 @@ class PLN(nn.Module):
         self.iou_threshold = iou_threshold
         self.gather = gather
         self.process_group = process_group
+        # "fp32": nn.Linear exactly as the reference; "tcgen05": bf16 tensor-core GEMM (fp32 accumulate), ~3e-3 relative
+        assert encoder_impl in ("fp32", "tcgen05")
+        self.encoder_impl = encoder_impl
 
         self.encoder = nn.Linear(feature_dim, embedding_dim, device=device)
         nn.init.normal_(self.encoder.weight, std=0.01)
@@ -174,7 +214,10 @@ class PLN(nn.Module):
 
     # -- training ------------------------------------------------------------------------------------------
     def loss_from_tensors(self, roi_features: torch.Tensor, gt_classes: torch.Tensor, ious: torch.Tensor):
-        emb_features = self.encoder(roi_features)            # :133
+        if self.encoder_impl == "tcgen05":
+            emb_features = pln_encode_tc(roi_features, self.encoder.weight, self.encoder.bias)   # :133 on tensor cores
+        else:
+            emb_features = self.encoder(roi_features)        # :133
         rec_features = self.decoder(emb_features)            # :135
         if not self.opendet_benchmark:
             gt_classes = self.id_map[gt_classes]             # :146-147

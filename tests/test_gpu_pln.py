@@ -122,3 +122,34 @@ def test_inference_matches_oracle():
             assert torch.equal(inst.pred_classes, pred)
             torch.testing.assert_close(inst.features, rec)
         assert any((o.pred_classes == 80).any() for o in out if len(o)) and any((o.pred_classes < 20).any() for o in out if len(o))
+
+
+@pytest.mark.parametrize("R", [8192, 1000, 128, 77])
+def test_tcgen05_encoder_matches_bf16_reference(R):
+    """tcgen05 encoder GEMM: bit-for-bit operands = bf16(x), bf16(W); fp32 accumulate.  Compared against the same bf16
+    operands multiplied in fp32 by torch (tolerance = fp32 summation order only) and against the fp32 nn.Linear
+    (tolerance = bf16 operand rounding, rtol 2e-2 on |emb| ~ 0.2)."""
+    from osr_b200 import synth
+    from osr_b200.pln import pln_encode_tc
+    pi = synth.make_pln_inputs(R, seed=R, device="cuda:0")
+    bias = torch.randn(256, device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(1)) * 0.01
+    got = pln_encode_tc(pi.roi_features, pi.enc_w, bias)
+    ref_bf16 = pi.roi_features.bfloat16().float() @ pi.enc_w.bfloat16().float().t() + bias
+    torch.testing.assert_close(got, ref_bf16, rtol=1e-4, atol=1e-5)
+    ref_fp32 = torch.nn.functional.linear(pi.roi_features, pi.enc_w, bias)
+    torch.testing.assert_close(got, ref_fp32, rtol=2e-2, atol=3e-3)
+
+
+def test_tcgen05_encoder_in_module_loss_and_grads():
+    from osr_b200 import synth
+    from osr_b200.pln import PLN
+    torch.manual_seed(0)
+    m = PLN(81, 20, 1024, 256, "COS", 1, 0.1, 0.9, 0.5, opendet_benchmark=True, encoder_impl="tcgen05")
+    m32 = PLN(81, 20, 1024, 256, "COS", 1, 0.1, 0.9, 0.5, opendet_benchmark=True)
+    m32.load_state_dict(m.state_dict())
+    pi = synth.make_pln_inputs(2048, seed=12, device="cuda:0")
+    _, _, l_tc = m.loss_from_tensors(pi.roi_features, pi.gt_classes, pi.ious)
+    _, _, l_32 = m32.loss_from_tensors(pi.roi_features, pi.gt_classes, pi.ious)
+    torch.testing.assert_close(l_tc, l_32, rtol=2e-2, atol=1e-4)   # bf16 operands: stated tolerance of the north star
+    l_tc.backward()
+    assert m.encoder.weight.grad is not None and torch.isfinite(m.encoder.weight.grad).all()
