@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   const int C = p.L.C;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.grad_out) & 15) == 0) && ((C * kP * kP) % 4 == 0);
+  const bool nhwc_vec = (lv.sC == 1) && ((lv.sW & 3) == 0) && ((lv.sH & 3) == 0) && ((lv.sN & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
 
   // first batch; if it covers the whole image's RoI range the tables are built once and reused by every channel pass
   collect_batch(p, S, level, tx0, ty0, r0, r1);
@@ -289,8 +291,13 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid
     const int nb = S.nb;
     const int nchunks = ceil_div(C, kCC);
     if (nb == 0) {  // untouched tile: zero fill
-      if (inside)
-        for (int c = 0; c < C; ++c) gpix[(int64_t)c * lv.sC] = 0.f;
+      if (inside) {
+        if (nhwc_vec && (C & 3) == 0) {
+          for (int c = 0; c < C; c += 4) *reinterpret_cast<float4*>(gpix + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int c = 0; c < C; ++c) gpix[(int64_t)c * lv.sC] = 0.f;
+        }
+      }
       return;
     }
     const int ngroups = ceil_div(nb, kG);
@@ -315,9 +322,15 @@ __global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid
       accumulate_group(S, st & 1, grp * kG, min(kG, nb - grp * kG), ty, tx, acc);
       if (grp == ngroups - 1 && inside) {
         const int c0 = chunk * kCC;
+        if (nhwc_vec && c0 + kCC <= C) {   // channels_last gradient: 4 x 16-byte stores per pixel and pass
 #pragma unroll
-        for (int c = 0; c < kCC; ++c)
-          if (c0 + c < C) gpix[(int64_t)(c0 + c) * lv.sC] = acc[c];
+          for (int c = 0; c < kCC; c += 4)
+            *reinterpret_cast<float4*>(gpix + c0 + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCC; ++c)
+            if (c0 + c < C) gpix[(int64_t)(c0 + c) * lv.sC] = acc[c];
+        }
       }
       __syncthreads();
       if (++grp == ngroups) { grp = 0; ++chunk; }

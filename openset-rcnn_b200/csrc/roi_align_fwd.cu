@@ -577,6 +577,257 @@ __global__ void __launch_bounds__(kThreads, OSR_FWD_MINB) roi_align_fwd_kernel(c
   }
 }
 
+// =========================================================================================================
+// channels_last (NHWC) forward: the layout the north star asks for ("coalesced NHWC reads").  A footprint row of a
+// channels_last map is ONE contiguous run of wf*C floats (22 KB for a 22-pixel-wide RoI at C = 256), so it is streamed
+// with a single cp.async.bulk (UBLKCP) per row into a 2-stage shared-memory ring guarded by mbarriers; no address
+// arithmetic, no sector waste, tens of KB in flight per CTA.  Thread t owns channel t and keeps all 49 outputs of the RoI
+// in registers:  per row  U[pw] = sum_x Wx[pw][x] * row[x][c]   (conflict-free LDS: consecutive threads, consecutive floats)
+//                then     out[ph][pw] += Wy[ph][y] * U[pw]      for the <= 3 bins containing the row (uniform switch).
+// The 49 x C tile is transposed through shared memory and stored with 16-byte coalesced writes (C-major output).
+constexpr int kNhwcCols = 32;   // columns per x chunk (wider footprints loop over chunks)
+constexpr int kNhwcStages = 3;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const __grid_constant__ FwdParams p) {
+  // dynamic smem: [ ring: kNhwcStages x (32 cols x C floats) (re-used as the 49 x C output tile) | barriers | T ]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  const int C = p.L.C;
+  const int stage_floats = kNhwcCols * C;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(ring + p.ring_floats);
+  Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNhwcStages);
+  uint64_t* full_bar = s_bar;
+  uint64_t* empty_bar = s_bar + kNhwcStages;
+
+  const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* roi = p.rois + (int64_t)m * 5;
+  const float fimg = __ldg(roi), x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
+  const int img = (int)fimg;
+  const int level = assign_level(x1, y1, x2, y2, p.L);
+  if (tid == 0) p.out_level[m] = level;
+  float* out_roi = p.out + (int64_t)m * C * (kP * kP);
+
+  const bool zero = (level < 0) || (level >= p.L.num_levels) || (img < 0) || (img >= p.L.num_images);
+  RoiGeom g;
+  int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+  bool overflow = false;
+  if (!zero) {
+    const LevelDesc& lv0 = p.L.lv[level];
+    g = roi_geometry(x1, y1, x2, y2, lv0.scale, p.L.sampling_ratio);
+    for (int i = tid; i < kP * kRB; i += kThreads) {
+      T.wy[i] = 0.f;
+      T.wx[i] = 0.f;
+    }
+    __syncthreads();
+    if (tid < kP) {
+      T.ny[tid] = build_bin_weights(g.start_h, g.bin_h, g.grid_h, lv0.H, tid, T.wy + tid * kRB, &T.yb[tid]);
+    } else if (tid >= 32 && tid < 32 + kP) {
+      const int pw = tid - 32;
+      T.nx[pw] = build_bin_weights(g.start_w, g.bin_w, g.grid_w, lv0.W, pw, T.wx + pw * kRB, &T.xb[pw]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kP; ++i) {
+      const int nx = T.nx[i], ny = T.ny[i];
+      overflow |= (nx < 0) | (ny < 0);
+      if (nx > 0) { xmin = min(xmin, T.xb[i]); xmax = max(xmax, T.xb[i] + nx - 1); }
+      if (ny > 0) { ymin = min(ymin, T.yb[i]); ymax = max(ymax, T.yb[i] + ny - 1); }
+    }
+  }
+  const int wf = xmax - xmin + 1, hf = ymax - ymin + 1;
+  if (zero || (!overflow && (xmax < 0 || ymax < 0))) {
+    for (int o = tid; o < C * kP * kP; o += kThreads) out_roi[o] = 0.f;
+    return;
+  }
+  const LevelDesc& lv = p.L.lv[level];
+  const float* img_base = lv.data + (int64_t)img * lv.sN;
+  if (overflow || hf > kMaxRows) {
+    // generic: torchvision's per-sample loop (any strides)
+    for (int o = tid; o < C * kP * kP; o += kThreads) {
+      const int c = o / (kP * kP);
+      const int rem = o - c * (kP * kP);
+      const int ph = rem / kP, pw = rem - ph * kP;
+      const float* plane = img_base + (int64_t)c * lv.sC;
+      float s = 0.f;
+      for (int iy = 0; iy < g.grid_h; ++iy) {
+        const float y = g.start_h + ph * g.bin_h + (iy + 0.5f) * g.bin_h / (float)g.grid_h;
+        for (int ix = 0; ix < g.grid_w; ++ix) {
+          const float x = g.start_w + pw * g.bin_w + (ix + 0.5f) * g.bin_w / (float)g.grid_w;
+          s += bilinear_sample(plane, lv.sH, lv.sW, lv.H, lv.W, y, x);
+        }
+      }
+      out_roi[o] = s / g.count;
+    }
+    return;
+  }
+  // row -> bins table (same as the NCHW shared-row form): rw[r] = (w(ph0), w(ph0+1), w(ph0+2), ph0); rows that sit in
+  // more than 3 bins (bins narrower than half a pixel) carry ph0 = -1 and are folded densely from wy.
+  for (int r = tid; r < hf; r += kThreads) {
+    const int y = ymin + r;
+    int ph0 = -1, cnt = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < kP; ++ph) {
+      const int rr = y - T.yb[ph];
+      if (rr >= 0 && rr < T.ny[ph]) {
+        if (ph0 < 0) ph0 = ph;
+        const int d = ph - ph0;
+        const float wv = T.wy[ph * kRB + rr];
+        if (d == 0) w0 = wv;
+        else if (d == 1) w1 = wv;
+        else if (d == 2) w2 = wv;
+        else cnt = 99;
+      }
+    }
+    T.rw[r] = make_float4(w0, w1, w2, __int_as_float(cnt == 99 ? -1 : (ph0 < 0 ? kP : ph0)));
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kNhwcStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  float acc[kP][kP];
+#pragma unroll
+  for (int a = 0; a < kP; ++a)
+#pragma unroll
+    for (int b = 0; b < kP; ++b) acc[a][b] = 0.f;
+
+  const int nxc = ceil_div(wf, kNhwcCols);
+  const int total = nxc * hf;          // (x chunk, row) tiles, chunk-major
+  const int c = tid;                   // my channel (C <= 256 enforced by the host)
+  const bool cin = c < C;
+  // register-resident taps for the common case (one x chunk, every bin touches <= 4 columns).  Taps past nx carry
+  // weight 0 and re-read the bin's last valid column (finite data), so no predicates are needed in the row loop.
+  bool fast_taps = (nxc == 1) && cin;
+  float tw[kP][4];
+  int toff[kP], tstep[kP][3];
+#pragma unroll
+  for (int pw = 0; pw < kP; ++pw) {
+    const int nx = T.nx[pw];
+    fast_taps = fast_taps && (nx <= 4);
+    const int x0 = nx > 0 ? T.xb[pw] - xmin : 0;
+    toff[pw] = x0 * C;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tw[pw][q] = (q < nx) ? T.wx[pw * kRB + q] : 0.f;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) tstep[pw][q - 1] = min(q, max(nx - 1, 0)) * C;
+  }
+  fast_taps = __syncthreads_and(fast_taps || !cin) && (nxc == 1);
+  // producer prologue
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int t = 0; t < min(kNhwcStages, total); ++t) {
+        const int xc = t / hf, r = t - xc * hf;
+        const int ncols = min(kNhwcCols, wf - xc * kNhwcCols);
+        const uint32_t bytes = (uint32_t)(ncols * C * 4);
+        mbar_expect_tx(&full_bar[t], bytes);
+        bulk_load_1d(ring + t * stage_floats, img_base + ((int64_t)(ymin + r) * lv.sH + (int64_t)(xmin + xc * kNhwcCols) * lv.sW), bytes, &full_bar[t]);
+      }
+    }
+    __syncwarp();
+  }
+  int xc = 0, r = 0;
+  for (int t = 0; t < total; ++t) {
+    const int slot = t % kNhwcStages;
+    const uint32_t parity = (uint32_t)((t / kNhwcStages) & 1);
+    mbar_wait(&full_bar[slot], parity);
+    const float* row = ring + slot * stage_floats + c;
+    const int x_lo = xmin + xc * kNhwcCols, x_hi = min(xmin + wf, x_lo + kNhwcCols);
+    // x contraction of this row (chunk): U[pw] = sum_x Wx[pw][x] * row[x][c]
+    float U[kP];
+    if (fast_taps) {
+      // single chunk, <= 4 taps per bin: fully unrolled, tap weights and column offsets live in registers
+#pragma unroll
+      for (int pw = 0; pw < kP; ++pw) {
+        const float* rp = row + toff[pw];
+        float u = tw[pw][0] * rp[0];
+        u = fmaf(tw[pw][1], rp[tstep[pw][0]], u);
+        u = fmaf(tw[pw][2], rp[tstep[pw][1]], u);
+        u = fmaf(tw[pw][3], rp[tstep[pw][2]], u);
+        U[pw] = u;
+      }
+    } else {
+#pragma unroll
+      for (int pw = 0; pw < kP; ++pw) {
+        float u = 0.f;
+        const int xb = T.xb[pw];
+        const int q0 = max(0, x_lo - xb), q1 = min(T.nx[pw], x_hi - xb);
+        for (int q = q0; q < q1; ++q) u = fmaf(T.wx[pw * kRB + q], cin ? row[(xb + q - x_lo) * C] : 0.f, u);
+        U[pw] = u;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);
+    // refill the slot with tile t + stages once every warp has released it
+    if (warp == 0 && t + kNhwcStages < total) {
+      if (elect_one()) {
+        mbar_wait(&empty_bar[slot], parity);
+        const int tn = t + kNhwcStages;
+        const int nxc2 = tn / hf, nr2 = tn - nxc2 * hf;
+        const int ncols = min(kNhwcCols, wf - nxc2 * kNhwcCols);
+        const uint32_t bytes = (uint32_t)(ncols * C * 4);
+        mbar_expect_tx(&full_bar[slot], bytes);
+        bulk_load_1d(ring + slot * stage_floats, img_base + ((int64_t)(ymin + nr2) * lv.sH + (int64_t)(xmin + nxc2 * kNhwcCols) * lv.sW), bytes, &full_bar[slot]);
+      }
+      __syncwarp();
+    }
+    // y fold: the row feeds the <= 3 consecutive bins that contain it (bin index is CTA-uniform)
+    const float4 w = T.rw[r];
+    switch (__float_as_int(w.w)) {
+#define OSR_NHWC_CASE(PH)                                                                                   \
+  case PH:                                                                                                  \
+    _Pragma("unroll") for (int pw = 0; pw < kP; ++pw) {                                                     \
+      acc[PH][pw] = fmaf(w.x, U[pw], acc[PH][pw]);                                                          \
+      if (PH + 1 < kP) acc[PH + 1 < kP ? PH + 1 : 0][pw] = fmaf(w.y, U[pw], acc[PH + 1 < kP ? PH + 1 : 0][pw]); \
+      if (PH + 2 < kP) acc[PH + 2 < kP ? PH + 2 : 0][pw] = fmaf(w.z, U[pw], acc[PH + 2 < kP ? PH + 2 : 0][pw]); \
+    }                                                                                                       \
+    break;
+      OSR_NHWC_CASE(0) OSR_NHWC_CASE(1) OSR_NHWC_CASE(2) OSR_NHWC_CASE(3) OSR_NHWC_CASE(4) OSR_NHWC_CASE(5) OSR_NHWC_CASE(6)
+#undef OSR_NHWC_CASE
+      case -1: {  // row inside more than 3 bins: dense fold from the per-bin tables
+        const int y = ymin + r;
+#pragma unroll
+        for (int ph = 0; ph < kP; ++ph) {
+          const int rr = y - T.yb[ph];
+          const float wy = (rr >= 0 && rr < T.ny[ph]) ? T.wy[ph * kRB + rr] : 0.f;
+#pragma unroll
+          for (int pw = 0; pw < kP; ++pw) acc[ph][pw] = fmaf(wy, U[pw], acc[ph][pw]);
+        }
+        break;
+      }
+      default: break;
+    }
+    if (++r == hf) { r = 0; ++xc; }
+  }
+  // epilogue: 49 x C tile -> shared memory as [c][49] (stride 49 is odd: conflict-free) -> coalesced 16-byte stores
+  __syncthreads();   // every warp is done with the ring (all bulk loads have landed and been consumed)
+  const float inv_count = 1.0f / g.count;
+  if (cin) {
+    float* o = ring + c * (kP * kP);
+#pragma unroll
+    for (int a = 0; a < kP; ++a)
+#pragma unroll
+      for (int b = 0; b < kP; ++b) o[a * kP + b] = acc[a][b] * inv_count;
+  }
+  __syncthreads();
+  const int n4 = (C * kP * kP) >> 2;
+  if ((((uintptr_t)out_roi) & 15) == 0 && ((C * kP * kP) & 3) == 0) {
+    for (int i = tid; i < n4; i += kThreads) reinterpret_cast<float4*>(out_roi)[i] = reinterpret_cast<const float4*>(ring)[i];
+  } else {
+    for (int i = tid; i < C * kP * kP; i += kThreads) out_roi[i] = ring[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Processing order: RoIs bucketed by (image, level, y band) with a single-CTA counting sort, so that CTAs that
 // run concurrently read neighbouring feature rows (L2-resident working set instead of a whole image's pyramid).
@@ -731,6 +982,22 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
   }
   // TMA staging is opt-in (OSR_ROIALIGN_TMA=1): on NCHW maps a footprint row is only ~50-130 bytes, and the TMA unit's
   // per-row request rate makes it slower than the LDG path (2.20 ms vs 1.71 ms at cfg2 on B200).
+  // channels_last maps (sC == 1, a pixel's C channels contiguous, 16-byte aligned) take the bulk-copy NHWC kernel
+  bool nhwc = (C <= kThreads) && (C % 4 == 0);
+  for (int l = 0; l < num_levels && nhwc; ++l) {
+    const LevelDesc& lv = p.L.lv[l];
+    nhwc = lv.sC == 1 && lv.sW == C && lv.sH == (int64_t)lv.W * C && (lv.sN % 4 == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
+  }
+  if (nhwc) {
+    const int ring = kNhwcStages * kNhwcCols * C > kP * kP * C ? kNhwcStages * kNhwcCols * C : kP * kP * C;
+    p.ring_floats = (ring + 31) & ~31;
+    for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = 0;
+    const size_t smem = (size_t)p.ring_floats * 4 + 2 * kNhwcStages * 8 + sizeof(Tables) + 16;
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    roi_align_fwd_nhwc_kernel<<<M, kThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+    return 0;
+  }
   FwdTma tm;
   memset(&tm, 0, sizeof(tm));
   const char* env = getenv("OSR_ROIALIGN_TMA");
