@@ -196,7 +196,7 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.lib()  # fail loudly if the extension is missing
-    cfg = PathConfig(channels_last=args.channels_last, seed=1234 + 1000 * 2 + rank)
+    cfg = PathConfig(channels_last=not args.nchw, seed=1234 + 1000 * 2 + rank)
     N = cfg.num_images
     path = RoiPathStep(cfg, dev)
 
@@ -253,6 +253,24 @@ def run_ours(args, rank, local_rank, world):
                                "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak},
             "stages": per_stage, "touched_feature_pixels": U}
 
+    # ---- the other feature layout, short run (same inputs, same code path selection rules) --------------
+    alt = None
+    if rank == 0 or world > 1:
+        alt_feats = [f.contiguous() if cfg.channels_last else f.contiguous(memory_format=torch.channels_last) for f in path.feats]
+        for _ in range(3):
+            path.step(feats=alt_feats)
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            path.step(feats=alt_feats)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        alt_ms = a0.elapsed_time(a1) / 5
+        alt = {"feature_layout": "NCHW" if cfg.channels_last else "channels_last", "ms_per_step": alt_ms,
+               "value_per_gpu": N * 1e3 / alt_ms, "steps": 5}
+        del alt_feats
+
     # ---- end to end: inputs start in pinned host memory every step ----------------------------------
     del path
     torch.cuda.empty_cache()
@@ -293,7 +311,7 @@ def run_ours(args, rank, local_rank, world):
                                    "fwd/bwd, S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))",
                    "parallelism": f"dp{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-        "stage_ms": stages,
+        "stage_ms": stages, "alt_layout": alt,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg)
@@ -306,7 +324,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--channels-last", action="store_true", help="feed channels_last FPN maps (default: NCHW, the reference layout)")
+    ap.add_argument("--nchw", action="store_true",
+                    help="feed NCHW-contiguous FPN maps (the reference's layout) instead of channels_last (the north star's "
+                         "'coalesced NHWC reads'; what a channels_last backbone emits); the other layout is reported under 'alt_layout'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

@@ -39,7 +39,7 @@ class PathConfig:
     beta: float = 0.9
     loss_weight: float = 0.5
     iou_threshold: float = 0.5
-    channels_last: bool = False
+    channels_last: bool = True    # FPN maps in channels_last (NHWC) memory format; False = NCHW as the reference
     encoder_impl: str = "tcgen05"   # PLN encoder: bf16 tensor cores (fp32 accumulate) | "fp32" = nn.Linear as the reference
     seed: int = 1234
 
@@ -66,7 +66,8 @@ class RoiPathStep:
             # pinned host copies of the step's inputs; two device buffer sets for copy/compute overlap
             self.h_deltas = [d.pin_memory() for d in ho.deltas]
             self.h_ctr = [c.pin_memory() for c in ho.centerness]
-            self.h_feats = [f.pin_memory() for f in synth.make_features(N, cfg.image_hw, cfg.channels, seed=feats_seed)]
+            self.h_feats = [f.pin_memory() for f in synth.make_features(N, cfg.image_hw, cfg.channels, seed=feats_seed,
+                                                                        channels_last=cfg.channels_last)]
             self.dev_sets = []
             for _ in range(2):
                 self.dev_sets.append(dict(

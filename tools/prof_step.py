@@ -13,9 +13,9 @@ from osr_b200.pipeline import PathConfig, RoiPathStep  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--images", type=int, default=16)
-ap.add_argument("--channels-last", action="store_true")
+ap.add_argument("--nchw", action="store_true")
 a = ap.parse_args()
-path = RoiPathStep(PathConfig(num_images=a.images, channels_last=a.channels_last, seed=3234), "cuda:0")
+path = RoiPathStep(PathConfig(num_images=a.images, channels_last=not a.nchw, seed=3234), "cuda:0")
 for _ in range(a.steps):
     path.step()
 torch.cuda.synchronize()
