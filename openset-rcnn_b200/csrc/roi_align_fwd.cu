@@ -65,6 +65,7 @@ struct Tables {
   float4 rw[kMaxRows];  // (w for bin ph0, ph0+1, ph0+2, unused)
   int own_b[kP], own_e[kP];
   int ymin, hf, shared_ok;
+  float4 wt[kP][2];   // x-tap weights of each bin padded to 8 taps (NHWC kernel)
 };
 
 // fold one loaded value into bins PH, PH+1, PH+2 (indices are compile-time after unrolling; guards keep them in range)
@@ -593,11 +594,12 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+template <int kC>   // kC > 0: compile-time channel count (immediate LDS offsets); 0: run-time C
 __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const __grid_constant__ FwdParams p) {
   // dynamic smem: [ ring: kNhwcStages x (32 cols x C floats) (re-used as the 49 x C output tile) | barriers | T ]
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
-  const int C = p.L.C;
+  const int C = kC > 0 ? kC : p.L.C;
   const int stage_floats = kNhwcCols * C;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(ring + p.ring_floats);
   Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNhwcStages);
@@ -706,23 +708,23 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   const int total = nxc * hf;          // (x chunk, row) tiles, chunk-major
   const int c = tid;                   // my channel (C <= 256 enforced by the host)
   const bool cin = c < C;
-  // register-resident taps for the common case (one x chunk, every bin touches <= 4 columns).  Taps past nx carry
-  // weight 0 and re-read the bin's last valid column (finite data), so no predicates are needed in the row loop.
-  bool fast_taps = (nxc == 1) && cin;
-  float tw[kP][4];
-  int toff[kP], tstep[kP][3];
+  // Common case (one x chunk): every bin's x taps are padded to 8 with zero weights (T.wt), so the row loop is fully
+  // unrolled and predicate-free; padded taps read finite data (the ring is zero-initialised once and only ever holds
+  // feature values; 8 columns of slack follow the last stage).
+  const bool fast_taps = (nxc == 1);
+  int toff[kP];
 #pragma unroll
-  for (int pw = 0; pw < kP; ++pw) {
-    const int nx = T.nx[pw];
-    fast_taps = fast_taps && (nx <= 4);
-    const int x0 = nx > 0 ? T.xb[pw] - xmin : 0;
-    toff[pw] = x0 * C;
+  for (int pw = 0; pw < kP; ++pw) toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
+  if (tid < kP) {
+    float w8[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) tw[pw][q] = (q < nx) ? T.wx[pw * kRB + q] : 0.f;
-#pragma unroll
-    for (int q = 1; q < 4; ++q) tstep[pw][q - 1] = min(q, max(nx - 1, 0)) * C;
+    for (int q = 0; q < 8; ++q) w8[q] = (q < T.nx[tid]) ? T.wx[tid * kRB + q] : 0.f;
+    T.wt[tid][0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+    T.wt[tid][1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
   }
-  fast_taps = __syncthreads_and(fast_taps || !cin) && (nxc == 1);
+  for (int i = tid; i < (p.ring_floats >> 2); i += kThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic zero-fill before async-proxy bulk writes
+  __syncthreads();
   // producer prologue
   if (warp == 0) {
     if (elect_one()) {
@@ -746,14 +748,19 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     // x contraction of this row (chunk): U[pw] = sum_x Wx[pw][x] * row[x][c]
     float U[kP];
     if (fast_taps) {
-      // single chunk, <= 4 taps per bin: fully unrolled, tap weights and column offsets live in registers
+      const float* rowc = ring + slot * stage_floats + min(c, C - 1);
 #pragma unroll
       for (int pw = 0; pw < kP; ++pw) {
-        const float* rp = row + toff[pw];
-        float u = tw[pw][0] * rp[0];
-        u = fmaf(tw[pw][1], rp[tstep[pw][0]], u);
-        u = fmaf(tw[pw][2], rp[tstep[pw][1]], u);
-        u = fmaf(tw[pw][3], rp[tstep[pw][2]], u);
+        const float* rp = rowc + toff[pw];
+        const float4 wa = T.wt[pw][0], wb = T.wt[pw][1];
+        float u = wa.x * rp[0];
+        u = fmaf(wa.y, rp[1 * C], u);
+        u = fmaf(wa.z, rp[2 * C], u);
+        u = fmaf(wa.w, rp[3 * C], u);
+        u = fmaf(wb.x, rp[4 * C], u);
+        u = fmaf(wb.y, rp[5 * C], u);
+        u = fmaf(wb.z, rp[6 * C], u);
+        u = fmaf(wb.w, rp[7 * C], u);
         U[pw] = u;
       }
     } else {
@@ -989,12 +996,18 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
     nhwc = lv.sC == 1 && lv.sW == C && lv.sH == (int64_t)lv.W * C && (lv.sN % 4 == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
   }
   if (nhwc) {
-    const int ring = kNhwcStages * kNhwcCols * C > kP * kP * C ? kNhwcStages * kNhwcCols * C : kP * kP * C;
+    int ring = (kNhwcStages * kNhwcCols + 8) * C;              // + 8 columns of slack for the zero-weight padded taps
+    if (ring < kP * kP * C) ring = kP * kP * C;                 // the ring doubles as the 49 x C output tile
     p.ring_floats = (ring + 31) & ~31;
     for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = 0;
     const size_t smem = (size_t)p.ring_floats * 4 + 2 * kNhwcStages * 8 + sizeof(Tables) + 16;
-    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    roi_align_fwd_nhwc_kernel<<<M, kThreads, smem, s>>>(p);
+    if (C == 256) {
+      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_fwd_nhwc_kernel<256><<<M, kThreads, smem, s>>>(p);
+    } else {
+      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_fwd_nhwc_kernel<0><<<M, kThreads, smem, s>>>(p);
+    }
     OSR_LAUNCH_CHECK();
     return 0;
   }
