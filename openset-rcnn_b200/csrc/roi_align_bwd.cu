@@ -23,7 +23,7 @@ using namespace osr;
 
 constexpr int kTH = 16, kTW = 16;       // tile
 constexpr int kThreads = kTH * kTW;     // one thread per tile pixel
-constexpr int kCC = 16;                 // channels accumulated in registers per pass
+constexpr int kCC = 32;                 // channels accumulated in registers per pass
 constexpr int kNB = 32;                 // RoIs whose tables are resident in shared memory at once
 constexpr int kG = 4;                   // RoIs whose grad_out chunk is staged per pipeline stage
 constexpr int kBlk = kCC * kP * kP;     // floats of one (RoI, channel-chunk) block of grad_out = 784 (16-byte multiple)
@@ -257,7 +257,7 @@ __device__ __forceinline__ void accumulate_group(const BwdSmem& S, int buf, int 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) roi_align_bwd_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kThreads, 2) roi_align_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& S = *reinterpret_cast<BwdSmem*>(smem_raw);
 
