@@ -2,7 +2,7 @@
 // Replaces autograd's torchvision roi_align_backward (fp32 atomicAdd scatter, non-deterministic, plus a
 // separate zero-fill of every dense gradient map) at train.py:145.
 //
-//   prep kernel   one thread per RoI: FPN level + conservative pixel bounding box of its footprint.
+//   prep kernel   one thread per RoI: FPN level + exact pixel bounding box of its footprint.
 //   gather kernel one CTA per (image, level, 16x16-pixel tile).  The CTA scans the RoIs of its image in index
 //                 order, keeps those whose box meets the tile (ordered => fixed accumulation order), builds
 //                 their separable weight tables restricted to the tile (same sample arithmetic as the
@@ -10,6 +10,8 @@
 //                 accumulates   g[c][y][x] += Wy[ph][y] * Wx[pw][x] / count * grad_out[roi][c][ph][pw]
 //                 in registers over the RoI list and writes its pixel ONCE with a plain store - which also
 //                 provides the zero fill of untouched pixels.  No atomics, no memset, run-to-run bit-identical.
+#include <cstdlib>
+
 #include "roi_geometry.cuh"
 
 namespace osr {
@@ -30,9 +32,21 @@ constexpr int kBlk = kCC * kP * kP;     // floats of one (RoI, channel-chunk) bl
 constexpr int kWin = 4 * kThreads;      // RoI indices scanned per batch (4 per thread, in order)
 
 struct RoiInfo {
-  int x0, x1, y0, y1;  // inclusive pixel bounds of the footprint (conservative); x1 < x0 => empty
+  int x0, x1, y0, y1;  // inclusive pixel bounds of the footprint (exact); x1 < x0 => empty
   int level;
 };
+struct __align__(16) RoiInfoPacked {   // 16 bytes: the per-tile scans read it with one coalesced 16-byte load per RoI
+  short x0, x1, y0, y1;
+  int level, pad;
+};
+__device__ __forceinline__ RoiInfo load_info(const RoiInfoPacked* q) {
+  const int4 v = __ldg(reinterpret_cast<const int4*>(q));
+  RoiInfo r;
+  r.x0 = (short)(v.x & 0xffff); r.x1 = v.x >> 16;
+  r.y0 = (short)(v.y & 0xffff); r.y1 = v.y >> 16;
+  r.level = v.z;
+  return r;
+}
 
 struct BwdParams {
   RoiLevels L;
@@ -40,26 +54,29 @@ struct BwdParams {
   const float* rois;
   const int32_t* roi_off;  // (N+1)
   int M;
-  RoiInfo* info;           // (M) workspace
+  RoiInfoPacked* info;     // (M) workspace
   int tile_base[OSR_MAX_LEVELS + 1];  // first tile id of each level (tiles ordered level, image, ty, tx)
   int tiles_x[OSR_MAX_LEVELS], tiles_y[OSR_MAX_LEVELS];
+  int cl_tile_base[OSR_MAX_LEVELS + 1];  // same for the channels_last kernel's 16x16 tiles
+  int cl_tiles_x[OSR_MAX_LEVELS], cl_tiles_y[OSR_MAX_LEVELS];
 };
 
 __device__ __forceinline__ void axis_bounds(float start, float bin, int grid, int L, int* lo, int* hi) {
-  // valid samples lie in [start, start + 7*bin]; rows touched = floor(clamped sample) and +1.
-  if (grid <= 0) {
-    *lo = 1; *hi = 0;
-    return;
-  }
-  const float cmin = start, cmax = start + (float)kP * bin;
-  if (cmax < -2.0f || cmin > (float)L + 1.0f || !(cmax >= cmin)) {
-    *lo = 1; *hi = 0;
-    return;
-  }
-  int a = (int)floorf(fmaxf(cmin, 0.f)) - 1;
-  int b = (int)floorf(fminf(fmaxf(cmax, 0.f), (float)L)) + 2;
-  *lo = max(a, 0);
-  *hi = min(b, L - 1);
+  // exact: rows touched by the valid samples, same arithmetic as tile_bin_weights (the loop is only 7 * grid long)
+  int a = 1 << 30, b = -1;
+  for (int p = 0; p < kP; ++p)
+    for (int i = 0; i < grid; ++i) {
+      float c = start + p * bin + (i + 0.5f) * bin / (float)grid;
+      if (c < -1.0f || c > (float)L) continue;
+      if (c <= 0.f) c = 0.f;
+      int l = (int)c, h;
+      if (l >= L - 1) h = l = L - 1;
+      else h = l + 1;
+      a = min(a, l);
+      b = max(b, h);
+    }
+  if (b < 0) { *lo = 1; *hi = 0; }
+  else { *lo = a; *hi = b; }
 }
 
 __global__ void __launch_bounds__(256) roi_bwd_prep_kernel(const __grid_constant__ BwdParams p) {
@@ -77,7 +94,10 @@ __global__ void __launch_bounds__(256) roi_bwd_prep_kernel(const __grid_constant
     axis_bounds(g.start_h, g.bin_h, g.grid_h, lv.H, &r.y0, &r.y1);
     if (r.y1 < r.y0) { r.x0 = 1; r.x1 = 0; }
   }
-  p.info[m] = r;
+  RoiInfoPacked q;
+  q.x0 = (short)r.x0; q.x1 = (short)r.x1; q.y0 = (short)r.y0; q.y1 = (short)r.y1;
+  q.level = r.level; q.pad = 0;
+  p.info[m] = q;
 }
 
 // Accumulate the separable weights of output bin `p` that land on rows [t0, t0+tn) into w[(row - t0) * kP + p].
@@ -136,7 +156,7 @@ __device__ __forceinline__ void collect_batch(const BwdParams& p, BwdSmem& S, in
     const int m = pos + tid * 4 + k;
     hit[k] = 0;
     if (m < r1) {
-      const RoiInfo r = p.info[m];
+      const RoiInfo r = load_info(p.info + m);
       hit[k] = (r.level == level) && (r.x0 <= tx0 + kTW - 1) && (r.x1 >= tx0) && (r.y0 <= ty0 + kTH - 1) && (r.y1 >= ty0);
     }
     cnt += hit[k];
@@ -374,6 +394,364 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_bwd_kernel(const __grid
   }
 }
 
+// =========================================================================================================
+// channels_last gather kernel: thread = CHANNEL (the mirror image of roi_align_fwd_nhwc_kernel).
+// One CTA per (image, level, 16x16-pixel tile, 128-channel slab), worked through as four 4x16 sub-tiles; warp w owns channels [32w, 32w+32) of the slab and a
+// private [pixel][lane] fp32 accumulator tile in shared memory (bank = lane: conflict-free).  Per RoI that meets the
+// tile (index order => fixed summation order) the warp
+//   1. copies its 32 x 49 block of grad_out (6272 contiguous bytes) into a private staging buffer with cp.async and
+//      each lane lifts its own channel's 49 values into registers (stride-49 LDS, conflict-free); the buffer is then
+//      refilled with the next RoI's block while this one is consumed;
+//   2. per tile row folds the y weights:  rg[pw] = sum_ph Wy[ph][y]/count * g[ph][pw]   (<= 3 bins per row in
+//      the common case: uniform switch on the first bin; dense 7-bin fold otherwise);
+//   3. walks the tile columns the RoI touches:  acc[y][x] += sum_pw Wx[pw][x] * rg[y][pw]  (<= 3 bins per column; the
+//      first bin never decreases with x, so the columns split into <= 5 runs of equal first bin, each a branch-free
+//      loop with compile-time register indices; columns in > 3 bins take a dense 7-bin loop).
+// This uses the separability in BOTH directions (the pixel-per-thread kernel above cannot: it pays one FMA per
+// (pixel, bin pair, channel)), every lane is busy, there is no CTA-wide barrier while a batch of RoIs is processed,
+// and the finished tile leaves with 16-byte coalesced stores (which is also the zero fill).  Arithmetic: same
+// sample -> weight code as the forward (tile_bin_weights), fp32 FMAs, deterministic.
+constexpr int kCT = 4, kCW = 16;            // sub-tile rows x cols: the unit whose accumulators live in shared memory
+constexpr int kCS = 4;                      // sub-tiles (stacked vertically) per CTA: they share one RoI scan + tables
+constexpr int kCH = kCT * kCS;              // CTA tile rows
+constexpr int kCWarps = 4;                  // warps per CTA = 32-channel groups per slab
+constexpr int kCThreads = kCWarps * 32;
+constexpr int kCNB = 12;                    // RoIs whose tables are resident at once
+constexpr int kGBlk = 32 * kP * kP;         // floats of one (RoI, 32-channel) block of grad_out = 1568
+
+struct __align__(16) ClSmem {
+  float acc[kCWarps][kCT * kCW * 32];       // [warp][pixel][lane]
+  float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
+  float wy[kCNB][kCH * kP];                 // dense [row][bin], pre-multiplied by 1/count
+  float wx[kCNB][kCW * kP];                 // dense [col][bin]
+  float4 yrow[kCNB][kCH];                   // (w(p0), w(p0+1), w(p0+2), code): code 0..4 = p0, 5 = dense, 6 = empty
+  float4 xcol[kCNB][kCW];                   // same per tile column
+  uchar2 run[kCNB][8];                      // [k] = (first, last + 1) tile column whose code is k (k = 0..5)
+  BatchEntry e[kCNB];
+  unsigned stmask[kCS];                     // bit j: RoI j of the batch puts weight on sub-tile st
+  int warp_cnt[kCWarps + 1];
+  int nb, next_pos;
+};
+
+__device__ __forceinline__ void cl_collect(const BwdParams& p, ClSmem& S, int level, int tx0, int ty0, int pos, int r1) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int hit[4], cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m = pos + tid * 4 + k;
+    hit[k] = 0;
+    if (m < r1) {
+      const RoiInfo r = load_info(p.info + m);
+      hit[k] = (r.level == level) && (r.x0 <= tx0 + kCW - 1) && (r.x1 >= tx0) && (r.y0 <= ty0 + kCH - 1) && (r.y1 >= ty0);
+    }
+    cnt += hit[k];
+  }
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) S.warp_cnt[warp] = inc;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < kCWarps; ++w) {
+      int c = S.warp_cnt[w];
+      S.warp_cnt[w] = run;
+      run += c;
+    }
+    S.nb = min(run, kCNB);
+    S.next_pos = min(pos + 4 * kCThreads, r1);
+  }
+  __syncthreads();
+  int rank = S.warp_cnt[warp] + inc - cnt;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (hit[k]) {
+      const int m = pos + tid * 4 + k;
+      if (rank < kCNB) S.e[rank].m = m;
+      else if (rank == kCNB) S.next_pos = m;
+      ++rank;
+    }
+  }
+  __syncthreads();
+}
+
+// (w(p0), w(p0+1), w(p0+2), code) of one tile row / column from its dense 7-bin weight vector
+__device__ __forceinline__ float4 cl_pack3(const float* w) {
+  int lo = kP, hi = -1;
+#pragma unroll
+  for (int b = 0; b < kP; ++b)
+    if (w[b] != 0.f) {
+      lo = min(lo, b);
+      hi = b;
+    }
+  if (hi < 0) return make_float4(0.f, 0.f, 0.f, __int_as_float(6));
+  if (hi - lo + 1 > 3) return make_float4(0.f, 0.f, 0.f, __int_as_float(5));
+  const int p0 = min(lo, kP - 3);
+  return make_float4(w[p0], w[p0 + 1], w[p0 + 2], __int_as_float(p0));
+}
+
+__device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, const LevelDesc& lv, int tx0, int ty0) {
+  const int tid = threadIdx.x;
+  const int nb = S.nb;
+  float* wyf = &S.wy[0][0];
+  float* wxf = &S.wx[0][0];
+  for (int i = tid; i < nb * kCH * kP; i += kCThreads) wyf[i] = 0.f;
+  for (int i = tid; i < nb * kCW * kP; i += kCThreads) wxf[i] = 0.f;
+  __syncthreads();
+  for (int q = tid; q < nb * 2 * kP; q += kCThreads) {
+    const int j = q / (2 * kP);
+    const int ab = q - j * (2 * kP);
+    const float* roi = p.rois + (int64_t)S.e[j].m * 5;
+    const RoiGeom g = roi_geometry(__ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4), lv.scale, p.L.sampling_ratio);
+    if (ab < kP) {
+      tile_bin_weights(g.start_h, g.bin_h, g.grid_h, lv.H, ab, ty0, kCH, S.wy[j]);
+      if (ab == 0) S.e[j].inv_count = 1.0f / g.count;
+    } else {
+      tile_bin_weights(g.start_w, g.bin_w, g.grid_w, lv.W, ab - kP, tx0, kCW, S.wx[j]);
+    }
+  }
+  __syncthreads();
+  for (int q = tid; q < nb * (kCH + kCW); q += kCThreads) {
+    const int j = q / (kCH + kCW);
+    const int r = q - j * (kCH + kCW);
+    if (r < kCH) {   // tile row: fold 1/count into the y weights
+      float* w = &S.wy[j][r * kP];
+      const float ic = S.e[j].inv_count;
+#pragma unroll
+      for (int b = 0; b < kP; ++b) w[b] *= ic;
+      S.yrow[j][r] = cl_pack3(w);
+    } else {
+      S.xcol[j][r - kCH] = cl_pack3(&S.wx[j][(r - kCH) * kP]);
+    }
+  }
+  __syncthreads();
+  // column runs: the first bin of a column never decreases with x, so columns of equal code are contiguous
+  for (int q = tid; q < nb * 6; q += kCThreads) {
+    const int j = q / 6, k = q - j * 6;
+    int lo = kCW, hi = 0;
+#pragma unroll
+    for (int x = 0; x < kCW; ++x)
+      if (__float_as_int(S.xcol[j][x].w) == k) {
+        lo = min(lo, x);
+        hi = x + 1;
+      }
+    S.run[j][k] = make_uchar2((unsigned char)lo, (unsigned char)hi);
+  }
+  if (tid >= kCThreads - kCS) {   // which RoIs put weight on each sub-tile
+    const int st = tid - (kCThreads - kCS);
+    unsigned m = 0;
+    for (int j = 0; j < nb; ++j) {
+      bool anyr = false, anyc = false;
+#pragma unroll
+      for (int r = 0; r < kCT; ++r) anyr |= (__float_as_int(S.yrow[j][st * kCT + r].w) != 6);
+#pragma unroll
+      for (int x = 0; x < kCW; ++x) anyc |= (__float_as_int(S.xcol[j][x].w) != 6);
+      if (anyr && anyc) m |= 1u << j;
+    }
+    S.stmask[st] = m;
+  }
+  __syncthreads();
+}
+
+template <int PH0>
+__device__ __forceinline__ void cl_fold3(const float (&g)[kP * kP], const float4 w, float (&rg)[kP]) {
+#pragma unroll
+  for (int b = 0; b < kP; ++b)
+    rg[b] = fmaf(w.z, g[(PH0 + 2) * kP + b], fmaf(w.y, g[(PH0 + 1) * kP + b], w.x * g[PH0 * kP + b]));
+}
+
+__device__ __forceinline__ void cl_fold_row(const float (&g)[kP * kP], const ClSmem& S, int j, int r, float (&rg)[kP]) {
+  const float4 w = S.yrow[j][r];
+  switch (__float_as_int(w.w)) {
+    case 0: cl_fold3<0>(g, w, rg); break;
+    case 1: cl_fold3<1>(g, w, rg); break;
+    case 2: cl_fold3<2>(g, w, rg); break;
+    case 3: cl_fold3<3>(g, w, rg); break;
+    case 4: cl_fold3<4>(g, w, rg); break;
+    case 5: {
+      const float* wd = &S.wy[j][r * kP];
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rg[b] = 0.f;
+#pragma unroll
+      for (int a = 0; a < kP; ++a) {
+        const float wa = wd[a];
+#pragma unroll
+        for (int b = 0; b < kP; ++b) rg[b] = fmaf(wa, g[a * kP + b], rg[b]);
+      }
+      break;
+    }
+    default:
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rg[b] = 0.f;
+  }
+}
+
+// columns [x0, x1) of the tile all start at bin K: acc[r][x] += w0 rg[r][K] + w1 rg[r][K+1] + w2 rg[r][K+2]
+template <int K>
+__device__ __forceinline__ void cl_run(const float4* xcol, uchar2 rn, float* accl, const float (&rg)[kCT][kP]) {
+#pragma unroll 2
+  for (int x = rn.x; x < rn.y; ++x) {
+    const float4 w = xcol[x];
+    float* ap = accl + x * 32;
+    float v[kCT];
+#pragma unroll
+    for (int r = 0; r < kCT; ++r) v[r] = ap[r * kCW * 32];
+#pragma unroll
+    for (int r = 0; r < kCT; ++r) v[r] = fmaf(w.z, rg[r][K + 2], fmaf(w.y, rg[r][K + 1], fmaf(w.x, rg[r][K], v[r])));
+#pragma unroll
+    for (int r = 0; r < kCT; ++r) ap[r * kCW * 32] = v[r];
+  }
+}
+
+// issue the async copy of the warp's 32 x 49 block of grad_out for RoI m
+__device__ __forceinline__ void cl_stage(const BwdParams& p, float* sg, int m, int c0w, int C, int lane) {
+  const float* src = p.grad_out + ((int64_t)m * C + c0w) * (kP * kP);
+#pragma unroll
+  for (int i = 0; i < (kGBlk / 4 + 31) / 32; ++i) {
+    const int v = i * 32 + lane;
+    if (v < kGBlk / 4) cp_async16(sg + v * 4, src + v * 4);
+  }
+  cp_async_commit();
+}
+
+// next (sub-tile, RoI) pair after sub-tile st with remaining mask m; returns the RoI slot or -1
+__device__ __forceinline__ int cl_next_pair(const ClSmem& S, int st, unsigned m) {
+  while (m == 0) {
+    if (++st >= kCS) return -1;
+    m = S.stmask[st];
+  }
+  return __ffs(m) - 1;
+}
+
+__global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClSmem& S = *reinterpret_cast<ClSmem*>(smem_raw);
+
+  int t = blockIdx.x, level = 0;
+  while (level + 1 < p.L.num_levels && t >= p.cl_tile_base[level + 1]) ++level;
+  t -= p.cl_tile_base[level];
+  const int per_img = p.cl_tiles_x[level] * p.cl_tiles_y[level];
+  const int n = t / per_img;
+  t -= n * per_img;
+  const int ty0 = (t / p.cl_tiles_x[level]) * kCH, tx0 = (t % p.cl_tiles_x[level]) * kCW;
+  const LevelDesc& lv = p.L.lv[level];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.L.C;
+  const int c0w = blockIdx.y * (kCWarps * 32) + warp * 32;   // first channel of this warp
+  const bool wactive = c0w < C;                              // C % 32 == 0 (host-checked)
+  const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
+  float* acc = S.acc[warp];
+  float* accl = acc + lane;
+  float* sg = S.sg[warp];
+  const bool vec = ((lv.sW & 3) == 0) && ((lv.sH & 3) == 0) && ((lv.sN & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
+  float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
+  // write-out slot: lane -> (pixel column xs + 4 q, channels quad .. quad + 4): four 128-byte runs per 16-byte store
+  const int quad = (lane & 7) * 4, xs = lane >> 3;
+
+  int pos = r0;
+  bool first = true;   // first batch of RoIs: the write-out stores; later batches (dense tiles) add to what is there
+  while (true) {
+    cl_collect(p, S, level, tx0, ty0, pos, r1);
+    const int nb = S.nb, next = S.next_pos;
+    if (nb > 0) {
+      cl_build_tables(p, S, lv, tx0, ty0);
+    } else {
+      if (tid < kCS) S.stmask[tid] = 0;
+      __syncthreads();
+    }
+    if (wactive) {
+      int nj = cl_next_pair(S, -1, 0);
+      if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
+      for (int st = 0; st < kCS; ++st) {
+        unsigned m = S.stmask[st];
+        const bool any = (m != 0);
+        if (any) {
+          float4* a4 = reinterpret_cast<float4*>(acc);
+#pragma unroll 4
+          for (int i = lane; i < kCT * kCW * 8; i += 32) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
+        }
+        while (m != 0) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          cp_async_wait<0>();
+          __syncwarp();
+          float g[kP * kP];
+#pragma unroll
+          for (int b = 0; b < kP * kP; ++b) g[b] = sg[lane * (kP * kP) + b];
+          __syncwarp();
+          nj = cl_next_pair(S, st, m);
+          if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
+          float rg[kCT][kP];
+#pragma unroll
+          for (int r = 0; r < kCT; ++r) cl_fold_row(g, S, j, st * kCT + r, rg[r]);
+          const float4* xcol = S.xcol[j];
+          cl_run<0>(xcol, S.run[j][0], accl, rg);
+          cl_run<1>(xcol, S.run[j][1], accl, rg);
+          cl_run<2>(xcol, S.run[j][2], accl, rg);
+          cl_run<3>(xcol, S.run[j][3], accl, rg);
+          cl_run<4>(xcol, S.run[j][4], accl, rg);
+          const uchar2 dn = S.run[j][5];      // columns that sit in more than 3 bins (bins narrower than half a pixel)
+          for (int x = dn.x; x < dn.y; ++x) {
+            if (__float_as_int(xcol[x].w) != 5) continue;
+            const float* wd = &S.wx[j][x * kP];
+#pragma unroll
+            for (int r = 0; r < kCT; ++r) {
+              float v = accl[(r * kCW + x) * 32];
+#pragma unroll
+              for (int b = 0; b < kP; ++b) v = fmaf(wd[b], rg[r][b], v);
+              accl[(r * kCW + x) * 32] = v;
+            }
+          }
+        }
+        // write-out of sub-tile st
+        if (!first && !any) continue;
+        __syncwarp();
+        const int ys = ty0 + st * kCT;
+        if (vec) {
+          const int ny = min(kCT, lv.H - ys);
+          float* gp = gimg + (int64_t)ys * lv.sH + (int64_t)(tx0 + xs) * lv.sW + quad;
+          const float* ap = acc + xs * 32 + quad;
+          const int64_t step = 4 * lv.sW;
+          for (int yy = 0; yy < ny; ++yy) {
+#pragma unroll
+            for (int q = 0; q < kCW / 4; ++q) {
+              if (tx0 + xs + 4 * q < lv.W) {
+                float4 v = any ? *reinterpret_cast<const float4*>(ap + (yy * kCW + 4 * q) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4* dst = reinterpret_cast<float4*>(gp + q * step);
+                if (!first) {
+                  const float4 o = *dst;
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *dst = v;
+              }
+            }
+            gp += lv.sH;
+          }
+        } else {
+          for (int pix = 0; pix < kCT * kCW; ++pix) {
+            const int y = ys + pix / kCW, x = tx0 + pix % kCW;
+            if (y < lv.H && x < lv.W) {
+              float* dst = gimg + (int64_t)y * lv.sH + (int64_t)x * lv.sW + lane;
+              const float v = any ? acc[pix * 32 + lane] : 0.f;
+              *dst = first ? v : (*dst + v);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    first = false;
+    pos = next;
+    if (pos >= r1) break;
+    __syncthreads();   // tables are rebuilt by the next batch
+  }
+}
+
 int fill_bwd(BwdParams& p, const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int P,
              int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level) {
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
@@ -387,6 +765,14 @@ int fill_bwd(BwdParams& p, const osr_feat_level_t* h_levels, int num_levels, int
     base += p.tiles_x[l] * p.tiles_y[l] * num_images;
   }
   p.tile_base[num_levels] = base;
+  base = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    p.cl_tiles_x[l] = osr::ceil_div(p.L.lv[l].W, kCW);
+    p.cl_tiles_y[l] = osr::ceil_div(p.L.lv[l].H, kCH);
+    p.cl_tile_base[l] = base;
+    base += p.cl_tiles_x[l] * p.cl_tiles_y[l] * num_images;
+  }
+  p.cl_tile_base[num_levels] = base;
   return 0;
 }
 
@@ -396,7 +782,7 @@ extern "C" {
 
 size_t osr_roi_align_bwd_workspace(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int M) {
   (void)h_levels; (void)num_levels; (void)num_images; (void)C;
-  return osr::align256((size_t)(M > 0 ? M : 1) * sizeof(RoiInfo));
+  return osr::align256((size_t)(M > 0 ? M : 1) * sizeof(RoiInfoPacked));
 }
 
 int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
@@ -417,11 +803,22 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   p.rois = rois;
   p.roi_off = roi_batch_offsets;
   p.M = M;
-  p.info = static_cast<RoiInfo*>(workspace);
+  p.info = static_cast<RoiInfoPacked*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (M > 0) {
     roi_bwd_prep_kernel<<<osr::ceil_div(M, 256), 256, 0, s>>>(p);
     OSR_LAUNCH_CHECK();
+  }
+  // channels_last gradient maps with whole 32-channel groups: thread-per-channel kernel
+  bool cl = (C % 32 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) && !getenv("OSR_ROIALIGN_BWD_PIXEL");
+  for (int l = 0; l < num_levels; ++l) cl = cl && (p.L.lv[l].sC == 1);
+  if (cl) {
+    const size_t smem = sizeof(ClSmem);
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(p.cl_tile_base[num_levels], osr::ceil_div(C, kCWarps * 32));
+    roi_align_bwd_cl_kernel<<<grid, kCThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+    return 0;
   }
   const int tiles = p.tile_base[num_levels];
   const size_t smem = sizeof(BwdSmem);

@@ -223,3 +223,52 @@ def test_backward_channels_last_grads():
         assert a.is_contiguous(memory_format=torch.channels_last)
         scale = max(1.0, float(b.abs().max()))
         torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
+
+
+@pytest.mark.parametrize("hw,n,per_img,C", [((800, 1333), 2, 256, 256), ((320, 480), 3, 200, 96), ((224, 224), 1, 64, 32),
+                                             ((224, 224), 1, 64, 40)])
+def test_backward_channels_last_kernel_matches_torchvision(hw, n, per_img, C):
+    """channels_last gradient maps with C % 32 == 0 take the thread-per-channel gather kernel (96 = a partly filled
+    128-channel slab; 40 falls back to the pixel-per-thread kernel)."""
+    from osr_b200 import synth
+    ours, ref = _pooler_pair()
+    feats = synth.make_features(n, hw, C, seed=4, device="cuda:0", channels_last=True)
+    rois = synth.make_rois(n, per_img, hw, seed=19)
+    rois[0] = torch.cat([rois[0], _special_rois(*hw)])
+    boxes = [OBoxes(r.cuda()) for r in rois]
+    M = sum(len(r) for r in rois)
+    gout = torch.randn(M, C, 7, 7, device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(1))
+    g_ours = _grads(ours, feats, boxes, gout)
+    g_ref = _grads(ref, [f.contiguous() for f in feats], boxes, gout)
+    g_nchw = _grads(ours, [f.contiguous() for f in feats], boxes, gout)
+    for a, b, c in zip(g_ours, g_ref, g_nchw):
+        assert a.is_contiguous(memory_format=torch.channels_last)
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
+        torch.testing.assert_close(a, c, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
+
+
+def test_backward_channels_last_dense_tile_tiny_rois_deterministic_adjoint():
+    """> kCNB RoIs on one tile (multi-batch path), sub-pixel bins (dense 7-bin fold), run-to-run bit-identical,
+    and <pool(F), G> == <F, pool^T(G)>."""
+    from osr_b200 import synth
+    ours, ref = _pooler_pair()
+    feats = synth.make_features(1, (224, 224), 64, seed=9, device="cuda:0", channels_last=True)
+    g = torch.Generator().manual_seed(5)
+    c = torch.rand(240, 2, generator=g) * 20 + 60
+    wh = torch.rand(240, 2, generator=g) * 30 + 10
+    wh[200:] = torch.rand(40, 2, generator=g) * 6 + 0.5      # tiny RoIs: bins narrower than half a pixel
+    rois = [torch.cat([c - wh / 2, c + wh / 2], dim=1)]
+    boxes = [OBoxes(r.cuda()) for r in rois]
+    gout = torch.randn(240, 64, 7, 7, device="cuda:0")
+    g1 = _grads(ours, feats, boxes, gout)
+    g2 = _grads(ours, feats, boxes, gout)
+    g_ref = _grads(ref, [f.contiguous() for f in feats], boxes, gout)
+    for a, a2, b in zip(g1, g2, g_ref):
+        assert torch.equal(a, a2), "backward must be run-to-run bit-identical"
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
+    out = ours.forward(feats, boxes)
+    lhs = (out.double() * gout.double()).sum()
+    rhs = sum((f.double() * gg.double()).sum() for f, gg in zip(feats, g1))
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-2, (float(lhs), float(rhs))
