@@ -713,8 +713,12 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   // feature values; 8 columns of slack follow the last stage).
   const bool fast_taps = (nxc == 1);
   int toff[kP];
+  int tmax = 0;   // widest bin in pixels: picks the 4-, 6- or 8-tap row loop
 #pragma unroll
-  for (int pw = 0; pw < kP; ++pw) toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
+  for (int pw = 0; pw < kP; ++pw) {
+    toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
+    tmax = max(tmax, T.nx[pw]);
+  }
   if (tid < kP) {
     float w8[8];
 #pragma unroll
@@ -749,19 +753,46 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     float U[kP];
     if (fast_taps) {
       const float* rowc = ring + slot * stage_floats + min(c, C - 1);
+      if (tmax <= 4) {          // CTA-uniform: widest bin of this RoI spans <= 4 pixels
 #pragma unroll
-      for (int pw = 0; pw < kP; ++pw) {
-        const float* rp = rowc + toff[pw];
-        const float4 wa = T.wt[pw][0], wb = T.wt[pw][1];
-        float u = wa.x * rp[0];
-        u = fmaf(wa.y, rp[1 * C], u);
-        u = fmaf(wa.z, rp[2 * C], u);
-        u = fmaf(wa.w, rp[3 * C], u);
-        u = fmaf(wb.x, rp[4 * C], u);
-        u = fmaf(wb.y, rp[5 * C], u);
-        u = fmaf(wb.z, rp[6 * C], u);
-        u = fmaf(wb.w, rp[7 * C], u);
-        U[pw] = u;
+        for (int pw = 0; pw < kP; ++pw) {
+          const float* rp = rowc + toff[pw];
+          const float4 wa = T.wt[pw][0];
+          float u = wa.x * rp[0];
+          u = fmaf(wa.y, rp[1 * C], u);
+          u = fmaf(wa.z, rp[2 * C], u);
+          u = fmaf(wa.w, rp[3 * C], u);
+          U[pw] = u;
+        }
+      } else if (tmax <= 6) {
+#pragma unroll
+        for (int pw = 0; pw < kP; ++pw) {
+          const float* rp = rowc + toff[pw];
+          const float4 wa = T.wt[pw][0];
+          const float2 wb = *reinterpret_cast<const float2*>(&T.wt[pw][1]);
+          float u = wa.x * rp[0];
+          u = fmaf(wa.y, rp[1 * C], u);
+          u = fmaf(wa.z, rp[2 * C], u);
+          u = fmaf(wa.w, rp[3 * C], u);
+          u = fmaf(wb.x, rp[4 * C], u);
+          u = fmaf(wb.y, rp[5 * C], u);
+          U[pw] = u;
+        }
+      } else {
+#pragma unroll
+        for (int pw = 0; pw < kP; ++pw) {
+          const float* rp = rowc + toff[pw];
+          const float4 wa = T.wt[pw][0], wb = T.wt[pw][1];
+          float u = wa.x * rp[0];
+          u = fmaf(wa.y, rp[1 * C], u);
+          u = fmaf(wa.z, rp[2 * C], u);
+          u = fmaf(wa.w, rp[3 * C], u);
+          u = fmaf(wb.x, rp[4 * C], u);
+          u = fmaf(wb.y, rp[5 * C], u);
+          u = fmaf(wb.z, rp[6 * C], u);
+          u = fmaf(wb.w, rp[7 * C], u);
+          U[pw] = u;
+        }
       }
     } else {
 #pragma unroll
