@@ -185,12 +185,28 @@ __global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_consta
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f, c = 0.f;
-    for (int i = 0; i < p.num_ctas; ++i) {
+  // ordered sum of the per-CTA partials: thread t adds partials t, t + 256, ... in that order, then a fixed tree
+  __shared__ float s_a[kThreads], s_b[kThreads];
+  {
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < p.num_ctas; i += kThreads) {
       a += p.partial[2 * i];
       b += p.partial[2 * i + 1];
     }
+    s_a[threadIdx.x] = a;
+    s_b[threadIdx.x] = b;
+  }
+  __syncthreads();
+  for (int o = kThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float a = s_a[0], b = s_b[0];
+    float c = 0.f;
     for (int k = 0; k < p.Kr; ++k) c += s_c[k];
     const float denom = fmaxf(p.r_norm, 1.0f);
     p.loss_terms[0] = (a + b + p.center_weight * c) * p.loss_weight / denom;
@@ -307,7 +323,8 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_con
   __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float s = __ldg(p.grad_loss) * p.loss_weight / fmaxf(p.r_norm, 1.0f);
-  for (int j = 0; j < p.Kr; ++j) {
+  {
+    const int j = blockIdx.x;   // one CTA per prototype
     float g = 0.f;
     if (tid < p.D) {
       for (int seg = 0; seg < kSeg; ++seg) g += p.partial[((int64_t)seg * p.Kr + j) * p.D + tid];
@@ -324,7 +341,6 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_con
     float tot = 0.f;
     for (int w = 0; w < kWarps; ++w) tot += s_red[w];
     if (tid < p.D) p.grad_reps[(int64_t)j * p.D + tid] = s * p.rep_inv_norm[j] * (g - rh[j * p.D + tid] * tot);
-    __syncthreads();
   }
 }
 
@@ -392,7 +408,8 @@ int check_shape(int R, int D, int K, int rpc) {
   return 0;
 }
 
-int fwd_ctas(int R) { return R < 8 * kWarps ? 1 : (R / (8 * kWarps) > 592 ? 592 : R / (8 * kWarps)); }
+// two rows per warp: enough CTAs to fill the GPU in one wave at R = 8192 (the stage is latency-bound)
+int fwd_ctas(int R) { return R < 2 * kWarps ? 1 : (R / (2 * kWarps) > 592 ? 592 : R / (2 * kWarps)); }
 
 }  // namespace
 
@@ -473,7 +490,7 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
   }
   pln_grad_reps_partial<<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
   OSR_LAUNCH_CHECK();
-  pln_grad_reps_final<<<1, kThreads, smem, s>>>(p);
+  pln_grad_reps_final<<<p.Kr, kThreads, smem, s>>>(p);
   OSR_LAUNCH_CHECK();
   return 0;
 }

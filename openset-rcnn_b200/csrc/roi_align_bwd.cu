@@ -399,11 +399,11 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_bwd_kernel(const __grid
 // One CTA per (image, level, 16x16-pixel tile, 128-channel slab), worked through as four 4x16 sub-tiles; warp w owns channels [32w, 32w+32) of the slab and a
 // private [pixel][lane] fp32 accumulator tile in shared memory (bank = lane: conflict-free).  Per RoI that meets the
 // tile (index order => fixed summation order) the warp
-//   1. copies its 32 x 49 block of grad_out (6272 contiguous bytes) into a private staging buffer with cp.async and
-//      each lane lifts its own channel's 49 values into registers (stride-49 LDS, conflict-free); the buffer is then
-//      refilled with the next RoI's block while this one is consumed;
-//   2. per tile row folds the y weights:  rg[pw] = sum_ph Wy[ph][y]/count * g[ph][pw]   (<= 3 bins per row in
-//      the common case: uniform switch on the first bin; dense 7-bin fold otherwise);
+//   1. copies its 32 x 49 block of grad_out (6272 contiguous bytes) into a private staging buffer with cp.async
+//      (lane = channel reads it at stride 49: conflict-free);
+//   2. per tile row folds the y weights:  rg[pw] = sum_ph Wy[ph][y]/count * g[ph][pw]   (<= 3 bins per row in the
+//      common case, addressed dynamically in the staged block; dense 7-bin fold otherwise); the staging buffer is
+//      then refilled with the next RoI's block while the columns are walked;
 //   3. walks the tile columns the RoI touches:  acc[y][x] += sum_pw Wx[pw][x] * rg[y][pw]  (<= 3 bins per column; the
 //      first bin never decreases with x, so the columns split into <= 5 runs of equal first bin, each a branch-free
 //      loop with compile-time register indices; columns in > 3 bins take a dense 7-bin loop).
@@ -556,36 +556,33 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
   __syncthreads();
 }
 
-template <int PH0>
-__device__ __forceinline__ void cl_fold3(const float (&g)[kP * kP], const float4 w, float (&rg)[kP]) {
-#pragma unroll
-  for (int b = 0; b < kP; ++b)
-    rg[b] = fmaf(w.z, g[(PH0 + 2) * kP + b], fmaf(w.y, g[(PH0 + 1) * kP + b], w.x * g[PH0 * kP + b]));
-}
-
-__device__ __forceinline__ void cl_fold_row(const float (&g)[kP * kP], const ClSmem& S, int j, int r, float (&rg)[kP]) {
+// rg[pw] = sum_ph Wy[ph][row] / count * g[ph][pw] for one tile row; gl = this lane's channel in the staged block
+// (49 floats, stride-49 across lanes: conflict-free).  The <= 3 bins of the row are addressed dynamically in shared
+// memory, so there is no per-first-bin code replication (the register-resident variant with a 5-way switch per row
+// was instruction-cache bound).
+__device__ __forceinline__ void cl_fold_row(const float* gl, const ClSmem& S, int j, int r, float (&rg)[kP]) {
   const float4 w = S.yrow[j][r];
-  switch (__float_as_int(w.w)) {
-    case 0: cl_fold3<0>(g, w, rg); break;
-    case 1: cl_fold3<1>(g, w, rg); break;
-    case 2: cl_fold3<2>(g, w, rg); break;
-    case 3: cl_fold3<3>(g, w, rg); break;
-    case 4: cl_fold3<4>(g, w, rg); break;
-    case 5: {
+  const int code = __float_as_int(w.w);
+  if (code < 5) {
+    const float* gp = gl + code * kP;
+#pragma unroll
+    for (int b = 0; b < kP; ++b) rg[b] = fmaf(w.y, gp[kP + b], w.x * gp[b]);
+    if (w.z != 0.f) {   // third bin only when the row really sits in three (bins narrower than two pixels)
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rg[b] = fmaf(w.z, gp[2 * kP + b], rg[b]);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < kP; ++b) rg[b] = 0.f;
+    if (code == 5) {    // row inside more than 3 bins: dense
       const float* wd = &S.wy[j][r * kP];
-#pragma unroll
-      for (int b = 0; b < kP; ++b) rg[b] = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int a = 0; a < kP; ++a) {
         const float wa = wd[a];
 #pragma unroll
-        for (int b = 0; b < kP; ++b) rg[b] = fmaf(wa, g[a * kP + b], rg[b]);
+        for (int b = 0; b < kP; ++b) rg[b] = fmaf(wa, gl[a * kP + b], rg[b]);
       }
-      break;
     }
-    default:
-#pragma unroll
-      for (int b = 0; b < kP; ++b) rg[b] = 0.f;
   }
 }
 
@@ -680,15 +677,12 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
           m &= m - 1;
           cp_async_wait<0>();
           __syncwarp();
-          float g[kP * kP];
-#pragma unroll
-          for (int b = 0; b < kP * kP; ++b) g[b] = sg[lane * (kP * kP) + b];
-          __syncwarp();
-          nj = cl_next_pair(S, st, m);
-          if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
           float rg[kCT][kP];
 #pragma unroll
-          for (int r = 0; r < kCT; ++r) cl_fold_row(g, S, j, st * kCT + r, rg[r]);
+          for (int r = 0; r < kCT; ++r) cl_fold_row(sg + lane * (kP * kP), S, j, st * kCT + r, rg[r]);
+          __syncwarp();   // every lane is done with the staged block: refill it while the columns are walked
+          nj = cl_next_pair(S, st, m);
+          if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
           const float4* xcol = S.xcol[j];
           cl_run<0>(xcol, S.run[j][0], accl, rg);
           cl_run<1>(xcol, S.run[j][1], accl, rg);
