@@ -586,8 +586,9 @@ __global__ void __launch_bounds__(kThreads, OSR_FWD_MINB) roi_align_fwd_kernel(c
 // in registers:  per row  U[pw] = sum_x Wx[pw][x] * row[x][c]   (conflict-free LDS: consecutive threads, consecutive floats)
 //                then     out[ph][pw] += Wy[ph][y] * U[pw]      for the <= 3 bins containing the row (uniform switch).
 // The 49 x C tile is transposed through shared memory and stored with 16-byte coalesced writes (C-major output).
-constexpr int kNhwcCols = 32;   // columns per x chunk (wider footprints loop over chunks)
-constexpr int kNhwcStages = 3;
+constexpr int kNhwcRingCols = 96;   // ring capacity in pixel columns (x C floats); split per RoI into 2..6 row stages
+constexpr int kNhwcMaxStages = 6;
+constexpr int kNhwcWide = 48;       // widest footprint staged as whole rows; wider ones go in 32-column chunks
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -596,15 +597,14 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 
 template <int kC>   // kC > 0: compile-time channel count (immediate LDS offsets); 0: run-time C
 __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const __grid_constant__ FwdParams p) {
-  // dynamic smem: [ ring: kNhwcStages x (32 cols x C floats) (re-used as the 49 x C output tile) | barriers | T ]
+  // dynamic smem: [ ring: 96 cols x C floats, cut into row stages sized to this RoI (re-used as the 49 x C output tile) | barriers | T ]
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
   const int C = kC > 0 ? kC : p.L.C;
-  const int stage_floats = kNhwcCols * C;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(ring + p.ring_floats);
-  Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNhwcStages);
+  Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNhwcMaxStages);
   uint64_t* full_bar = s_bar;
-  uint64_t* empty_bar = s_bar + kNhwcStages;
+  uint64_t* empty_bar = s_bar + kNhwcMaxStages;
 
   const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     T.rw[r] = make_float4(w0, w1, w2, __int_as_float(cnt == 99 ? -1 : (ph0 < 0 ? kP : ph0)));
   }
   if (tid == 0) {
-    for (int i = 0; i < kNhwcStages; ++i) {
+    for (int i = 0; i < kNhwcMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], kWarps);
     }
@@ -704,14 +704,18 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
 #pragma unroll
     for (int b = 0; b < kP; ++b) acc[a][b] = 0.f;
 
-  const int nxc = ceil_div(wf, kNhwcCols);
+  // stage geometry: a stage holds one footprint row (chunk).  Narrow RoIs get more, smaller stages (deeper prefetch),
+  // RoIs up to 48 pixels wide are still staged as whole rows, wider ones in 32-column chunks.
+  const int scols = wf <= kNhwcWide ? ((wf + 3) & ~3) : 32;
+  const int nstages = min(kNhwcMaxStages, kNhwcRingCols / scols);
+  const int stage_floats = scols * C;
+  const int nxc = ceil_div(wf, scols);
   const int total = nxc * hf;          // (x chunk, row) tiles, chunk-major
   const int c = tid;                   // my channel (C <= 256 enforced by the host)
   const bool cin = c < C;
   // Common case (one x chunk): every bin's x taps are padded to 8 with zero weights (T.wt), so the row loop is fully
   // unrolled and predicate-free; padded taps read finite data (the ring is zero-initialised once and only ever holds
   // feature values; 8 columns of slack follow the last stage).
-  const bool fast_taps = (nxc == 1);
   int toff[kP];
   int tmax = 0;   // widest bin in pixels: picks the 4-, 6- or 8-tap row loop
 #pragma unroll
@@ -719,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
     tmax = max(tmax, T.nx[pw]);
   }
+  const bool fast_taps = (nxc == 1) && (tmax <= 8);
   if (tid < kP) {
     float w8[8];
 #pragma unroll
@@ -732,23 +737,23 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   // producer prologue
   if (warp == 0) {
     if (elect_one()) {
-      for (int t = 0; t < min(kNhwcStages, total); ++t) {
+      for (int t = 0; t < min(nstages, total); ++t) {
         const int xc = t / hf, r = t - xc * hf;
-        const int ncols = min(kNhwcCols, wf - xc * kNhwcCols);
+        const int ncols = min(scols, wf - xc * scols);
         const uint32_t bytes = (uint32_t)(ncols * C * 4);
         mbar_expect_tx(&full_bar[t], bytes);
-        bulk_load_1d(ring + t * stage_floats, img_base + ((int64_t)(ymin + r) * lv.sH + (int64_t)(xmin + xc * kNhwcCols) * lv.sW), bytes, &full_bar[t]);
+        bulk_load_1d(ring + t * stage_floats, img_base + ((int64_t)(ymin + r) * lv.sH + (int64_t)(xmin + xc * scols) * lv.sW), bytes, &full_bar[t]);
       }
     }
     __syncwarp();
   }
   int xc = 0, r = 0;
   for (int t = 0; t < total; ++t) {
-    const int slot = t % kNhwcStages;
-    const uint32_t parity = (uint32_t)((t / kNhwcStages) & 1);
+    const int slot = t % nstages;
+    const uint32_t parity = (uint32_t)((t / nstages) & 1);
     mbar_wait(&full_bar[slot], parity);
     const float* row = ring + slot * stage_floats + c;
-    const int x_lo = xmin + xc * kNhwcCols, x_hi = min(xmin + wf, x_lo + kNhwcCols);
+    const int x_lo = xmin + xc * scols, x_hi = min(xmin + wf, x_lo + scols);
     // x contraction of this row (chunk): U[pw] = sum_x Wx[pw][x] * row[x][c]
     float U[kP];
     if (fast_taps) {
@@ -807,15 +812,15 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);
     // refill the slot with tile t + stages once every warp has released it
-    if (warp == 0 && t + kNhwcStages < total) {
+    if (warp == 0 && t + nstages < total) {
       if (elect_one()) {
         mbar_wait(&empty_bar[slot], parity);
-        const int tn = t + kNhwcStages;
+        const int tn = t + nstages;
         const int nxc2 = tn / hf, nr2 = tn - nxc2 * hf;
-        const int ncols = min(kNhwcCols, wf - nxc2 * kNhwcCols);
+        const int ncols = min(scols, wf - nxc2 * scols);
         const uint32_t bytes = (uint32_t)(ncols * C * 4);
         mbar_expect_tx(&full_bar[slot], bytes);
-        bulk_load_1d(ring + slot * stage_floats, img_base + ((int64_t)(ymin + nr2) * lv.sH + (int64_t)(xmin + nxc2 * kNhwcCols) * lv.sW), bytes, &full_bar[slot]);
+        bulk_load_1d(ring + slot * stage_floats, img_base + ((int64_t)(ymin + nr2) * lv.sH + (int64_t)(xmin + nxc2 * scols) * lv.sW), bytes, &full_bar[slot]);
       }
       __syncwarp();
     }
@@ -1027,11 +1032,11 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
     nhwc = lv.sC == 1 && lv.sW == C && lv.sH == (int64_t)lv.W * C && (lv.sN % 4 == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
   }
   if (nhwc) {
-    int ring = (kNhwcStages * kNhwcCols + 8) * C;              // + 8 columns of slack for the zero-weight padded taps
+    int ring = (kNhwcRingCols + 8) * C;              // + 8 columns of slack for the zero-weight padded taps
     if (ring < kP * kP * C) ring = kP * kP * C;                 // the ring doubles as the 49 x C output tile
     p.ring_floats = (ring + 31) & ~31;
     for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = 0;
-    const size_t smem = (size_t)p.ring_floats * 4 + 2 * kNhwcStages * 8 + sizeof(Tables) + 16;
+    const size_t smem = (size_t)p.ring_floats * 4 + 2 * kNhwcMaxStages * 8 + sizeof(Tables) + 16;
     if (C == 256) {
       OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       roi_align_fwd_nhwc_kernel<256><<<M, kThreads, smem, s>>>(p);
