@@ -30,10 +30,13 @@ constexpr int kNB = 32;                 // RoIs whose tables are resident in sha
 constexpr int kG = 4;                   // RoIs whose grad_out chunk is staged per pipeline stage
 constexpr int kBlk = kCC * kP * kP;     // floats of one (RoI, channel-chunk) block of grad_out = 784 (16-byte multiple)
 constexpr int kWin = 4 * kThreads;      // RoI indices scanned per batch (4 per thread, in order)
+constexpr int kFW = 64;                 // footprint rows / columns per RoI kept in the workspace weight table
+constexpr int kWRoi = 2 * kFW * kP;     // floats per RoI in that table: [y rows | x columns] x 7 bins
 
 struct RoiInfo {
   int x0, x1, y0, y1;  // inclusive pixel bounds of the footprint (exact); x1 < x0 => empty
   int level;
+  int flags;           // bit 0: the RoI's dense weight rows are in the workspace table (footprint <= kFW x kFW)
 };
 struct __align__(16) RoiInfoPacked {   // 16 bytes: the per-tile scans read it with one coalesced 16-byte load per RoI
   short x0, x1, y0, y1;
@@ -45,6 +48,7 @@ __device__ __forceinline__ RoiInfo load_info(const RoiInfoPacked* q) {
   r.x0 = (short)(v.x & 0xffff); r.x1 = v.x >> 16;
   r.y0 = (short)(v.y & 0xffff); r.y1 = v.y >> 16;
   r.level = v.z;
+  r.flags = v.w;
   return r;
 }
 
@@ -55,49 +59,98 @@ struct BwdParams {
   const int32_t* roi_off;  // (N+1)
   int M;
   RoiInfoPacked* info;     // (M) workspace
+  float* wfull;            // (M, 2, kFW, 7) workspace: per RoI, per footprint row / column, the 7 bin weights
   int tile_base[OSR_MAX_LEVELS + 1];  // first tile id of each level (tiles ordered level, image, ty, tx)
   int tiles_x[OSR_MAX_LEVELS], tiles_y[OSR_MAX_LEVELS];
   int cl_tile_base[OSR_MAX_LEVELS + 1];  // same for the channels_last kernel's 16x16 tiles
   int cl_tiles_x[OSR_MAX_LEVELS], cl_tiles_y[OSR_MAX_LEVELS];
 };
 
-__device__ __forceinline__ void axis_bounds(float start, float bin, int grid, int L, int* lo, int* hi) {
-  // exact: rows touched by the valid samples, same arithmetic as tile_bin_weights (the loop is only 7 * grid long)
-  int a = 1 << 30, b = -1;
-  for (int p = 0; p < kP; ++p)
-    for (int i = 0; i < grid; ++i) {
-      float c = start + p * bin + (i + 0.5f) * bin / (float)grid;
-      if (c < -1.0f || c > (float)L) continue;
-      if (c <= 0.f) c = 0.f;
-      int l = (int)c, h;
-      if (l >= L - 1) h = l = L - 1;
-      else h = l + 1;
-      a = min(a, l);
-      b = max(b, h);
+// one bin of one axis: visit its valid samples as (low row, high row, weight at low, weight at high) - the sample
+// arithmetic of torchvision's bilinear_interpolate, shared by the forward tables (=> exact adjoint)
+template <class F>
+__device__ __forceinline__ void for_bin_samples(float start, float bin, int grid, int L, int p, F&& f) {
+  for (int i = 0; i < grid; ++i) {
+    float c = start + p * bin + (i + 0.5f) * bin / (float)grid;
+    if (c < -1.0f || c > (float)L) continue;
+    if (c <= 0.f) c = 0.f;
+    int lo = (int)c, hi;
+    if (lo >= L - 1) {
+      hi = lo = L - 1;
+      c = (float)lo;
+    } else {
+      hi = lo + 1;
     }
-  if (b < 0) { *lo = 1; *hi = 0; }
-  else { *lo = a; *hi = b; }
+    const float l = c - (float)lo;
+    f(lo, hi, 1.f - l, l);
+  }
 }
 
-__global__ void __launch_bounds__(256) roi_bwd_prep_kernel(const __grid_constant__ BwdParams p) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= p.M) return;
+// Prep: one WARP per RoI.  Lanes 0..6 own the y bins, lanes 7..13 the x bins.  Pass 1 finds the exact footprint box,
+// pass 2 (footprints up to kFW x kFW) accumulates the dense weight rows Wy[row][bin] / count and Wx[col][bin] in
+// shared memory and writes them to the workspace, so the gather CTAs (one RoI is seen by ~7 tiles x 2 slabs) only
+// load and pack them instead of re-deriving them from the samples.
+constexpr int kPrepWarps = 4;
+__global__ void __launch_bounds__(kPrepWarps * 32) roi_bwd_prep_kernel(const __grid_constant__ BwdParams p) {
+  __shared__ float sw[kPrepWarps][kWRoi];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * kPrepWarps + warp;
+  if (m >= p.M) return;   // warp-uniform; no block-level barrier below
   const float* roi = p.rois + (int64_t)m * 5;
   const float x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
-  RoiInfo r;
-  r.level = assign_level(x1, y1, x2, y2, p.L);
-  r.x0 = 1; r.x1 = 0; r.y0 = 1; r.y1 = 0;
-  if (r.level >= 0 && r.level < p.L.num_levels) {
-    const LevelDesc& lv = p.L.lv[r.level];
-    const RoiGeom g = roi_geometry(x1, y1, x2, y2, lv.scale, p.L.sampling_ratio);
-    axis_bounds(g.start_w, g.bin_w, g.grid_w, lv.W, &r.x0, &r.x1);
-    axis_bounds(g.start_h, g.bin_h, g.grid_h, lv.H, &r.y0, &r.y1);
-    if (r.y1 < r.y0) { r.x0 = 1; r.x1 = 0; }
+  const int level = assign_level(x1, y1, x2, y2, p.L);
+  const bool lvl_ok = (level >= 0 && level < p.L.num_levels);
+  float* w = sw[warp];
+  for (int i = lane; i < kWRoi; i += 32) w[i] = 0.f;
+  RoiGeom g{};
+  int L = 1;
+  const bool isy = lane < kP;
+  const int bin = isy ? lane : lane - kP;
+  int lo = 1 << 30, hi = -1;
+  if (lvl_ok) {
+    const LevelDesc& lv = p.L.lv[level];
+    g = roi_geometry(x1, y1, x2, y2, lv.scale, p.L.sampling_ratio);
+    L = isy ? lv.H : lv.W;
+    if (lane < 2 * kP)
+      for_bin_samples(isy ? g.start_h : g.start_w, isy ? g.bin_h : g.bin_w, isy ? g.grid_h : g.grid_w, L, bin,
+                      [&](int l, int h, float, float) { lo = min(lo, l); hi = max(hi, h); });
   }
-  RoiInfoPacked q;
-  q.x0 = (short)r.x0; q.x1 = (short)r.x1; q.y0 = (short)r.y0; q.y1 = (short)r.y1;
-  q.level = r.level; q.pad = 0;
-  p.info[m] = q;
+  int ylo = isy ? lo : (1 << 30), yhi = isy ? hi : -1;
+  int xlo = (!isy && lane < 2 * kP) ? lo : (1 << 30), xhi = (!isy && lane < 2 * kP) ? hi : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ylo = min(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+    yhi = max(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    xlo = min(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+    xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+  }
+  const bool nonempty = (yhi >= 0) && (xhi >= 0);
+  const bool pre = nonempty && (yhi - ylo < kFW) && (xhi - xlo < kFW);
+  __syncwarp();
+  if (pre && lane < 2 * kP) {
+    float* wa = w + (isy ? 0 : kFW * kP);
+    const int base = isy ? ylo : xlo;
+    for_bin_samples(isy ? g.start_h : g.start_w, isy ? g.bin_h : g.bin_w, isy ? g.grid_h : g.grid_w, L, bin,
+                    [&](int l, int h, float wl, float wh) {
+                      wa[(l - base) * kP + bin] += wl;
+                      wa[(h - base) * kP + bin] += wh;
+                    });
+  }
+  __syncwarp();
+  if (pre) {
+    const float ic = 1.0f / g.count;
+    float* dst = p.wfull + (int64_t)m * kWRoi;
+    const int ny = (yhi - ylo + 1) * kP, nx = (xhi - xlo + 1) * kP;
+    for (int i = lane; i < ny; i += 32) dst[i] = w[i] * ic;
+    for (int i = lane; i < nx; i += 32) dst[kFW * kP + i] = w[kFW * kP + i];
+  }
+  if (lane == 0) {
+    RoiInfoPacked q;
+    q.x0 = (short)(nonempty ? xlo : 1); q.x1 = (short)(nonempty ? xhi : 0);
+    q.y0 = (short)(nonempty ? ylo : 1); q.y1 = (short)(nonempty ? yhi : 0);
+    q.level = level; q.pad = pre ? 1 : 0;
+    p.info[m] = q;
+  }
 }
 
 // Accumulate the separable weights of output bin `p` that land on rows [t0, t0+tn) into w[(row - t0) * kP + p].
@@ -496,36 +549,43 @@ __device__ __forceinline__ float4 cl_pack3(const float* w) {
 __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, const LevelDesc& lv, int tx0, int ty0) {
   const int tid = threadIdx.x;
   const int nb = S.nb;
-  float* wyf = &S.wy[0][0];
-  float* wxf = &S.wx[0][0];
-  for (int i = tid; i < nb * kCH * kP; i += kCThreads) wyf[i] = 0.f;
-  for (int i = tid; i < nb * kCW * kP; i += kCThreads) wxf[i] = 0.f;
-  __syncthreads();
-  for (int q = tid; q < nb * 2 * kP; q += kCThreads) {
-    const int j = q / (2 * kP);
-    const int ab = q - j * (2 * kP);
-    const float* roi = p.rois + (int64_t)S.e[j].m * 5;
-    const RoiGeom g = roi_geometry(__ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4), lv.scale, p.L.sampling_ratio);
-    if (ab < kP) {
-      tile_bin_weights(g.start_h, g.bin_h, g.grid_h, lv.H, ab, ty0, kCH, S.wy[j]);
-      if (ab == 0) S.e[j].inv_count = 1.0f / g.count;
-    } else {
-      tile_bin_weights(g.start_w, g.bin_w, g.grid_w, lv.W, ab - kP, tx0, kCW, S.wx[j]);
-    }
-  }
-  __syncthreads();
+  // one thread per (RoI, tile row | tile column): fetch its 7 bin weights (precomputed per RoI by the prep kernel;
+  // footprints wider than kFW re-derive them from the samples), keep them dense for the rare > 3-bin rows, pack.
   for (int q = tid; q < nb * (kCH + kCW); q += kCThreads) {
     const int j = q / (kCH + kCW);
     const int r = q - j * (kCH + kCW);
-    if (r < kCH) {   // tile row: fold 1/count into the y weights
-      float* w = &S.wy[j][r * kP];
-      const float ic = S.e[j].inv_count;
+    const bool isy = r < kCH;
+    const int m = S.e[j].m;
+    const RoiInfo info = load_info(p.info + m);
+    const int pos = isy ? ty0 + r : tx0 + (r - kCH);
+    const int base = isy ? info.y0 : info.x0, last = isy ? info.y1 : info.x1;
+    float* wd = isy ? &S.wy[j][r * kP] : &S.wx[j][(r - kCH) * kP];
 #pragma unroll
-      for (int b = 0; b < kP; ++b) w[b] *= ic;
-      S.yrow[j][r] = cl_pack3(w);
-    } else {
-      S.xcol[j][r - kCH] = cl_pack3(&S.wx[j][(r - kCH) * kP]);
+    for (int b = 0; b < kP; ++b) wd[b] = 0.f;
+    if (pos >= base && pos <= last) {
+      if (info.flags & 1) {
+        const float* src = p.wfull + (int64_t)m * kWRoi + (isy ? 0 : kFW * kP) + (pos - base) * kP;
+#pragma unroll
+        for (int b = 0; b < kP; ++b) wd[b] = __ldg(src + b);
+      } else {
+        const float* roi = p.rois + (int64_t)m * 5;
+        const RoiGeom g = roi_geometry(__ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4), lv.scale, p.L.sampling_ratio);
+        const float sc = isy ? 1.0f / g.count : 1.0f;
+#pragma unroll 1
+        for (int b = 0; b < kP; ++b) {
+          float a = 0.f;
+          for_bin_samples(isy ? g.start_h : g.start_w, isy ? g.bin_h : g.bin_w, isy ? g.grid_h : g.grid_w,
+                          isy ? lv.H : lv.W, b, [&](int l, int h, float wl, float wh) {
+                            if (l == pos) a += wl;
+                            if (h == pos) a += wh;
+                          });
+          wd[b] = a * sc;
+        }
+      }
     }
+    const float4 v = cl_pack3(wd);
+    if (isy) S.yrow[j][r] = v;
+    else S.xcol[j][r - kCH] = v;
   }
   __syncthreads();
   // column runs: the first bin of a column never decreases with x, so columns of equal code are contiguous
@@ -776,7 +836,8 @@ extern "C" {
 
 size_t osr_roi_align_bwd_workspace(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int M) {
   (void)h_levels; (void)num_levels; (void)num_images; (void)C;
-  return osr::align256((size_t)(M > 0 ? M : 1) * sizeof(RoiInfoPacked));
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  return osr::align256(m * sizeof(RoiInfoPacked)) + osr::align256(m * kWRoi * sizeof(float));
 }
 
 int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
@@ -798,9 +859,10 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   p.roi_off = roi_batch_offsets;
   p.M = M;
   p.info = static_cast<RoiInfoPacked*>(workspace);
+  p.wfull = reinterpret_cast<float*>(static_cast<char*>(workspace) + osr::align256((size_t)(M > 0 ? M : 1) * sizeof(RoiInfoPacked)));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (M > 0) {
-    roi_bwd_prep_kernel<<<osr::ceil_div(M, 256), 256, 0, s>>>(p);
+    roi_bwd_prep_kernel<<<osr::ceil_div(M, kPrepWarps), kPrepWarps * 32, 0, s>>>(p);
     OSR_LAUNCH_CHECK();
   }
   // channels_last gradient maps with whole 32-channel groups: thread-per-channel kernel

@@ -272,3 +272,23 @@ def test_backward_channels_last_dense_tile_tiny_rois_deterministic_adjoint():
     lhs = (out.double() * gout.double()).sum()
     rhs = sum((f.double() * gg.double()).sum() for f, gg in zip(feats, g1))
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-2, (float(lhs), float(rhs))
+
+
+def test_channels_last_width_sweep_stage_geometry():
+    """Footprints 25..56 feature pixels wide at level 2: whole-row stages (<= 48 px, 2-3 stages) and the 32-column
+    chunked path (> 48 px) of the channels_last forward, plus the matching backward tiles."""
+    from osr_b200 import synth
+    ours, ref = _pooler_pair()
+    feats = synth.make_features(1, (256, 320), 64, seed=12, device="cuda:0", channels_last=True)
+    widths = torch.arange(100.0, 226.0, 7.0)
+    x1 = torch.linspace(3.3, 60.0, len(widths))
+    boxes_t = torch.stack((x1, torch.full_like(x1, 20.5), x1 + widths, torch.full_like(x1, 20.5) + 40.0), dim=1)
+    boxes = [OBoxes(boxes_t.cuda())]
+    out, lvl = ours.forward_with_levels(feats, boxes)
+    assert int(lvl.max()) == 0   # all on p2
+    exp = ref.forward([f.contiguous() for f in feats], boxes)
+    torch.testing.assert_close(out, exp, rtol=FWD_RTOL, atol=FWD_ATOL)
+    gout = torch.randn(len(widths), 64, 7, 7, device="cuda:0")
+    for a, b in zip(_grads(ours, feats, boxes, gout), _grads(ref, [f.contiguous() for f in feats], boxes, gout)):
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
