@@ -4,12 +4,13 @@
 //
 // forward  pln_rows_kernel   : one warp per RoI row; non-foreground rows are skipped without reading emb.
 //                              Prototypes are normalised into shared memory once per CTA (K*D*4 <= 28 KB).
-//                              Per-CTA partial hinge sums go to the workspace (fixed order => deterministic).
-//          pln_final_kernel  : prototype-separation term (K x K, one CTA) + ordered sum of the partials.
+//                              Per-CTA partial hinge sums go to the workspace (fixed order => deterministic); the
+//                              prototype-separation term (K x K) is spread over the same grid, one warp per prototype.
+//          pln_final_kernel  : ordered sum of the partials and the separation hinges (one CTA, fixed tree).
 // backward pln_grad_emb_kernel   : one warp per row, d loss/d emb through the normalisation (zeros for inactive rows)
 //          pln_grad_reps_partial : grid (rep, row-segment): ordered compaction of the rows whose active hinge points
 //                                  at this prototype, then a fixed-order sum of their unit embeddings
-//          pln_grad_reps_final   : ordered sum over segments + separation-term gradient + projection.
+//          pln_grad_reps_final   : one CTA per prototype: ordered sum over segments + separation-term gradient + projection.
 // No atomics anywhere: results are run-to-run bit-identical.
 #include "osr_common.cuh"
 
@@ -70,7 +71,7 @@ __device__ __forceinline__ void load_unit_reps(const PlnParams& p, float* rh, fl
 __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constant__ PlnParams p) {
   extern __shared__ __align__(16) float rh[];  // (Kr, D)
   __shared__ float s_part[kWarps][2];
-  load_unit_reps(p, rh, nullptr);
+  load_unit_reps(p, rh, blockIdx.x == 0 ? p.rep_inv_norm : nullptr);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float intra_sum = 0.f, inter_sum = 0.f;
@@ -155,16 +156,9 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
     p.partial[2 * blockIdx.x] = a;
     p.partial[2 * blockIdx.x + 1] = b;
   }
-}
-
-// prototype-separation term (:171-181) + final ordered reduction (:183-187)
-__global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_constant__ PlnParams p) {
-  extern __shared__ __align__(16) float rh[];
-  __shared__ float s_c[kMaxReps];
-  load_unit_reps(p, rh, p.rep_inv_norm);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = warp; k < p.Kr; k += kWarps) {
+  // prototype-separation term (:171-181): one warp per prototype k, spread over the grid (the unit prototypes are
+  // already in shared memory); hinge value to the workspace, arg-min prototype saved for the backward
+  for (int k = blockIdx.x * kWarps + warp; k < p.Kr; k += gridDim.x * kWarps) {
     float best = 1000.f;
     int best_j = -1;
     for (int j = 0; j < p.Kr; ++j) {
@@ -180,11 +174,16 @@ __global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_consta
     }
     const float h = (p.beta + p.alpha) - best;
     if (lane == 0) {
-      s_c[k] = h > 0.f ? h : 0.f;
+      p.partial[2 * gridDim.x + k] = h > 0.f ? h : 0.f;
       p.center_rep[k] = (h > 0.f) ? best_j : -1;
     }
   }
-  __syncthreads();
+}
+
+// final ordered reduction (:183-187) of the per-CTA partial sums and the per-prototype separation hinges
+__global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_constant__ PlnParams p) {
+  __shared__ float s_c[kMaxReps];
+  if (threadIdx.x < p.Kr) s_c[threadIdx.x] = p.partial[2 * p.num_ctas + threadIdx.x];
   // ordered sum of the per-CTA partials: thread t adds partials t, t + 256, ... in that order, then a fixed tree
   __shared__ float s_a[kThreads], s_b[kThreads];
   {
@@ -416,7 +415,7 @@ int fwd_ctas(int R) { return R < 2 * kWarps ? 1 : (R / (2 * kWarps) > 592 ? 592 
 extern "C" {
 
 size_t osr_pln_workspace(int R, int D, int K, int reps_per_class) {
-  const size_t fwd = (size_t)fwd_ctas(R > 0 ? R : 1) * 2 * sizeof(float);
+  const size_t fwd = ((size_t)fwd_ctas(R > 0 ? R : 1) * 2 + (size_t)K * reps_per_class) * sizeof(float);
   const size_t bwd = (size_t)kSeg * K * reps_per_class * D * sizeof(float);
   return osr::align256(fwd > bwd ? fwd : bwd);
 }
@@ -445,13 +444,10 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
   OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  p.num_ctas = 0;
-  if (R > 0) {
-    p.num_ctas = fwd_ctas(R);
-    pln_rows_kernel<<<p.num_ctas, kThreads, smem, s>>>(p);
-    OSR_LAUNCH_CHECK();
-  }
-  pln_final_kernel<<<1, kThreads, smem, s>>>(p);
+  p.num_ctas = fwd_ctas(R > 0 ? R : 1);   // also launched for R == 0: the separation term does not depend on the rows
+  pln_rows_kernel<<<p.num_ctas, kThreads, smem, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  pln_final_kernel<<<1, kThreads, 0, s>>>(p);
   OSR_LAUNCH_CHECK();
   return 0;
 }
