@@ -748,9 +748,15 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     __syncwarp();
   }
   int xc = 0, r = 0;
+  int slot = 0;            // t % nstages and (t / nstages) & 1, kept incrementally (nstages is a run-time value)
+  uint32_t parity = 0;
+  int rxc = 0, rr = 0;     // (chunk, row) of tile t + nstages, the one the producer refills
+  {
+    const int t0 = min(nstages, total);
+    rxc = t0 / hf;
+    rr = t0 - rxc * hf;
+  }
   for (int t = 0; t < total; ++t) {
-    const int slot = t % nstages;
-    const uint32_t parity = (uint32_t)((t / nstages) & 1);
     mbar_wait(&full_bar[slot], parity);
     const float* row = ring + slot * stage_floats + c;
     const int x_lo = xmin + xc * scols, x_hi = min(xmin + wf, x_lo + scols);
@@ -815,8 +821,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     if (warp == 0 && t + nstages < total) {
       if (elect_one()) {
         mbar_wait(&empty_bar[slot], parity);
-        const int tn = t + nstages;
-        const int nxc2 = tn / hf, nr2 = tn - nxc2 * hf;
+        const int nxc2 = rxc, nr2 = rr;
         const int ncols = min(scols, wf - nxc2 * scols);
         const uint32_t bytes = (uint32_t)(ncols * C * 4);
         mbar_expect_tx(&full_bar[slot], bytes);
@@ -851,6 +856,8 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
       default: break;
     }
     if (++r == hf) { r = 0; ++xc; }
+    if (++rr == hf) { rr = 0; ++rxc; }
+    if (++slot == nstages) { slot = 0; parity ^= 1u; }
   }
   // epilogue: 49 x C tile -> shared memory as [c][49] (stride 49 is odd: conflict-free) -> coalesced 16-byte stores
   __syncthreads();   // every warp is done with the ring (all bulk loads have landed and been consumed)

@@ -153,3 +153,19 @@ def test_tcgen05_encoder_in_module_loss_and_grads():
     torch.testing.assert_close(l_tc, l_32, rtol=2e-2, atol=1e-4)   # bf16 operands: stated tolerance of the north star
     l_tc.backward()
     assert m.encoder.weight.grad is not None and torch.isfinite(m.encoder.weight.grad).all()
+
+
+def test_zero_rows_gives_separation_term_only():
+    """R == 0 (an image batch with no sampled RoIs): the loss is the prototype-separation term alone."""
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb
+    pi = synth.make_pln_inputs(8, seed=3, device="cuda:0")
+    emb = torch.zeros(0, pi.enc_w.shape[0], device="cuda:0", requires_grad=True)
+    labels = torch.zeros(0, dtype=torch.int64, device="cuda:0")
+    ious = torch.zeros(0, device="cuda:0")
+    reps = pi.reps.clone().requires_grad_(True)
+    la = pln_loss_from_emb(emb, reps, labels, ious, **_kw())
+    la.backward()
+    lb = opln.pln_loss_from_emb(emb.detach().cpu(), pi.reps.cpu(), labels.cpu(), ious.cpu(), **_kw())
+    torch.testing.assert_close(la.cpu(), lb, rtol=1e-5, atol=1e-8)
+    assert torch.isfinite(reps.grad).all()
