@@ -193,6 +193,26 @@ int osr_pln_encode_fwd(const float* x, const float* W, const float* bias, int R,
 int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, float unk_thr,
                     int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist, void* stream);
 
+/*
+ * Proposal <-> ground-truth matching of the ROI-head sampling glue, all images at once
+ * (label_and_sample_proposals, osrcnn_roi_heads.py:136-230: detectron2 pairwise_iou + Matcher([0.5],[0,1]) +
+ * the matched-IoU gather at :193 + the class assignment of ROIHeads._sample_proposals).
+ *   boxes        (P,4) fp32 xyxy, the per-image proposal lists concatenated (ground-truth boxes already appended
+ *                when PROPOSAL_APPEND_GT is on); box_offsets (N+1) int32 DEVICE: image n owns [off[n], off[n+1]),
+ *                or, when box_counts != NULL, [off[n], off[n] + box_counts[n * box_counts_stride]) - the padded
+ *                (N, Kmax, 4) output of osr_rpn_select_decode with its counts column, no repacking
+ *   gt_boxes     (G,4) fp32, gt_classes (G) int64, gt_offsets (N+1) int32 DEVICE
+ *   max_boxes_per_image  host upper bound of off[n+1]-off[n] (grid sizing only)
+ * Outputs, (P) each: matched_idx int32 = FIRST arg-max GT of the image (0 when the image has no GT),
+ *   matched_iou fp32 = that IoU (bit-exact with torch's op-by-op fp32 evaluation), matched_label int32 = iou >= thr,
+ *   matched_class int64 = gt_classes[matched] or background_label.  No workspace, one launch.
+ */
+int osr_match_label(const float* boxes, const int32_t* box_offsets, const int32_t* box_counts,
+                    int box_counts_stride, const float* gt_boxes, const int64_t* gt_classes,
+                    const int32_t* gt_offsets, int num_images, int max_boxes_per_image, float iou_threshold,
+                    int64_t background_label, int32_t* matched_idx, float* matched_iou, int32_t* matched_label,
+                    int64_t* matched_class, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ from . import _lib, synth
 from .poolers import ROIPooler
 from .pln import pln_encode_tc, pln_loss_from_emb
 from .proposals import rpn_select_decode
+from .sampling import match_proposals
 
 
 @dataclass
@@ -107,6 +108,11 @@ class RoiPathStep:
             idx.append(torch.randperm(c, generator=gs)[:cfg.rois_per_image] + n * sel.kmax)
         self.sample_idx = torch.cat(idx).to(dev)
         self.kmax = sel.kmax
+        # S2 matching inputs: synthetic ground truth + the static offsets of the padded proposal layout
+        self.gt_boxes, self.gt_classes, self.gt_off = synth.make_gt(N, 8, cfg.image_hw, num_known=cfg.num_known,
+                                                                   seed=cfg.seed + 5, device=dev)
+        self.prop_off = torch.arange(0, (N + 1) * sel.kmax, sel.kmax, dtype=torch.int32, device=dev)
+        self.count_col = sel.num_levels
         self.last: Dict[str, torch.Tensor] = {}
         self.events: Optional[List[torch.cuda.Event]] = None
 
@@ -125,7 +131,12 @@ class RoiPathStep:
         # S1
         sel = rpn_select_decode(self.anchors, deltas, ctr, self.image_hw_dev, cfg.pre_nms_topk)
         self._mark(1)
-        # S2 (glue)
+        # S2 (glue): proposal <-> GT matching of ALL kept proposals (osr_match_label, as label_and_sample_proposals
+        # does), then the sampling stand-in: pre-drawn indices (the reference's randperm needs a host sync per image)
+        L2 = sel.counts.shape[1]
+        match = match_proposals(sel.boxes.view(-1, 4), self.prop_off, self.gt_boxes, self.gt_classes, self.gt_off,
+                                self.kmax, iou_threshold=cfg.iou_threshold, background_label=cfg.num_classes,
+                                box_counts=sel.counts[:, self.count_col], box_counts_stride=L2)
         boxes = sel.boxes.view(-1, 4).index_select(0, self.sample_idx)
         rois = torch.cat((self.img_col, boxes), dim=1)
         self._mark(2)
@@ -148,7 +159,7 @@ class RoiPathStep:
         # S3 backward
         g_feats = torch.autograd.grad(pooled, feats_g, self.grad_pooled)
         self._mark(5)
-        self.last = dict(sel=sel, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
+        self.last = dict(sel=sel, match=match, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
                          g_feats=g_feats)
         return loss, sel.counts
 

@@ -1,0 +1,128 @@
+"""ROI-head sampling glue: proposal <-> ground-truth matching and labelled sampling.
+
+Drop-in for ``OpensetROIHeads.label_and_sample_proposals`` (``osrcnn_roi_heads.py:136-230``), same arguments and
+returned ``List[Instances]`` (fields ``proposal_boxes``, ``objectness_logits``, ``gt_classes``, ``ious`` and the
+targets' ``gt_*`` fields).  The per-image ``pairwise_iou`` matrix + ``Matcher`` + matched-IoU gather + class assignment
+run as ONE kernel launch for the whole batch (``osr_match_label``: one thread per proposal, GT boxes in shared memory,
+the G x P matrix is never materialised).  The random subsampling keeps detectron2's ``subsample_labels`` with
+``torch.randperm`` (positives first, then negatives, per image) so a seeded run draws what the reference draws.
+
+``match_proposals`` is the batched tensor-level entry (no ``Instances``), used by the pipeline / bench.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .structures import Boxes, Instances
+
+GT_LOGIT = math.log((1.0 - 1e-10) / (1e-10))
+
+
+def match_proposals(boxes: torch.Tensor, box_offsets: torch.Tensor, gt_boxes: torch.Tensor, gt_classes: torch.Tensor,
+                    gt_offsets: torch.Tensor, max_boxes_per_image: int, *, iou_threshold: float = 0.5,
+                    background_label: int = 80, box_counts: Optional[torch.Tensor] = None,
+                    box_counts_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All images at once.  ``boxes`` (P,4) fp32 = the images' proposal lists concatenated, ``box_offsets`` (N+1)
+    int32 on the device, likewise ``gt_boxes`` (G,4) / ``gt_classes`` (G) int64 / ``gt_offsets``.
+    Returns ``(matched_idx int32, matched_iou fp32, matched_label int32, matched_class int64)``, each (P):
+    detectron2 ``Matcher([thr],[0,1])`` on ``pairwise_iou(gt, proposals)`` + ``gt_classes[matched]`` / background.
+    With ``box_counts`` (int32, device) image n owns ``[off[n], off[n] + box_counts[n * stride])`` - the padded
+    ``RpnSelection`` layout - and rows outside every image are left untouched."""
+    _lib.require_cuda(boxes, box_offsets, gt_boxes, gt_classes, gt_offsets)
+    lib = _lib.lib()
+    dev = boxes.device
+    boxes = boxes.contiguous().float()
+    gt_boxes = gt_boxes.contiguous().float()
+    gt_classes = gt_classes.contiguous().to(torch.int64)
+    assert box_offsets.dtype == torch.int32 and gt_offsets.dtype == torch.int32
+    N = box_offsets.numel() - 1
+    P = boxes.shape[0]
+    midx = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    miou = torch.empty(max(P, 1), dtype=torch.float32, device=dev)
+    mlab = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+    mcls = torch.empty(max(P, 1), dtype=torch.int64, device=dev)
+    if P > 0 and N > 0:
+        rc = lib.osr_match_label(boxes.data_ptr(), box_offsets.data_ptr(), _lib.ptr(box_counts), int(box_counts_stride),
+                                 _lib.ptr(gt_boxes if gt_boxes.numel() else None),
+                                 _lib.ptr(gt_classes if gt_classes.numel() else None), gt_offsets.data_ptr(), int(N),
+                                 int(max_boxes_per_image), float(iou_threshold), int(background_label),
+                                 midx.data_ptr(), miou.data_ptr(), mlab.data_ptr(), mcls.data_ptr(),
+                                 _lib.stream_ptr(dev))
+        _lib.check(rc, "osr_match_label")
+    return midx[:P], miou[:P], mlab[:P], mcls[:P]
+
+
+def subsample_labels(labels: torch.Tensor, num_samples: int, positive_fraction: float, bg_label: int,
+                     randperm: Optional[Callable[[int], torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """detectron2 ``sampling.subsample_labels`` (two ``torch.randperm`` draws on the labels' device)."""
+    rp = randperm or (lambda n: torch.randperm(n, device=labels.device))
+    positive = torch.nonzero((labels != -1) & (labels != bg_label), as_tuple=True)[0]
+    negative = torch.nonzero(labels == bg_label, as_tuple=True)[0]
+    num_pos = min(positive.numel(), int(num_samples * positive_fraction))
+    num_neg = min(negative.numel(), num_samples - num_pos)
+    perm1 = rp(positive.numel())[:num_pos].to(labels.device)
+    perm2 = rp(negative.numel())[:num_neg].to(labels.device)
+    return positive[perm1], negative[perm2]
+
+
+def label_and_sample_proposals(proposals: List[Instances], targets: List[Instances], *, num_classes: int,
+                               batch_size_per_image: int = 512, positive_fraction: float = 0.25,
+                               iou_threshold: float = 0.5, proposal_append_gt: bool = True,
+                               randperm: Optional[Callable[[int], torch.Tensor]] = None) -> List[Instances]:
+    """``OpensetROIHeads.label_and_sample_proposals(proposals, targets)`` (``osrcnn_roi_heads.py:136-230``); the
+    keyword arguments are the module attributes it reads (``num_classes``, ``batch_size_per_image``,
+    ``positive_fraction``, ``proposal_matcher`` threshold, ``proposal_append_gt``).  Like the reference it raises
+    ``IndexError`` for an image without ground truth (the matched-IoU gather at ``:193`` indexes an empty matrix)."""
+    N = len(proposals)
+    assert len(targets) == N
+    if N == 0:
+        return []
+    dev = proposals[0].get("proposal_boxes").tensor.device
+    box_list, logit_list, counts, gcounts = [], [], [], []
+    for p, t in zip(proposals, targets):
+        b = p.get("proposal_boxes").tensor
+        lg = p.get("objectness_logits")
+        g = t.get("gt_boxes").tensor.to(dev)
+        if len(g) == 0:
+            raise IndexError("index 0 is out of bounds for dimension 0 with size 0 "
+                             "(image without ground truth: osrcnn_roi_heads.py:193)")
+        if proposal_append_gt:   # add_ground_truth_to_proposals: GT boxes after the proposals, logit log((1-1e-10)/1e-10)
+            b = torch.cat((b, g), dim=0)
+            lg = torch.cat((lg, GT_LOGIT * torch.ones(len(g), device=dev)), dim=0)
+        box_list.append(b)
+        logit_list.append(lg)
+        counts.append(b.shape[0])
+        gcounts.append(len(g))
+    boxes = torch.cat(box_list, dim=0)
+    gt_boxes = torch.cat([t.get("gt_boxes").tensor.to(dev) for t in targets], dim=0)
+    gt_classes = torch.cat([t.get("gt_classes").to(dev) for t in targets], dim=0)
+    off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    goff = torch.tensor([0] + list(torch.tensor(gcounts).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    midx, miou, mlab, mcls = match_proposals(boxes, off, gt_boxes, gt_classes, goff, max(counts),
+                                             iou_threshold=iou_threshold, background_label=num_classes)
+    out = []
+    b0 = 0
+    for n, (p, t) in enumerate(zip(proposals, targets)):
+        b1 = b0 + counts[n]
+        cls_n = mcls[b0:b1]
+        fg, bg = subsample_labels(cls_n, batch_size_per_image, positive_fraction, num_classes, randperm)
+        sampled = torch.cat([fg, bg], dim=0)
+        q = Instances(p.image_size)
+        q.set("proposal_boxes", Boxes(box_list[n][sampled]))
+        q.set("objectness_logits", logit_list[n][sampled])
+        for name, value in p.get_fields().items():
+            if name not in ("proposal_boxes", "objectness_logits") and not proposal_append_gt:
+                q.set(name, value[sampled])
+        q.set("gt_classes", cls_n[sampled])
+        q.set("ious", miou[b0:b1][sampled])
+        st = midx[b0:b1][sampled].long()
+        for name, value in t.get_fields().items():
+            if name.startswith("gt_") and not q.has(name):
+                q.set(name, value.to(dev)[st] if hasattr(value, "to") else value[st])
+        out.append(q)
+        b0 = b1
+    return out

@@ -139,6 +139,23 @@ def make_rois(num_images: int, rois_per_image: int, image_hw=(800, 1333), *, see
     return out
 
 
+def make_gt(num_images: int, gt_per_image: int = 8, image_hw=(800, 1333), *, num_known: int = 20, seed: int = 5,
+            device="cpu") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Synthetic ground truth: ``gt_per_image`` boxes per image, side U(32,512), class
+    U{0..K-1}.  Returns concatenated ``(boxes (G,4), classes (G) int64, offsets (N+1) int32)``."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    h, w = image_hw
+    G = num_images * gt_per_image
+    side = torch.rand(G, 2, generator=g) * (512.0 - 32.0) + 32.0
+    ctr = torch.rand(G, 2, generator=g) * torch.tensor([float(w), float(h)])
+    x1 = (ctr[:, 0] - side[:, 0] / 2).clamp(0, w); x2 = (ctr[:, 0] + side[:, 0] / 2).clamp(0, w)
+    y1 = (ctr[:, 1] - side[:, 1] / 2).clamp(0, h); y2 = (ctr[:, 1] + side[:, 1] / 2).clamp(0, h)
+    boxes = torch.stack((x1, y1, x2, y2), dim=1)
+    classes = torch.randint(0, num_known, (G,), generator=g)
+    off = torch.arange(0, G + 1, gt_per_image, dtype=torch.int32)
+    return boxes.to(device), classes.to(device), off.to(device)
+
+
 @dataclass
 class PLNInputs:
     roi_features: torch.Tensor   # (R, feat_dim)

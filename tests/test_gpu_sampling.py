@@ -1,0 +1,128 @@
+"""GPU parity of the sampling glue (osr_match_label + label_and_sample_proposals) against the oracle."""
+import pytest
+import torch
+
+from oracle import sampling as osamp
+from oracle.structures import Boxes as OBoxes, Instances as OInstances, pairwise_iou
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(n_img, n_prop, n_gt, seed, hw=(800, 1333)):
+    g = torch.Generator().manual_seed(seed)
+    props, tgts = [], []
+    for i in range(n_img):
+        h, w = hw
+        G = n_gt if isinstance(n_gt, int) else n_gt[i]
+        gc = torch.rand(G, 2, generator=g) * torch.tensor([w * 0.8, h * 0.8])
+        gwh = torch.rand(G, 2, generator=g) * 480 + 32
+        gtb = torch.cat((gc, (gc + gwh).minimum(torch.tensor([float(w), float(h)]))), 1)
+        P = n_prop if isinstance(n_prop, int) else n_prop[i]
+        # proposals: jittered copies of GT boxes (so many IoUs straddle 0.5) + random boxes + exact duplicates
+        k = P // 2
+        src = gtb[torch.randint(0, G, (k,), generator=g)]
+        jit = src + (torch.rand(k, 4, generator=g) - 0.5) * 0.6 * (src[:, 2:] - src[:, :2]).repeat(1, 2)
+        c = torch.rand(P - k, 2, generator=g) * torch.tensor([float(w), float(h)])
+        rwh = torch.rand(P - k, 2, generator=g) * 300 + 4
+        rnd = torch.cat((c, c + rwh), 1)
+        pb = torch.cat((jit, rnd), 0)
+        pb = torch.stack((pb[:, 0].clamp(0, w), pb[:, 1].clamp(0, h), pb[:, 2].clamp(0, w), pb[:, 3].clamp(0, h)), 1)
+        pb[-1] = gtb[0]                       # exact GT duplicate: IoU == 1
+        if P >= 2:
+            pb[-2] = torch.tensor([5., 5., 5., 9.])  # zero-area box
+        props.append(pb)
+        tgts.append((gtb, torch.randint(0, 20, (G,), generator=g)))
+    return props, tgts
+
+
+@pytest.mark.parametrize("n_img,n_prop,n_gt", [(4, 7323, 8), (3, [100, 2000, 1], [1, 300, 5]), (1, 33, 2)])
+def test_match_label_bit_exact(n_img, n_prop, n_gt):
+    from osr_b200.sampling import match_proposals
+    props, tgts = _make(n_img, n_prop, n_gt, seed=3)
+    dev = "cuda:0"
+    counts = [p.shape[0] for p in props]
+    gcounts = [t[0].shape[0] for t in tgts]
+    off = torch.tensor([0] + torch.tensor(counts).cumsum(0).tolist(), dtype=torch.int32, device=dev)
+    goff = torch.tensor([0] + torch.tensor(gcounts).cumsum(0).tolist(), dtype=torch.int32, device=dev)
+    midx, miou, mlab, mcls = match_proposals(torch.cat(props).to(dev), off, torch.cat([t[0] for t in tgts]).to(dev),
+                                             torch.cat([t[1] for t in tgts]).to(dev), goff, max(counts),
+                                             iou_threshold=0.5, background_label=80)
+    b0 = 0
+    for p, (gb, gc) in zip(props, tgts):
+        for where in ("cpu", dev):   # torch's own op chain on the CPU and on the GPU
+            m = pairwise_iou(OBoxes(gb.to(where)), OBoxes(p.to(where)))
+            idx, lab = osamp.matcher(m, 0.5)
+            iou = m[idx, torch.arange(m.shape[1], device=where)]
+            sl = slice(b0, b0 + p.shape[0])
+            assert torch.equal(midx[sl].cpu().long(), idx.cpu())
+            assert torch.equal(miou[sl].cpu(), iou.cpu()), "matched IoU must be bit-exact"
+            assert torch.equal(mlab[sl].cpu().to(torch.int8), lab.cpu())
+            cls = gc.to(where)[idx]
+            cls[lab == 0] = 80
+            assert torch.equal(mcls[sl].cpu(), cls.cpu())
+        b0 += p.shape[0]
+
+
+def test_label_and_sample_proposals_matches_oracle():
+    from osr_b200.sampling import label_and_sample_proposals
+    from osr_b200.structures import Boxes, Instances
+    props, tgts = _make(3, [7323, 500, 40], 8, seed=11)
+    dev = "cuda:0"
+    ours_p, ours_t, ref_p, ref_t = [], [], [], []
+    for p, (gb, gc) in zip(props, tgts):
+        lg = torch.linspace(3, -3, p.shape[0])
+        a = Instances((800, 1333)); a.set("proposal_boxes", Boxes(p.to(dev))); a.set("objectness_logits", lg.to(dev))
+        b = Instances((800, 1333)); b.set("gt_boxes", Boxes(gb.to(dev))); b.set("gt_classes", gc.to(dev))
+        ours_p.append(a); ours_t.append(b)
+        c = OInstances((800, 1333)); c.set("proposal_boxes", OBoxes(p)); c.set("objectness_logits", lg)
+        d = OInstances((800, 1333)); d.set("gt_boxes", OBoxes(gb)); d.set("gt_classes", gc)
+        ref_p.append(c); ref_t.append(d)
+    # identical "random" draws on both sides: a seeded CPU permutation stream consumed in the same order
+    def stream(seed):
+        g = torch.Generator().manual_seed(seed)
+        return lambda n: torch.randperm(n, generator=g)
+    kw = dict(num_classes=80, batch_size_per_image=512, positive_fraction=0.25)
+    ours = label_and_sample_proposals(ours_p, ours_t, randperm=stream(5), **kw)
+    ref = osamp.label_and_sample_proposals(ref_p, ref_t, randperm=stream(5), **kw)
+    for a, b in zip(ours, ref):
+        assert len(a) == len(b)
+        assert torch.equal(a.get("proposal_boxes").tensor.cpu(), b.get("proposal_boxes").tensor)
+        assert torch.equal(a.get("gt_classes").cpu(), b.get("gt_classes"))
+        assert torch.equal(a.get("ious").cpu(), b.get("ious"))
+        assert torch.equal(a.get("gt_boxes").tensor.cpu(), b.get("gt_boxes").tensor)
+        assert torch.equal(a.get("objectness_logits").cpu(), b.get("objectness_logits"))
+
+
+def test_image_without_gt_raises_like_the_reference():
+    from osr_b200.sampling import label_and_sample_proposals
+    from osr_b200.structures import Boxes, Instances
+    a = Instances((100, 100)); a.set("proposal_boxes", Boxes(torch.rand(5, 4).cuda())); a.set("objectness_logits", torch.zeros(5).cuda())
+    b = Instances((100, 100)); b.set("gt_boxes", Boxes(torch.empty(0, 4).cuda())); b.set("gt_classes", torch.empty(0, dtype=torch.int64).cuda())
+    with pytest.raises(IndexError):
+        label_and_sample_proposals([a], [b], num_classes=80)
+
+
+def test_padded_layout_with_counts_column():
+    """The RpnSelection layout: (N, Kmax, 4) padded boxes + a strided counts column; rows past the count untouched."""
+    from osr_b200.sampling import match_proposals
+    props, tgts = _make(3, [50, 7, 31], 4, seed=9)
+    dev = "cuda:0"
+    kmax = 64
+    padded = torch.full((3, kmax, 4), float("nan"))
+    counts = torch.zeros(3, 7, dtype=torch.int32)
+    for n, p in enumerate(props):
+        padded[n, :p.shape[0]] = p
+        counts[n, 5] = p.shape[0]
+    counts = counts.to(dev)
+    off = torch.arange(0, 4 * kmax, kmax, dtype=torch.int32, device=dev)
+    goff = torch.arange(0, 13, 4, dtype=torch.int32, device=dev)
+    midx, miou, mlab, mcls = match_proposals(padded.view(-1, 4).to(dev), off, torch.cat([t[0] for t in tgts]).to(dev),
+                                             torch.cat([t[1] for t in tgts]).to(dev), goff, kmax,
+                                             background_label=80, box_counts=counts[:, 5], box_counts_stride=7)
+    for n, (p, (gb, gc)) in enumerate(zip(props, tgts)):
+        m = pairwise_iou(OBoxes(gb), OBoxes(p))
+        idx, lab = osamp.matcher(m, 0.5)
+        sl = slice(n * kmax, n * kmax + p.shape[0])
+        assert torch.equal(midx[sl].cpu().long(), idx)
+        assert torch.equal(miou[sl].cpu(), m[idx, torch.arange(p.shape[0])])
+        assert torch.equal(mlab[sl].cpu().to(torch.int8), lab)
