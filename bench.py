@@ -247,8 +247,16 @@ def run_ours(args, rank, local_rank, world):
     dom = max(alg, key=lambda k: stages[k])
     path_bytes = sum(alg.values())
     path_ms = sum(stages[k] for k in alg)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
+    if cfg.channels_last and os.path.exists(tpath):   # ncu capture of the same workload (per launch), committed
+        with open(tpath) as f:
+            tj = json.load(f)
+        if dom in tj:
+            traffic, traffic_src = tj[dom]["dram_bytes_per_launch"], tj[dom]["source"]
     roof = {"bound": "hbm", "kernel": dom, "achieved": per_stage[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": per_stage[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "frac": per_stage[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
+            "alg_bytes": alg[dom], "peak_source": peak_src,
             "path_aggregate": {"alg_bytes": path_bytes, "ms": path_ms, "gbs": path_bytes / (path_ms * 1e-3) / 1e9,
                                "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak},
             "stages": per_stage, "touched_feature_pixels": U}
@@ -307,7 +315,7 @@ def run_ours(args, rank, local_rank, world):
                    "feature_layout": "channels_last" if cfg.channels_last else "NCHW",
                    "proposal_mode": "as_shipped (find_top_proposals.py:112-120 commented out)",
                    "l2": "inputs larger than L2 (FPN maps 1.46 GB + 0.41 GB pooled grads per step vs 126 MB L2)",
-                   "timed_stages": "S1 proposals, S2 sampling glue (torch gather), S3 ROIAlign fwd, S5 encoder+PLN loss "
+                   "timed_stages": "S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, S5 encoder+PLN loss "
                                    "fwd/bwd, S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))",
                    "parallelism": f"dp{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,

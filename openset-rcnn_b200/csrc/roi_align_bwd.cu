@@ -36,7 +36,7 @@ constexpr int kWRoi = 2 * kFW * kP;     // floats per RoI in that table: [y rows
 struct RoiInfo {
   int x0, x1, y0, y1;  // inclusive pixel bounds of the footprint (exact); x1 < x0 => empty
   int level;
-  int flags;           // bit 0: the RoI's dense weight rows are in the workspace table (footprint <= kFW x kFW)
+  int flags;           // bit 0 / bit 1: the RoI's y / x weight rows are in the workspace table (extent <= kFW)
 };
 struct __align__(16) RoiInfoPacked {   // 16 bytes: the per-tile scans read it with one coalesced 16-byte load per RoI
   short x0, x1, y0, y1;
@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(kPrepWarps * 32) roi_bwd_prep_kernel(const __g
     xhi = max(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
   }
   const bool nonempty = (yhi >= 0) && (xhi >= 0);
-  const bool pre = nonempty && (yhi - ylo < kFW) && (xhi - xlo < kFW);
+  const bool prey = nonempty && (yhi - ylo < kFW), prex = nonempty && (xhi - xlo < kFW);
   __syncwarp();
-  if (pre && lane < 2 * kP) {
+  if (lane < 2 * kP && (isy ? prey : prex)) {
     float* wa = w + (isy ? 0 : kFW * kP);
     const int base = isy ? ylo : xlo;
     for_bin_samples(isy ? g.start_h : g.start_w, isy ? g.bin_h : g.bin_w, isy ? g.grid_h : g.grid_w, L, bin,
@@ -137,18 +137,22 @@ __global__ void __launch_bounds__(kPrepWarps * 32) roi_bwd_prep_kernel(const __g
                     });
   }
   __syncwarp();
-  if (pre) {
+  float* dst = p.wfull + (int64_t)m * kWRoi;
+  if (prey) {
     const float ic = 1.0f / g.count;
-    float* dst = p.wfull + (int64_t)m * kWRoi;
-    const int ny = (yhi - ylo + 1) * kP, nx = (xhi - xlo + 1) * kP;
+    const int ny = (yhi - ylo + 1) * kP;
     for (int i = lane; i < ny; i += 32) dst[i] = w[i] * ic;
+  }
+  if (prex) {
+    const int nx = (xhi - xlo + 1) * kP;
     for (int i = lane; i < nx; i += 32) dst[kFW * kP + i] = w[kFW * kP + i];
   }
+  const int pre = (prey ? 1 : 0) | (prex ? 2 : 0);
   if (lane == 0) {
     RoiInfoPacked q;
     q.x0 = (short)(nonempty ? xlo : 1); q.x1 = (short)(nonempty ? xhi : 0);
     q.y0 = (short)(nonempty ? ylo : 1); q.y1 = (short)(nonempty ? yhi : 0);
-    q.level = level; q.pad = pre ? 1 : 0;
+    q.level = level; q.pad = pre;
     p.info[m] = q;
   }
 }
@@ -469,18 +473,17 @@ constexpr int kCS = 4;                      // sub-tiles (stacked vertically) pe
 constexpr int kCH = kCT * kCS;              // CTA tile rows
 constexpr int kCWarps = 4;                  // warps per CTA = 32-channel groups per slab
 constexpr int kCThreads = kCWarps * 32;
-constexpr int kCNB = 12;                    // RoIs whose tables are resident at once
+constexpr int kCNB = 24;                    // RoIs whose tables are resident at once
 constexpr int kGBlk = 32 * kP * kP;         // floats of one (RoI, 32-channel) block of grad_out = 1568
 
 struct __align__(16) ClSmem {
   float acc[kCWarps][kCT * kCW * 32];       // [warp][pixel][lane]
   float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
-  float wy[kCNB][kCH * kP];                 // dense [row][bin], pre-multiplied by 1/count
-  float wx[kCNB][kCW * kP];                 // dense [col][bin]
   float4 yrow[kCNB][kCH];                   // (w(p0), w(p0+1), w(p0+2), code): code 0..4 = p0, 5 = dense, 6 = empty
   float4 xcol[kCNB][kCW];                   // same per tile column
   uchar2 run[kCNB][8];                      // [k] = (first, last + 1) tile column whose code is k (k = 0..5)
   BatchEntry e[kCNB];
+  int2 org[kCNB];                           // (y0, x0) of the RoI's footprint: origin of its rows in the workspace table
   unsigned stmask[kCS];                     // bit j: RoI j of the batch puts weight on sub-tile st
   int warp_cnt[kCWarps + 1];
   int nb, next_pos;
@@ -550,7 +553,8 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
   const int tid = threadIdx.x;
   const int nb = S.nb;
   // one thread per (RoI, tile row | tile column): fetch its 7 bin weights (precomputed per RoI by the prep kernel;
-  // footprints wider than kFW re-derive them from the samples), keep them dense for the rare > 3-bin rows, pack.
+  // extents wider than kFW re-derive them from the samples) and pack them.  Rows / columns in more than 3 bins (code 5;
+  // only possible for extents of a few pixels, which are always in the table) re-read the table when they are used.
   for (int q = tid; q < nb * (kCH + kCW); q += kCThreads) {
     const int j = q / (kCH + kCW);
     const int r = q - j * (kCH + kCW);
@@ -559,11 +563,12 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
     const RoiInfo info = load_info(p.info + m);
     const int pos = isy ? ty0 + r : tx0 + (r - kCH);
     const int base = isy ? info.y0 : info.x0, last = isy ? info.y1 : info.x1;
-    float* wd = isy ? &S.wy[j][r * kP] : &S.wx[j][(r - kCH) * kP];
+    float* wd = &S.sg[0][0] + tid * 8;   // thread-private scratch (the staging buffers are idle while tables are built)
+    if (r == 0) S.org[j] = make_int2(info.y0, info.x0);
 #pragma unroll
     for (int b = 0; b < kP; ++b) wd[b] = 0.f;
     if (pos >= base && pos <= last) {
-      if (info.flags & 1) {
+      if (info.flags & (isy ? 1 : 2)) {
         const float* src = p.wfull + (int64_t)m * kWRoi + (isy ? 0 : kFW * kP) + (pos - base) * kP;
 #pragma unroll
         for (int b = 0; b < kP; ++b) wd[b] = __ldg(src + b);
@@ -620,7 +625,7 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
 // (49 floats, stride-49 across lanes: conflict-free).  The <= 3 bins of the row are addressed dynamically in shared
 // memory, so there is no per-first-bin code replication (the register-resident variant with a 5-way switch per row
 // was instruction-cache bound).
-__device__ __forceinline__ void cl_fold_row(const float* gl, const ClSmem& S, int j, int r, float (&rg)[kP]) {
+__device__ __forceinline__ void cl_fold_row(const float* gl, const ClSmem& S, int j, int r, const float* wdense, float (&rg)[kP]) {
   const float4 w = S.yrow[j][r];
   const int code = __float_as_int(w.w);
   if (code < 5) {
@@ -635,10 +640,9 @@ __device__ __forceinline__ void cl_fold_row(const float* gl, const ClSmem& S, in
 #pragma unroll
     for (int b = 0; b < kP; ++b) rg[b] = 0.f;
     if (code == 5) {    // row inside more than 3 bins: dense
-      const float* wd = &S.wy[j][r * kP];
 #pragma unroll 1
       for (int a = 0; a < kP; ++a) {
-        const float wa = wd[a];
+        const float wa = __ldg(wdense + a);
 #pragma unroll
         for (int b = 0; b < kP; ++b) rg[b] = fmaf(wa, gl[a * kP + b], rg[b]);
       }
@@ -738,8 +742,11 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
           cp_async_wait<0>();
           __syncwarp();
           float rg[kCT][kP];
+          const int2 org = S.org[j];
+          const float* wtab = p.wfull + (int64_t)S.e[j].m * kWRoi;   // dense rows, only dereferenced for code-5 rows / columns
 #pragma unroll
-          for (int r = 0; r < kCT; ++r) cl_fold_row(sg + lane * (kP * kP), S, j, st * kCT + r, rg[r]);
+          for (int r = 0; r < kCT; ++r)
+            cl_fold_row(sg + lane * (kP * kP), S, j, st * kCT + r, wtab + (ty0 + st * kCT + r - org.x) * kP, rg[r]);
           __syncwarp();   // every lane is done with the staged block: refill it while the columns are walked
           nj = cl_next_pair(S, st, m);
           if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
@@ -752,12 +759,15 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
           const uchar2 dn = S.run[j][5];      // columns that sit in more than 3 bins (bins narrower than half a pixel)
           for (int x = dn.x; x < dn.y; ++x) {
             if (__float_as_int(xcol[x].w) != 5) continue;
-            const float* wd = &S.wx[j][x * kP];
+            const float* wd = wtab + kFW * kP + (tx0 + x - org.y) * kP;
+            float wv[kP];
+#pragma unroll
+            for (int b = 0; b < kP; ++b) wv[b] = __ldg(wd + b);
 #pragma unroll
             for (int r = 0; r < kCT; ++r) {
               float v = accl[(r * kCW + x) * 32];
 #pragma unroll
-              for (int b = 0; b < kP; ++b) v = fmaf(wd[b], rg[r][b], v);
+              for (int b = 0; b < kP; ++b) v = fmaf(wv[b], rg[r][b], v);
               accl[(r * kCW + x) * 32] = v;
             }
           }

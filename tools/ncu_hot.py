@@ -8,7 +8,7 @@ rows = list(csv.reader(io.StringIO(txt)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 ci = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+body = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[0] != "Address"]
 tot = sum(int(r[ci["# Samples"]] or 0) for r in body)
 inst = sum(int(r[ci["Instructions Executed"]] or 0) for r in body)
 print(f"total samples {tot}, warp instructions {inst}")
