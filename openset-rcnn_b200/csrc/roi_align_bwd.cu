@@ -473,7 +473,7 @@ constexpr int kCS = 4;                      // sub-tiles (stacked vertically) pe
 constexpr int kCH = kCT * kCS;              // CTA tile rows
 constexpr int kCWarps = 4;                  // warps per CTA = 32-channel groups per slab
 constexpr int kCThreads = kCWarps * 32;
-constexpr int kCNB = 24;                    // RoIs whose tables are resident at once
+constexpr int kCNB = 32;                    // RoIs whose tables are resident at once
 constexpr int kGBlk = 32 * kP * kP;         // floats of one (RoI, 32-channel) block of grad_out = 1568
 
 struct __align__(16) ClSmem {
