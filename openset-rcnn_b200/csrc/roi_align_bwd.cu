@@ -691,7 +691,8 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClSmem& S = *reinterpret_cast<ClSmem*>(smem_raw);
 
-  int t = blockIdx.x, level = 0;
+  // coarsest level first: its few tiles see the most (and largest) RoIs, so the longest CTAs start early
+  int t = (int)(gridDim.x - 1 - blockIdx.x), level = 0;
   while (level + 1 < p.L.num_levels && t >= p.cl_tile_base[level + 1]) ++level;
   t -= p.cl_tile_base[level];
   const int per_img = p.cl_tiles_x[level] * p.cl_tiles_y[level];
