@@ -279,6 +279,28 @@ def run_ours(args, rank, local_rank, world):
                "value_per_gpu": N * 1e3 / alt_ms, "steps": 5}
         del alt_feats
 
+    # ---- north-star variant at N > 1: PLN loss over the global batch (NCCL all-gather of the embeddings) ---------
+    gathered = None
+    if world > 1:
+        for _ in range(3):
+            path.step(gather_pln=True)
+        torch.cuda.synchronize(dev)
+        barrier(world)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(10):
+            path.step(gather_pln=True)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        g_ms = max_over_ranks(g0.elapsed_time(g1), world, dev) / 10
+        R_loc = N * cfg.rois_per_image
+        gathered = {"ms_per_step": g_ms, "value": world * N * 1e3 / g_ms, "steps": 10,
+                    "all_gather_bytes_received_per_rank": (world - 1) * R_loc * (cfg.emb_dim * 4 + 8),
+                    "note": "same step with the PLN loss evaluated over the global batch: all_gather_into_tensor of "
+                            "(emb, label, iou) over NVLink, every rank then runs the loss kernels on W*R rows "
+                            "(osr_b200/dist.py); the headline value keeps the reference's per-rank loss"}
+        barrier(world)
+
     # ---- end to end: inputs start in pinned host memory every step ----------------------------------
     del path
     torch.cuda.empty_cache()
@@ -321,6 +343,8 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
         "stage_ms": stages, "alt_layout": alt,
     }
+    if gathered is not None:
+        line["gathered_pln"] = gathered
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg)
     print(json.dumps(line), flush=True)

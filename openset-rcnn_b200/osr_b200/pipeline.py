@@ -23,6 +23,7 @@ from .poolers import ROIPooler
 from .pln import pln_encode_tc, pln_loss_from_emb
 from .proposals import rpn_select_decode
 from .sampling import match_proposals
+from .dist import gathered_pln_loss
 
 
 @dataclass
@@ -121,7 +122,7 @@ class RoiPathStep:
         if self.events is not None:
             self.events[i].record()
 
-    def step(self, deltas=None, ctr=None, feats=None, stage_events: bool = False):
+    def step(self, deltas=None, ctr=None, feats=None, stage_events: bool = False, gather_pln: bool = False):
         cfg = self.cfg
         deltas = self.deltas if deltas is None else deltas
         ctr = self.ctr if ctr is None else ctr
@@ -151,9 +152,12 @@ class RoiPathStep:
         else:
             emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
         reps = pi.reps.requires_grad_(True)
-        loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, num_known_classes=cfg.num_known,
-                                 alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,
-                                 iou_threshold=cfg.iou_threshold)
+        kw = dict(num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,
+                  iou_threshold=cfg.iou_threshold)
+        if gather_pln:   # north-star variant: NCCL all-gather of (emb, label, iou), global-batch loss (dist.py)
+            loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, **kw)
+        else:            # the reference's semantics: per-rank loss
+            loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, **kw)
         g_emb, g_reps = torch.autograd.grad(loss, [emb, reps])
         self._mark(4)
         # S3 backward
