@@ -296,9 +296,11 @@ def run_ours(args, rank, local_rank, world):
         R_loc = N * cfg.rois_per_image
         gathered = {"ms_per_step": g_ms, "value": world * N * 1e3 / g_ms, "steps": 10,
                     "all_gather_bytes_received_per_rank": (world - 1) * R_loc * (cfg.emb_dim * 4 + 8),
-                    "note": "same step with the PLN loss evaluated over the global batch: all_gather_into_tensor of "
-                            "(emb, label, iou) over NVLink, every rank then runs the loss kernels on W*R rows "
-                            "(osr_b200/dist.py); the headline value keeps the reference's per-rank loss"}
+                    "note": "same step with the PLN loss evaluated over the global batch: the tcgen05 encoder GEMM's "
+                            "epilogue stores its tiles into every rank's symmetric-memory buffer over NVLink (fused "
+                            "all-gather, osr_pln_encode_gather_fwd), labels/ious by NCCL all_gather, every rank then "
+                            "runs the loss kernels on W*R rows (osr_b200/dist.py); the headline value keeps the "
+                            "reference's per-rank loss"}
         barrier(world)
 
     # ---- end to end: inputs start in pinned host memory every step ----------------------------------

@@ -183,6 +183,18 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
 size_t osr_pln_encode_workspace(int R, int F, int E);
 int osr_pln_encode_fwd(const float* x, const float* W, const float* bias, int R, int F, int E, float* emb,
                        void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * The same GEMM FUSED with the all-gather of the embeddings that the multi-GPU (gathered) PLN loss needs: the epilogue
+ * stores each output tile straight into every rank's (world*R, E) fp32 buffer at rows [rank*R, rank*R + R) - its own
+ * and the peers', which the caller maps into this process (CUDA IPC / torch symmetric memory; NVLink P2P stores).
+ * h_peer_buffers: HOST array of `world` device addresses, entry r = rank r's buffer as seen from this process.
+ * multicast_buffer: the NVLS multicast mapping of the same buffer (0 if none): one multimem.st per 16 bytes, replicated
+ * by the NVSwitch into every rank's copy, instead of `world` P2P stores.
+ * The caller brackets the call with a cross-rank barrier (peers done reading the previous contents / all stores landed).
+ */
+int osr_pln_encode_gather_fwd(const float* x, const float* W, const float* bias, int R, int F, int E,
+                              const uint64_t* h_peer_buffers, int world, int rank, uint64_t multicast_buffer,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * PLN.inference nearest-prototype classification (prototype_learning_network.py:203-226), all images at once:

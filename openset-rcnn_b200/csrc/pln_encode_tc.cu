@@ -76,10 +76,17 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+constexpr int kMaxPeers = 16;
 struct EncParams {
   const float* bias;
-  float* emb;
+  float* emb;              // destination 0 (local)
   int R, F, E;
+  // fused all-gather: the epilogue stores every tile into `num_outs` buffers (this rank's and its peers', mapped
+  // through NVLink) at row offset `row_off` - the embeddings never take a second trip through HBM or a collective.
+  float* outs[kMaxPeers];
+  int num_outs;
+  int64_t row_off;
+  float* mc;               // NVLS multicast mapping of the same buffer (NULL: one P2P store per destination)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -169,18 +176,37 @@ __global__ void __launch_bounds__(kThreads, 1)
             "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < p.R) {
-        float* out = p.emb + (int64_t)row * p.E + n0 + c0;
+      // bias, then transpose the 32 x 32 chunk through shared memory (the operand stages are idle: every MMA has
+      // retired) so that each store instruction writes four 128-byte row segments - what NVLink peers want -
+      // instead of 32 scattered 16-byte pieces
+      float* tr = reinterpret_cast<float*>(sA) + q * (32 * 33);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o;
-          o.x = __uint_as_float(v[j + 0]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 0) : 0.f);
-          o.y = __uint_as_float(v[j + 1]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 1) : 0.f);
-          o.z = __uint_as_float(v[j + 2]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 2) : 0.f);
-          o.w = __uint_as_float(v[j + 3]) + (p.bias ? __ldg(p.bias + n0 + c0 + j + 3) : 0.f);
-          *reinterpret_cast<float4*>(out + j) = o;
+      for (int j = 0; j < 32; ++j)
+        tr[lane * 33 + j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+      __syncwarp();
+      const int sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 1
+      for (int d = 0; d < (p.mc ? 1 : p.num_outs); ++d) {
+        float* base = p.mc ? p.mc : p.outs[d];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sub;
+          const int grow = m0 + q * 32 + rr;
+          if (grow < p.R) {
+            const float* sp = tr + rr * 33 + c4;
+            const float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            float* out = base + (p.row_off + grow) * p.E + n0 + c0 + c4;
+            if (p.mc) {
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(o.x), "f"(o.y),
+                           "f"(o.z), "f"(o.w)
+                           : "memory");
+            } else {
+              *reinterpret_cast<float4*>(out) = o;
+            }
+          }
         }
       }
+      __syncwarp();
     }
   }
   // teardown
@@ -237,8 +263,32 @@ size_t osr_pln_encode_workspace(int R, int F, int E) {
   return osr::align256((size_t)(R > 0 ? R : 1) * F * 2) + osr::align256((size_t)E * F * 2) + 256;
 }
 
+static int encode_launch(const float* x, const float* W, const float* bias, int R, int F, int E, float* const* outs,
+                         int num_outs, int64_t row_off, float* mc, void* workspace, size_t workspace_bytes, void* stream);
+
 int osr_pln_encode_fwd(const float* x, const float* W, const float* bias, int R, int F, int E, float* emb,
                        void* workspace, size_t workspace_bytes, void* stream) {
+  float* outs[1] = {emb};
+  return encode_launch(x, W, bias, R, F, E, outs, 1, 0, nullptr, workspace, workspace_bytes, stream);
+}
+
+int osr_pln_encode_gather_fwd(const float* x, const float* W, const float* bias, int R, int F, int E,
+                              const uint64_t* h_peer_buffers, int world, int rank, uint64_t multicast_buffer,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !h_peer_buffers)
+    return osr::fail_arg(OSR_E_ARG, "pln_encode_gather: bad world/rank (1 <= world <= %d) or null buffer list", kMaxPeers);
+  float* outs[kMaxPeers];
+  for (int d = 0; d < world; ++d) {   // own buffer first, then the peers in ring order (spreads the NVLink traffic)
+    outs[d] = reinterpret_cast<float*>(static_cast<uintptr_t>(h_peer_buffers[(rank + d) % world]));
+    if (!outs[d]) return osr::fail_arg(OSR_E_ARG, "pln_encode_gather: null peer buffer %d", d);
+  }
+  return encode_launch(x, W, bias, R, F, E, outs, world, (int64_t)rank * R,
+                       reinterpret_cast<float*>(static_cast<uintptr_t>(multicast_buffer)), workspace, workspace_bytes, stream);
+}
+
+static int encode_launch(const float* x, const float* W, const float* bias, int R, int F, int E, float* const* outs,
+                         int num_outs, int64_t row_off, float* mc, void* workspace, size_t workspace_bytes, void* stream) {
+  float* emb = outs[0];
   if (R < 0 || F <= 0 || E <= 0) return osr::fail_arg(OSR_E_ARG, "pln_encode: bad R/F/E");
   if (F % BK != 0 || E % BN != 0)
     return osr::fail_arg(OSR_E_SHAPE, "pln_encode: feature dim %d must be a multiple of %d and embedding dim %d of %d", F, BK, E, BN);
@@ -263,6 +313,10 @@ int osr_pln_encode_fwd(const float* x, const float* W, const float* bias, int R,
     return osr::fail_arg(OSR_E_ARG, "pln_encode: cuTensorMapEncodeTiled failed");
   EncParams p;
   p.bias = bias; p.emb = emb; p.R = R; p.F = F; p.E = E;
+  p.num_outs = num_outs; p.row_off = row_off; p.mc = mc;
+  for (int d = 0; d < kMaxPeers; ++d) p.outs[d] = d < num_outs ? outs[d] : nullptr;
+  for (int d = 0; d < num_outs; ++d)
+    if (reinterpret_cast<uintptr_t>(outs[d]) & 15) return osr::fail_arg(OSR_E_ARG, "pln_encode: output buffers must be 16-byte aligned");
   OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   pln_encode_tc_kernel<<<dim3(osr::ceil_div(R, BM), E / BN), kThreads, kSmemBytes, s>>>(ma, mb, p);
   OSR_LAUNCH_CHECK();

@@ -71,6 +71,9 @@ SIGNATURES = {
     "osr_pln_encode_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "osr_pln_encode_fwd": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "osr_pln_encode_gather_fwd": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
+        C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_nearest": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p]),

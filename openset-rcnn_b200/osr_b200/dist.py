@@ -51,6 +51,90 @@ def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def _loss_on_global_rows(emb, emb_all_const, reps, labels_all, ious_all, rank, world, loss_fn, **kw):
+    """Global-batch loss given the gathered rows: local rows keep their autograd edge, remote rows are constants
+    (their gradient lives on their own rank)."""
+    R = emb.shape[0]
+    emb_all = emb_all_const.clone()
+    emb_all[rank * R:(rank + 1) * R] = emb
+    return loss_fn(emb_all, reps, labels_all, ious_all, r_norm=float(max(world * R, 1)),
+                   center_weight=float(world), emb_grad_scale=float(world), **kw)
+
+
+def _gather_meta(labels, ious, group):
+    meta = torch.stack((labels.to(torch.float32), ious.to(torch.float32)), dim=1)  # labels < 2^24: exact in fp32
+    meta_all = all_gather_rows(meta, group)
+    return meta_all[:, 0].to(torch.int64), meta_all[:, 1].contiguous()
+
+
+class FusedEncoderGather:
+    """Encoder GEMM fused with the all-gather of its output (B200: tcgen05 GEMM whose epilogue stores every tile into
+    all ranks' ``(W*R, E)`` buffers over NVLink - ``osr_pln_encode_gather_fwd``).  The buffers are torch symmetric
+    memory (``torch.distributed._symmetric_memory``): allocated once, rendezvoused once, peer addresses handed to the
+    kernel; with NVLS multicast support one ``multimem.st`` per 16 bytes is replicated by the NVSwitch.
+    ``__call__(x, weight, bias)`` returns ``(emb_local, emb_all)``, views of this rank's buffer, valid until the
+    call after next."""
+
+    def __init__(self, rows_per_rank: int, emb_dim: int, device, group=None, multicast: Optional[bool] = None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.R, self.E = int(rows_per_rank), int(emb_dim)
+        # two buffer sets used alternately: a set is rewritten two calls later, and every rank has passed the barrier
+        # of the call in between by then, so ONE barrier per call (after the stores) is enough
+        self.bufs, self.hdls, self._ptrs, self._mc = [], [], [], []
+        for _ in range(2):
+            buf = symm_mem.empty(self.world * self.R, self.E, dtype=torch.float32, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group)
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self._ptrs.append((ctypes.c_uint64 * self.world)(*[int(p) for p in hdl.buffer_ptrs]))
+            use_mc = bool(hdl.has_multicast_support) if multicast is None else bool(multicast)
+            self._mc.append(int(hdl.multicast_ptr) if use_mc and hdl.multicast_ptr else 0)
+        self.multicast = self._mc[0] != 0
+        self._ws = None
+        self._flip = 0
+
+    def __call__(self, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        import ctypes
+        from . import _lib
+        lib = _lib.lib()
+        _lib.require_cuda(x, weight)
+        xc = x.detach().contiguous().float()
+        wc = weight.detach().contiguous().float()
+        bc = None if bias is None else bias.detach().contiguous().float()
+        R, Fd = xc.shape
+        assert R == self.R and wc.shape[0] == self.E, (R, self.R, wc.shape, self.E)
+        need = max(int(lib.osr_pln_encode_workspace(R, Fd, self.E)), 256)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=xc.device)
+        k = self._flip
+        self._flip ^= 1
+        rc = lib.osr_pln_encode_gather_fwd(xc.data_ptr(), wc.data_ptr(), _lib.ptr(bc), R, Fd, self.E,
+                                           ctypes.cast(self._ptrs[k], ctypes.c_void_p), self.world, self.rank,
+                                           self._mc[k], self._ws.data_ptr(), self._ws.numel(),
+                                           _lib.stream_ptr(xc.device))
+        _lib.check(rc, "osr_pln_encode_gather_fwd")
+        self.hdls[k].barrier(channel=0)   # all ranks' tiles have landed in this rank's buffer
+        buf = self.bufs[k]
+        return buf[self.rank * R:(self.rank + 1) * R], buf
+
+
+def fused_gathered_pln_loss(enc: "FusedEncoderGather", x, weight, bias, reps, labels, ious, *, loss_fn=None, **kw):
+    """Gathered PLN loss with the fused encoder -> all-gather kernel.  Returns ``(loss, emb_local)`` where
+    ``emb_local`` is a leaf that receives d loss / d emb (the encoder's own backward GEMMs stay with the caller)."""
+    if loss_fn is None:
+        from .pln import pln_loss_from_emb as loss_fn
+    with torch.no_grad():
+        emb_loc, emb_all = enc(x, weight, bias)
+        labels_all, ious_all = _gather_meta(labels, ious, enc.group)
+    emb = emb_loc.clone().requires_grad_(True)
+    loss = _loss_on_global_rows(emb, emb_all, reps, labels_all, ious_all, enc.rank, enc.world, loss_fn, **kw)
+    return loss, emb
+
+
 def gathered_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tensor, ious: torch.Tensor, *,
                       group=None, loss_fn: Optional[Callable] = None, **kw) -> torch.Tensor:
     """Global-batch PLN loss.  ``loss_fn(emb_all, reps, labels_all, ious_all, r_norm=, center_weight=,
@@ -65,12 +149,5 @@ def gathered_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tenso
     rank = dist.get_rank(group)
     with torch.no_grad():
         emb_all = all_gather_rows(emb.detach(), group)
-        meta = torch.stack((labels.to(torch.float32), ious.to(torch.float32)), dim=1)  # labels < 2^24: exact in fp32
-        meta_all = all_gather_rows(meta, group)
-    labels_all = meta_all[:, 0].to(torch.int64)
-    ious_all = meta_all[:, 1].contiguous()
-    # local rows keep their autograd edge; remote rows are constants (their gradient lives on their own rank)
-    emb_all = emb_all.clone()
-    emb_all[rank * R:(rank + 1) * R] = emb
-    return loss_fn(emb_all, reps, labels_all, ious_all, r_norm=float(max(world * R, 1)),
-                   center_weight=float(world), emb_grad_scale=float(world), **kw)
+        labels_all, ious_all = _gather_meta(labels, ious, group)
+    return _loss_on_global_rows(emb, emb_all, reps, labels_all, ious_all, rank, world, loss_fn, **kw)

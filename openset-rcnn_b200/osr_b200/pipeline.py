@@ -23,7 +23,7 @@ from .poolers import ROIPooler
 from .pln import pln_encode_tc, pln_loss_from_emb
 from .proposals import rpn_select_decode
 from .sampling import match_proposals
-from .dist import gathered_pln_loss
+from .dist import FusedEncoderGather, fused_gathered_pln_loss, gathered_pln_loss
 
 
 @dataclass
@@ -115,6 +115,7 @@ class RoiPathStep:
         self.prop_off = torch.arange(0, (N + 1) * sel.kmax, sel.kmax, dtype=torch.int32, device=dev)
         self.count_col = sel.num_levels
         self.last: Dict[str, torch.Tensor] = {}
+        self._fused_enc = None
         self.events: Optional[List[torch.cuda.Event]] = None
 
     # ------------------------------------------------------------------------------------------------
@@ -147,17 +148,25 @@ class RoiPathStep:
         self._mark(3)
         # S5: encoder (nn.Linear) + prototype loss forward + backward to (emb, representatives)
         pi = self.pln
-        if cfg.encoder_impl == "tcgen05":
-            emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
-        else:
-            emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
         reps = pi.reps.requires_grad_(True)
         kw = dict(num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,
                   iou_threshold=cfg.iou_threshold)
-        if gather_pln:   # north-star variant: NCCL all-gather of (emb, label, iou), global-batch loss (dist.py)
-            loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, **kw)
-        else:            # the reference's semantics: per-rank loss
-            loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, **kw)
+        if gather_pln and cfg.encoder_impl == "tcgen05":
+            # north-star variant, B200-native: the encoder GEMM's epilogue stores its tiles into every rank's buffer
+            # over NVLink (fused all-gather), then the global-batch loss (dist.py)
+            if self._fused_enc is None:
+                self._fused_enc = FusedEncoderGather(pi.roi_features.shape[0], cfg.emb_dim, self.device)
+            loss, emb = fused_gathered_pln_loss(self._fused_enc, pi.roi_features, pi.enc_w, pi.enc_b, reps,
+                                                pi.gt_classes, pi.ious, **kw)
+        else:
+            if cfg.encoder_impl == "tcgen05":
+                emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+            else:
+                emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+            if gather_pln:   # encoder, then NCCL all-gather of (emb, label, iou), global-batch loss
+                loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, **kw)
+            else:            # the reference's semantics: per-rank loss
+                loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, **kw)
         g_emb, g_reps = torch.autograd.grad(loss, [emb, reps])
         self._mark(4)
         # S3 backward
