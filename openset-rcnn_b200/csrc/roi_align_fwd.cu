@@ -37,6 +37,7 @@ struct FwdParams {
   float* out;
   int32_t* out_level;
   const int32_t* order;  // (M) processing order (RoIs sorted by image, level, y band) or nullptr
+  float* rec;            // (M, kRecFloats) per-RoI table records written by roi_fwd_prep_kernel, or nullptr
   int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules AND the TMA path is enabled for this call
   int ring_floats;             // floats of the staging ring at the start of dynamic shared memory
 };
@@ -595,6 +596,98 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Per-RoI table records for the channels_last kernel, written once by a warp-per-RoI prep kernel so that the 256-thread
+// RoI CTAs do not spend the first quarter of their life deriving tables with 14 active threads.  A record is only
+// marked FAST for the common case the fully unrolled row loop handles (footprint <= 48 x 64 pixels, bins <= 8 pixels
+// wide, every row in <= 3 bins); every other RoI keeps the in-CTA prologue.  Layout (floats):
+//   [0..3]   int4   flags(bit 0 = FAST) | level << 8,  xmin,  ymin,  wf | hf << 16
+//   [4..7]   float4 1/count, tmax (int bits), image (int bits), -
+//   [8..15]  int    first column of each bin relative to xmin (0 for empty bins)
+//   [16..71] float  x-tap weights of each bin padded to 8
+//   [72.. ]  float4 per footprint row: (w(ph0), w(ph0+1), w(ph0+2), ph0)
+constexpr int kRecRows = 64;
+constexpr int kRecFloats = 72 + 4 * kRecRows;
+constexpr int kPrepWarpsF = 4;
+
+struct PrepScratch {
+  float wy[kP * kRB];
+  float wx[kP * kRB];
+  int yb[kP], ny[kP], xb[kP], nx[kP];
+};
+
+__global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __grid_constant__ FwdParams p) {
+  __shared__ PrepScratch S4[kPrepWarpsF];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = blockIdx.x * kPrepWarpsF + warp;
+  if (m >= p.M) return;   // warp-uniform, no block barrier below
+  PrepScratch& T = S4[warp];
+  float* rec = p.rec + (int64_t)m * kRecFloats;
+  const float* roi = p.rois + (int64_t)m * 5;
+  const float fimg = __ldg(roi), x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
+  const int img = (int)fimg;
+  const int level = assign_level(x1, y1, x2, y2, p.L);
+  const bool zero = (level < 0) || (level >= p.L.num_levels) || (img < 0) || (img >= p.L.num_images);
+  if (zero) {
+    if (lane == 0) reinterpret_cast<int4*>(rec)[0] = make_int4(0, 0, 0, 0);
+    return;
+  }
+  const LevelDesc& lv = p.L.lv[level];
+  const RoiGeom g = roi_geometry(x1, y1, x2, y2, lv.scale, p.L.sampling_ratio);
+  for (int i = lane; i < kP * kRB; i += 32) {
+    T.wy[i] = 0.f;
+    T.wx[i] = 0.f;
+  }
+  __syncwarp();
+  if (lane < kP) T.ny[lane] = build_bin_weights(g.start_h, g.bin_h, g.grid_h, lv.H, lane, T.wy + lane * kRB, &T.yb[lane]);
+  else if (lane < 2 * kP) T.nx[lane - kP] = build_bin_weights(g.start_w, g.bin_w, g.grid_w, lv.W, lane - kP, T.wx + (lane - kP) * kRB, &T.xb[lane - kP]);
+  __syncwarp();
+  int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1, tmax = 0;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < kP; ++i) {
+    const int nx = T.nx[i], ny = T.ny[i];
+    bad |= (nx < 0) | (ny < 0);
+    tmax = max(tmax, nx);
+    if (nx > 0) { xmin = min(xmin, T.xb[i]); xmax = max(xmax, T.xb[i] + nx - 1); }
+    if (ny > 0) { ymin = min(ymin, T.yb[i]); ymax = max(ymax, T.yb[i] + ny - 1); }
+  }
+  const int wf = xmax - xmin + 1, hf = ymax - ymin + 1;
+  bool fast = !bad && xmax >= 0 && ymax >= 0 && wf <= kNhwcWide && hf <= kRecRows && tmax <= 8;
+  if (fast) {
+    for (int r = lane; r < hf; r += 32) {   // same packing as the in-CTA prologue
+      const int y = ymin + r;
+      int ph0 = -1, cnt = 0;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+#pragma unroll
+      for (int ph = 0; ph < kP; ++ph) {
+        const int rr = y - T.yb[ph];
+        if (rr >= 0 && rr < T.ny[ph]) {
+          if (ph0 < 0) ph0 = ph;
+          const int d = ph - ph0;
+          const float wv = T.wy[ph * kRB + rr];
+          if (d == 0) w0 = wv;
+          else if (d == 1) w1 = wv;
+          else if (d == 2) w2 = wv;
+          else cnt = 99;
+        }
+      }
+      if (cnt == 99) bad = true;
+      reinterpret_cast<float4*>(rec + 72)[r] = make_float4(w0, w1, w2, __int_as_float(ph0 < 0 ? kP : ph0));
+    }
+    fast = !__any_sync(0xffffffffu, bad);
+  }
+  if (fast) {
+    for (int i = lane; i < kP * 8; i += 32) {
+      const int pw = i >> 3, q = i & 7;
+      rec[16 + i] = (q < T.nx[pw]) ? T.wx[pw * kRB + q] : 0.f;
+    }
+    if (lane < 8) reinterpret_cast<int*>(rec)[8 + lane] = (lane < kP && T.nx[lane] > 0) ? T.xb[lane] - xmin : 0;
+    if (lane == 0) reinterpret_cast<float4*>(rec)[1] = make_float4(1.0f / g.count, __int_as_float(tmax), __int_as_float(img), 0.f);
+  }
+  if (lane == 0) reinterpret_cast<int4*>(rec)[0] = make_int4((fast ? 1 : 0) | (level << 8), xmin, ymin, wf | (hf << 16));
+}
+
 template <int kC>   // kC > 0: compile-time channel count (immediate LDS offsets); 0: run-time C
 __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const __grid_constant__ FwdParams p) {
   // dynamic smem: [ ring: 96 cols x C floats, cut into row stages sized to this RoI (re-used as the 49 x C output tile) | barriers | T ]
@@ -608,16 +701,43 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
 
   const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* out_roi = p.out + (int64_t)m * C * (kP * kP);
+  // ---- prologue: tables either from the prep kernel's record (common case) or derived here ----------------------
+  int level, img, xmin, ymin, wf, hf, tmax = 0;
+  float inv_count;
+  int toff[kP];
+  bool pre = false;
+  int4 h0 = make_int4(0, 0, 0, 0);
+  const float* rec = nullptr;
+  if (p.rec != nullptr) {
+    rec = p.rec + (int64_t)m * kRecFloats;
+    h0 = __ldg(reinterpret_cast<const int4*>(rec));
+    pre = (h0.x & 1) != 0;
+  }
+  if (pre) {
+    level = h0.x >> 8;
+    xmin = h0.y; ymin = h0.z; wf = h0.w & 0xffff; hf = h0.w >> 16;
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(rec) + 1);
+    inv_count = h1.x;
+    tmax = __float_as_int(h1.y);
+    img = __float_as_int(h1.z);
+    if (tid == 0) p.out_level[m] = level;
+    const int4 o0 = __ldg(reinterpret_cast<const int4*>(rec) + 2), o1 = __ldg(reinterpret_cast<const int4*>(rec) + 3);
+    toff[0] = o0.x * C; toff[1] = o0.y * C; toff[2] = o0.z * C; toff[3] = o0.w * C;
+    toff[4] = o1.x * C; toff[5] = o1.y * C; toff[6] = o1.z * C;
+    if (tid < 2 * kP) reinterpret_cast<float4*>(&T.wt[0][0])[tid] = __ldg(reinterpret_cast<const float4*>(rec + 16) + tid);
+    for (int r = tid; r < hf; r += kThreads) T.rw[r] = __ldg(reinterpret_cast<const float4*>(rec + 72) + r);
+  } else {
   const float* roi = p.rois + (int64_t)m * 5;
   const float fimg = __ldg(roi), x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
-  const int img = (int)fimg;
-  const int level = assign_level(x1, y1, x2, y2, p.L);
+  img = (int)fimg;
+  level = assign_level(x1, y1, x2, y2, p.L);
   if (tid == 0) p.out_level[m] = level;
-  float* out_roi = p.out + (int64_t)m * C * (kP * kP);
 
   const bool zero = (level < 0) || (level >= p.L.num_levels) || (img < 0) || (img >= p.L.num_images);
   RoiGeom g;
-  int xmin = 1 << 30, xmax = -1, ymin = 1 << 30, ymax = -1;
+  int xmax = -1, ymax = -1;
+  xmin = 1 << 30; ymin = 1 << 30;
   bool overflow = false;
   if (!zero) {
     const LevelDesc& lv0 = p.L.lv[level];
@@ -642,14 +762,14 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
       if (ny > 0) { ymin = min(ymin, T.yb[i]); ymax = max(ymax, T.yb[i] + ny - 1); }
     }
   }
-  const int wf = xmax - xmin + 1, hf = ymax - ymin + 1;
+  wf = xmax - xmin + 1; hf = ymax - ymin + 1;
   if (zero || (!overflow && (xmax < 0 || ymax < 0))) {
     for (int o = tid; o < C * kP * kP; o += kThreads) out_roi[o] = 0.f;
     return;
   }
-  const LevelDesc& lv = p.L.lv[level];
-  const float* img_base = lv.data + (int64_t)img * lv.sN;
   if (overflow || hf > kMaxRows) {
+    const LevelDesc& lv = p.L.lv[level];
+    const float* img_base = lv.data + (int64_t)img * lv.sN;
     // generic: torchvision's per-sample loop (any strides)
     for (int o = tid; o < C * kP * kP; o += kThreads) {
       const int c = o / (kP * kP);
@@ -689,6 +809,23 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     }
     T.rw[r] = make_float4(w0, w1, w2, __int_as_float(cnt == 99 ? -1 : (ph0 < 0 ? kP : ph0)));
   }
+    inv_count = 1.0f / g.count;
+    __syncthreads();   // T.rw complete; T.nx / T.xb / T.wx read below
+#pragma unroll
+    for (int pw = 0; pw < kP; ++pw) {
+      toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
+      tmax = max(tmax, T.nx[pw]);
+    }
+    if (tid < kP) {
+      float w8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w8[q] = (q < T.nx[tid]) ? T.wx[tid * kRB + q] : 0.f;
+      T.wt[tid][0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
+      T.wt[tid][1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+    }
+  }
+  const LevelDesc& lv = p.L.lv[level];
+  const float* img_base = lv.data + (int64_t)img * lv.sN;
   if (tid == 0) {
     for (int i = 0; i < kNhwcMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -696,7 +833,6 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
 
   float acc[kP][kP];
 #pragma unroll
@@ -716,21 +852,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   // Common case (one x chunk): every bin's x taps are padded to 8 with zero weights (T.wt), so the row loop is fully
   // unrolled and predicate-free; padded taps read finite data (the ring is zero-initialised once and only ever holds
   // feature values; 8 columns of slack follow the last stage).
-  int toff[kP];
-  int tmax = 0;   // widest bin in pixels: picks the 4-, 6- or 8-tap row loop
-#pragma unroll
-  for (int pw = 0; pw < kP; ++pw) {
-    toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
-    tmax = max(tmax, T.nx[pw]);
-  }
-  const bool fast_taps = (nxc == 1) && (tmax <= 8);
-  if (tid < kP) {
-    float w8[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) w8[q] = (q < T.nx[tid]) ? T.wx[tid * kRB + q] : 0.f;
-    T.wt[tid][0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
-    T.wt[tid][1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
-  }
+  const bool fast_taps = (nxc == 1) && (tmax <= 8);   // tmax = widest bin in pixels: picks the 4-, 6- or 8-tap row loop
   for (int i = tid; i < (p.ring_floats >> 2); i += kThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic zero-fill before async-proxy bulk writes
   __syncthreads();
@@ -861,7 +983,6 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   }
   // epilogue: 49 x C tile -> shared memory as [c][49] (stride 49 is odd: conflict-free) -> coalesced 16-byte stores
   __syncthreads();   // every warp is done with the ring (all bulk loads have landed and been consumed)
-  const float inv_count = 1.0f / g.count;
   if (cin) {
     float* o = ring + c * (kP * kP);
 #pragma unroll
@@ -999,7 +1120,10 @@ int fill_roi_levels(RoiLevels& L, const osr_feat_level_t* h_levels, int num_leve
 
 extern "C" {
 
-size_t osr_roi_align_fwd_workspace(int M) { return osr::align256((size_t)(M > 0 ? M : 1) * 4) * 2; }
+size_t osr_roi_align_fwd_workspace(int M) {
+  const size_t m = (size_t)(M > 0 ? M : 1);
+  return osr::align256(m * 4) * 2 + osr::align256(m * kRecFloats * 4);   // order, keys, per-RoI table records
+}
 
 int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
                       int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
@@ -1017,6 +1141,7 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
   p.out = out;
   p.out_level = out_level;
   p.order = nullptr;
+  p.rec = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // locality ordering (optional: skipped without a workspace, or for tiny problems where it cannot pay)
   if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && M >= 256) {
@@ -1039,6 +1164,11 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
     nhwc = lv.sC == 1 && lv.sW == C && lv.sH == (int64_t)lv.W * C && (lv.sN % 4 == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
   }
   if (nhwc) {
+    if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && !getenv("OSR_ROIALIGN_NO_PREP")) {
+      p.rec = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 2 * osr::align256((size_t)M * 4));
+      roi_fwd_prep_kernel<<<osr::ceil_div(M, kPrepWarpsF), kPrepWarpsF * 32, 0, s>>>(p);
+      OSR_LAUNCH_CHECK();
+    }
     int ring = (kNhwcRingCols + 8) * C;              // + 8 columns of slack for the zero-weight padded taps
     if (ring < kP * kP * C) ring = kP * kP * C;                 // the ring doubles as the 49 x C output tile
     p.ring_floats = (ring + 31) & ~31;
