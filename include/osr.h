@@ -225,6 +225,22 @@ int osr_match_label(const float* boxes, const int32_t* box_offsets, const int32_
                     int64_t background_label, int32_t* matched_idx, float* matched_iou, int32_t* matched_label,
                     int64_t* matched_class, void* stream);
 
+/*
+ * ROI-head inference post-processing, stage 1 (osrcnn_fast_rcnn.py:380-450 and :89-126), all images in one launch:
+ * detectron2 Box2BoxTransform(weights = wx,wy,ww,wh; scale_clamp = log(1000/16)).apply_deltas on the class-agnostic
+ * (R,4) deltas, objectness = sqrt(iou * centerness) (geometric_mean != 0) or (iou + centerness) / 2, isfinite filter,
+ * Boxes.clip to the image, score > score_thresh.  box_offsets (N+1) int32 DEVICE, image_hw (N,2) int32 DEVICE (h, w).
+ * out_boxes (R,4): clipped predictions (zeros for dropped rows); out_scores (R): the objectness (NaN for rows with a
+ * non-finite box or score, which the reference's isfinite filter removes);
+ * out_effective_scores (R): objectness, or -inf for rows the reference drops - feed them to osr_nms_segmented with
+ * segments = images: survivors come out first, in the reference's order.  Arithmetic is torch's op-by-op fp32 chain.
+ */
+int osr_rcnn_decode_score(const float* proposal_boxes, const float* deltas, const float* ious, const float* centerness,
+                          const int32_t* box_offsets, const int32_t* image_hw, int num_images,
+                          int max_boxes_per_image, float wx, float wy, float ww, float wh, float scale_clamp,
+                          int geometric_mean, float score_thresh, float* out_boxes, float* out_scores,
+                          float* out_effective_scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

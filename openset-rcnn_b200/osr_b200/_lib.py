@@ -77,6 +77,10 @@ SIGNATURES = {
     "osr_pln_nearest": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "osr_rcnn_decode_score": (C.c_int, [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "osr_match_label": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int64,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,74 @@
+"""GPU parity of the ROI-head inference post-processing (osr_rcnn_decode_score + segmented NMS) against the oracle's
+restatement of osrcnn_fast_rcnn.py run on the same GPU (torch's own ops + torchvision CUDA nms): bit-exact boxes,
+scores, kept indices and gathered features."""
+import pytest
+import torch
+
+from oracle import rcnn_inference as oinf
+from oracle.structures import Boxes as OBoxes, Instances as OInstances
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _inputs(lens, seed, hw=(800, 1333), bad=True):
+    from osr_b200 import synth
+    from osr_b200.structures import Boxes, Instances
+    g = torch.Generator().manual_seed(seed)
+    ours, ref = [], []
+    for n, k in enumerate(lens):
+        b = synth.make_rois(1, k, hw, seed=seed + n)[0] if k else torch.empty(0, 4)
+        ctr = torch.rand(k, generator=g)
+        a = Instances(hw); a.set("proposal_boxes", Boxes(b.to(DEV))); a.set("objectness_logits", ctr.to(DEV))
+        c = OInstances(hw); c.set("proposal_boxes", OBoxes(b.to(DEV))); c.set("objectness_logits", ctr.to(DEV))
+        ours.append(a); ref.append(c)
+    R = sum(lens)
+    deltas = torch.randn(R, 4, generator=g) * torch.tensor([1.5, 1.5, 1.0, 1.0])
+    deltas[::17, 2] = 30.0          # exercises the scale clamp
+    ious = torch.rand(R, 1, generator=g)
+    if bad and R > 50:
+        deltas[5, 0] = float("nan"); deltas[11, 3] = float("inf"); ious[23, 0] = float("nan"); ious[31, 0] = -0.5
+    feats = torch.randn(R, 32, generator=g)
+    return ours, ref, (deltas.to(DEV), ious.to(DEV)), feats.to(DEV)
+
+
+@pytest.mark.parametrize("lens,thr,nms,topk,mean", [
+    ([1000, 1000, 873, 1000], 0.05, 0.5, 100, "geometric"),
+    ([4273, 4273], 0.0, 1.0, 1000, "geometric"),       # the reference's shipped thresholds (nms 1.0: sort + top-1000)
+    ([300, 0, 7], 0.3, 0.7, -1, "arithmetic"),
+    ([64], 0.99, 0.5, 100, "geometric"),               # almost everything filtered
+])
+def test_inference_matches_oracle_on_gpu(lens, thr, nms, topk, mean):
+    from osr_b200.inference import inference
+    ours_p, ref_p, preds, feats = _inputs(lens, seed=21)
+    kw = dict(mean_type=mean, score_thresh=thr, nms_thresh=nms, topk_per_image=topk)
+    got, got_idx = inference(preds, ours_p, feats, **kw)
+    exp, exp_idx = oinf.inference(preds, ref_p, feats, **kw)
+    assert len(got) == len(exp) == len(lens)
+    for a, b, ia, ib in zip(got, exp, got_idx, exp_idx):
+        assert len(a) == len(b), (len(a), len(b))
+        assert torch.equal(a.get("pred_boxes").tensor, b.get("pred_boxes").tensor)
+        assert torch.equal(a.get("scores"), b.get("scores"))
+        assert torch.equal(a.get("pred_classes"), b.get("pred_classes"))
+        assert torch.equal(a.get("features"), b.get("features"))
+        assert torch.equal(ia, ib)
+
+
+def test_decode_close_to_cpu_reference():
+    """Same path against the oracle on the CPU: boxes within 1e-4 px (expf / reciprocal-multiply differ by ulps
+    between the CPU and CUDA math libraries), identical survivor sets for well-separated scores."""
+    from osr_b200.inference import inference
+    ours_p, ref_p, preds, feats = _inputs([500, 321], seed=4, bad=False)
+    got, _ = inference(preds, ours_p, feats, score_thresh=0.0, nms_thresh=1.0, topk_per_image=-1)
+    ref_cpu = []
+    for p in ref_p:
+        q = OInstances(p.image_size)
+        q.set("proposal_boxes", OBoxes(p.get("proposal_boxes").tensor.cpu()))
+        q.set("objectness_logits", p.get("objectness_logits").cpu())
+        ref_cpu.append(q)
+    exp, _ = oinf.inference((preds[0].cpu(), preds[1].cpu()), ref_cpu, feats.cpu(), score_thresh=0.0, nms_thresh=1.0,
+                            topk_per_image=-1)
+    for a, b in zip(got, exp):
+        assert len(a) == len(b)
+        torch.testing.assert_close(a.get("pred_boxes").tensor.cpu(), b.get("pred_boxes").tensor, rtol=1e-6, atol=1e-3)
+        torch.testing.assert_close(a.get("scores").cpu(), b.get("scores"), rtol=1e-6, atol=1e-7)
