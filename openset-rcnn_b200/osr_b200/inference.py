@@ -107,3 +107,62 @@ def inference(predictions: Tuple[torch.Tensor, torch.Tensor], proposals: List[In
         results.append(r)
         kept.append(fin_pos[g] - fin_base[n])
     return results, kept
+
+
+def _clip(boxes: torch.Tensor, image_size) -> torch.Tensor:
+    h, w = image_size
+    return torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
+                        boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1)
+
+
+def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, unknown_id: int = 80,
+                                 known_score_thresh: float = 0.05, known_nms_thresh: float = 0.5, known_topk: int = 100,
+                                 unknown_score_thresh: float = 0.05, unknown_nms_thresh: float = 0.5,
+                                 unknown_topk: int = 50, class_id=None) -> List[Instances]:
+    """``SoftMaxClassifier.inference(fg_instances)`` (``softmax_classifier.py:287-346``): known detections through the
+    linear classifier + softmax + per-class NMS, unknown detections through class-agnostic NMS, unknown first.
+    The classifier GEMM and the softmax stay torch (not on the RoI path); the two per-image NMS loops
+    (``fast_rcnn_inference_single_image_known/unknown``, ``:47-168``) run as ONE segmented NMS call each for the whole
+    batch (``batched_nms_images``: segments = images, torchvision's per-image coordinate trick preserved)."""
+    from .nms import batched_nms_images
+    if not fg_instances:
+        return []
+    dev = fg_instances[0].get("scores").device
+    kb, ks, kc, ub, us, uc, has_unknown = [], [], [], [], [], [], []
+    known_masks = [inst.get("pred_classes") != unknown_id for inst in fg_instances]
+    n_known = torch.stack([k.sum() for k in known_masks]).cpu().tolist()   # host sync 1
+    for inst, k, nk in zip(fg_instances, known_masks, n_known):
+        boxes = inst.get("pred_boxes").tensor
+        # the classifier runs per image like the reference (a batched GEMM could round differently)
+        probs = torch.softmax(cls_score(inst.get("features")[k]), dim=-1)
+        b = boxes[k]
+        valid = torch.isfinite(b).all(dim=1) & torch.isfinite(probs).all(dim=1)
+        b, probs = b[valid], probs[valid][:, :-1]
+        b = _clip(b, inst.image_size)
+        inds = (probs > known_score_thresh).nonzero()
+        kb.append(b[inds[:, 0]]); ks.append(probs[inds[:, 0], inds[:, 1]]); kc.append(inds[:, 1])
+        has_unknown.append(nk < len(inst))
+        bu, su = boxes[~k], inst.get("scores")[~k]
+        vu = torch.isfinite(bu).all(dim=1) & torch.isfinite(su)
+        bu, su = _clip(bu[vu], inst.image_size), su[vu]
+        fu = su > unknown_score_thresh
+        ub.append(bu[fu]); us.append(su[fu]); uc.append(torch.zeros(bu[fu].shape[0], dtype=torch.int64, device=dev))
+    keep_k = batched_nms_images(kb, ks, kc, known_nms_thresh, topk_per_image=known_topk)
+    keep_u = batched_nms_images(ub, us, uc, unknown_nms_thresh, topk_per_image=unknown_topk)
+    out = []
+    for n, inst in enumerate(fg_instances):
+        res = Instances(inst.image_size)
+        kcls = kc[n][keep_k[n]]
+        if class_id is not None:
+            kcls = class_id[kcls]
+        if has_unknown[n]:
+            ucls = (torch.zeros(len(keep_u[n]), device=dev) + unknown_id).long()
+            res.set("pred_boxes", Boxes(torch.cat([ub[n][keep_u[n]], kb[n][keep_k[n]]])))
+            res.set("scores", torch.cat([us[n][keep_u[n]], ks[n][keep_k[n]]]))
+            res.set("pred_classes", torch.cat([ucls, kcls]))
+        else:
+            res.set("pred_boxes", Boxes(kb[n][keep_k[n]]))
+            res.set("scores", ks[n][keep_k[n]])
+            res.set("pred_classes", kcls)
+        out.append(res)
+    return out

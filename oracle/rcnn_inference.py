@@ -108,3 +108,90 @@ def inference(predictions: Tuple[torch.Tensor, torch.Tensor], proposals: List[In
     res = [fast_rcnn_inference_single_image(b, s, sh, f, score_thresh, nms_thresh, topk_per_image)
            for s, b, sh, f in zip(ious, boxes, shapes, feats)]
     return [r[0] for r in res], [r[1] for r in res]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SoftMaxClassifier.inference (openset_rcnn/modeling/roi_heads/softmax_classifier.py:47-168, 287-346)
+def _single_image_known(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image):
+    """``fast_rcnn_inference_single_image_known`` (``softmax_classifier.py:47-104``)."""
+    valid_mask = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+    if not valid_mask.all():
+        boxes = boxes[valid_mask]
+        scores = scores[valid_mask]
+    scores = scores[:, :-1]
+    num_bbox_reg_classes = boxes.shape[1] // 4
+    b = Boxes(boxes.reshape(-1, 4))
+    b.clip(image_shape)
+    boxes = b.tensor.view(-1, num_bbox_reg_classes, 4)
+    filter_mask = scores > score_thresh
+    filter_inds = filter_mask.nonzero()
+    if num_bbox_reg_classes == 1:
+        boxes = boxes[filter_inds[:, 0], 0]
+    else:
+        boxes = boxes[filter_mask]
+    scores = scores[filter_mask]
+    keep = batched_nms(boxes, scores, filter_inds[:, 1], nms_thresh)
+    if topk_per_image >= 0:
+        keep = keep[:topk_per_image]
+    boxes, scores, filter_inds = boxes[keep], scores[keep], filter_inds[keep]
+    result = Instances(image_shape)
+    result.set("pred_boxes", Boxes(boxes))
+    result.set("scores", scores)
+    result.set("pred_classes", filter_inds[:, 1])
+    return result
+
+
+def _single_image_unknown(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image, unknown_id):
+    """``fast_rcnn_inference_single_image_unknown`` (``softmax_classifier.py:106-168``)."""
+    scores = scores.unsqueeze(dim=1)
+    valid_mask = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+    if not valid_mask.all():
+        boxes = boxes[valid_mask]
+        scores = scores[valid_mask]
+    num_bbox_reg_classes = boxes.shape[1] // 4
+    b = Boxes(boxes.reshape(-1, 4))
+    b.clip(image_shape)
+    boxes = b.tensor.view(-1, num_bbox_reg_classes, 4)
+    filter_mask = scores > score_thresh
+    filter_inds = filter_mask.nonzero()
+    boxes = boxes[filter_inds[:, 0], 0] if num_bbox_reg_classes == 1 else boxes[filter_mask]
+    scores = scores[filter_mask]
+    keep = batched_nms(boxes, scores, filter_inds[:, 1], nms_thresh)
+    if topk_per_image >= 0:
+        keep = keep[:topk_per_image]
+    boxes, scores = boxes[keep], scores[keep]
+    result = Instances(image_shape)
+    result.set("pred_boxes", Boxes(boxes))
+    result.set("scores", scores)
+    result.set("pred_classes", (torch.zeros(len(scores), device=scores.device) + unknown_id).long())
+    return result
+
+
+def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, unknown_id: int = 80,
+                                 known_score_thresh: float = 0.05, known_nms_thresh: float = 0.5, known_topk: int = 100,
+                                 unknown_score_thresh: float = 0.05, unknown_nms_thresh: float = 0.5,
+                                 unknown_topk: int = 50, class_id=None) -> List[Instances]:
+    """``SoftMaxClassifier.inference`` (``softmax_classifier.py:287-346``); ``cls_score`` is the module's linear layer,
+    ``unknown_id`` = 80 (OpenDet benchmark) or 1000, ``class_id`` the GraspNet id table (None = benchmark)."""
+    results = []
+    for inst in fg_instances:
+        known = inst.get("pred_classes") != unknown_id
+        known_features = inst.get("features")[known]
+        known_probs = torch.softmax(cls_score(known_features), dim=-1)
+        result_k = _single_image_known(inst.get("pred_boxes")[known].tensor, known_probs, inst.image_size,
+                                       known_score_thresh, known_nms_thresh, known_topk)
+        res = Instances(inst.image_size)
+        kc = result_k.get("pred_classes") if class_id is None else class_id[result_k.get("pred_classes")]
+        if not known.all():
+            result_unk = _single_image_unknown(inst.get("pred_boxes")[~known].tensor, inst.get("scores")[~known],
+                                               inst.image_size, unknown_score_thresh, unknown_nms_thresh, unknown_topk,
+                                               unknown_id)
+            res.set("pred_boxes", Boxes(torch.cat([result_unk.get("pred_boxes").tensor, result_k.get("pred_boxes").tensor])))
+            res.set("scores", torch.cat([result_unk.get("scores"), result_k.get("scores")]))
+            res.set("pred_classes", torch.cat([result_unk.get("pred_classes"), kc]))
+        else:
+            res.set("pred_boxes", result_k.get("pred_boxes"))
+            res.set("scores", result_k.get("scores"))
+            res.set("pred_classes", kc)
+        results.append(res)
+    return results

@@ -72,3 +72,37 @@ def test_decode_close_to_cpu_reference():
         assert len(a) == len(b)
         torch.testing.assert_close(a.get("pred_boxes").tensor.cpu(), b.get("pred_boxes").tensor, rtol=1e-6, atol=1e-3)
         torch.testing.assert_close(a.get("scores").cpu(), b.get("scores"), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("class_table", [False, True])
+def test_softmax_classifier_inference_matches_oracle(class_table):
+    """SoftMaxClassifier.inference (known: per-class NMS over K classes; unknown: class-agnostic NMS; unknown first)."""
+    from osr_b200.inference import softmax_classifier_inference
+    from osr_b200 import synth
+    from osr_b200.structures import Boxes, Instances
+    torch.manual_seed(0)
+    K = 20
+    cls = torch.nn.Linear(32, K + 1).to(DEV)
+    g = torch.Generator().manual_seed(8)
+    ours, ref = [], []
+    for n, (k, frac_unk) in enumerate([(300, 0.3), (100, 0.0), (57, 1.0), (0, 0.0)]):
+        b = synth.make_rois(1, k, (800, 1333), seed=40 + n)[0] if k else torch.empty(0, 4)
+        sc = torch.rand(k, generator=g)
+        pc = torch.where(torch.rand(k, generator=g) < frac_unk, torch.full((k,), 80), torch.randint(0, K, (k,), generator=g))
+        f = torch.randn(k, 32, generator=g) * 3
+        for cont, Bx, Inst in ((ours, Boxes, Instances), (ref, OBoxes, OInstances)):
+            i = Inst((800, 1333))
+            i.set("pred_boxes", Bx(b.to(DEV))); i.set("scores", sc.to(DEV)); i.set("pred_classes", pc.to(DEV))
+            i.set("features", f.to(DEV))
+            cont.append(i)
+    table = (torch.arange(K, device=DEV) * 3 + 1) if class_table else None
+    kw = dict(unknown_id=80, known_score_thresh=0.05, known_nms_thresh=0.5, known_topk=100, unknown_score_thresh=0.2,
+              unknown_nms_thresh=0.5, unknown_topk=50, class_id=table)
+    with torch.no_grad():
+        got = softmax_classifier_inference(ours, cls, **kw)
+        exp = oinf.softmax_classifier_inference(ref, cls, **kw)
+    for a, b in zip(got, exp):
+        assert len(a) == len(b)
+        assert torch.equal(a.get("pred_boxes").tensor, b.get("pred_boxes").tensor)
+        assert torch.equal(a.get("scores"), b.get("scores"))
+        assert torch.equal(a.get("pred_classes"), b.get("pred_classes"))
