@@ -653,7 +653,7 @@ __device__ __forceinline__ void cl_fold_row(const float* gl, const ClSmem& S, in
 // columns [x0, x1) of the tile all start at bin K: acc[r][x] += w0 rg[r][K] + w1 rg[r][K+1] + w2 rg[r][K+2]
 template <int K>
 __device__ __forceinline__ void cl_run(const float4* xcol, uchar2 rn, float* accl, const float (&rg)[kCT][kP]) {
-#pragma unroll 2
+#pragma unroll 1
   for (int x = rn.x; x < rn.y; ++x) {
     const float4 w = xcol[x];
     float* ap = accl + x * 32;
