@@ -479,8 +479,11 @@ constexpr int kGBlk = 32 * kP * kP;         // floats of one (RoI, 32-channel) b
 struct __align__(16) ClSmem {
   float acc[kCWarps][kCT * kCW * 32];       // [warp][pixel][lane]
   float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
-  float4 yrow[kCNB][kCH];                   // (w(p0), w(p0+1), w(p0+2), code): code 0..4 = p0, 5 = dense, 6 = empty
-  float4 xcol[kCNB][kCW];                   // same per tile column
+  float4 yrow[kCNB][kCH];                   // y weights of the row at bins pm .. pm+3, pm = first bin of its SUB-TILE (below)
+  float4 xcol[kCNB][kCW];                   // (w(p0), w(p0+1), w(p0+2), code): code 0..4 = p0, 5 = dense, 6 = empty
+  uchar2 lohi[kCNB][kCH];                   // scratch: (first, last) bin with weight of each tile row; first > last = none
+  unsigned char pm[kCNB][kCS];              // first bin of the 4-bin window shared by the sub-tile's rows; 254 = no weight,
+                                            // 255 = the rows span more than 4 bins (dense 7-bin fold)
   uchar2 run[kCNB][8];                      // [k] = (first, last + 1) tile column whose code is k (k = 0..5)
   BatchEntry e[kCNB];
   int2 org[kCNB];                           // (y0, x0) of the RoI's footprint: origin of its rows in the workspace table
@@ -488,6 +491,8 @@ struct __align__(16) ClSmem {
   int warp_cnt[kCWarps + 1];
   int nb, next_pos;
 };
+
+static_assert((kCNB * kCH + kCThreads) * 8 <= kCWarps * kGBlk, "table scratch must fit in the staging buffers");
 
 __device__ __forceinline__ void cl_collect(const BwdParams& p, ClSmem& S, int level, int tx0, int ty0, int pos, int r1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -563,7 +568,9 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
     const RoiInfo info = load_info(p.info + m);
     const int pos = isy ? ty0 + r : tx0 + (r - kCH);
     const int base = isy ? info.y0 : info.x0, last = isy ? info.y1 : info.x1;
-    float* wd = &S.sg[0][0] + tid * 8;   // thread-private scratch (the staging buffers are idle while tables are built)
+    // scratch in the idle staging buffers: y rows keep their 7 weights until the packing pass below ((j, row) slot),
+    // columns only need them inside this iteration (per-thread slot behind the row slots)
+    float* wd = &S.sg[0][0] + (isy ? (j * kCH + r) * 8 : kCNB * kCH * 8 + tid * 8);
     if (r == 0) S.org[j] = make_int2(info.y0, info.x0);
 #pragma unroll
     for (int b = 0; b < kP; ++b) wd[b] = 0.f;
@@ -588,9 +595,40 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
         }
       }
     }
-    const float4 v = cl_pack3(wd);
-    if (isy) S.yrow[j][r] = v;
-    else S.xcol[j][r - kCH] = v;
+    if (isy) {
+      int lo = kP, hi = 0;
+#pragma unroll
+      for (int b = 0; b < kP; ++b)
+        if (wd[b] != 0.f) {
+          lo = min(lo, b);
+          hi = b;
+        }
+      S.lohi[j][r] = make_uchar2((unsigned char)lo, (unsigned char)hi);
+    } else {
+      S.xcol[j][r - kCH] = cl_pack3(wd);
+    }
+  }
+  __syncthreads();
+  // y rows: the rows of a sub-tile share ONE window of 4 consecutive bins (pm .. pm+3) whenever their bins fit in it
+  // (always, unless bins are narrower than a pixel), so the fold reads 4 rows of g once for all of them.
+  for (int q = tid; q < nb * kCH; q += kCThreads) {
+    const int j = q / kCH;
+    const int r = q - j * kCH;
+    const int st = r / kCT;
+    int lo = kP, hi = -1;
+#pragma unroll
+    for (int i = 0; i < kCT; ++i) {
+      const uchar2 lh = S.lohi[j][st * kCT + i];
+      if (lh.x <= lh.y) {
+        lo = min(lo, (int)lh.x);
+        hi = max(hi, (int)lh.y);
+      }
+    }
+    const int pmv = min(lo, kP - 4);
+    const bool fits = (hi < 0) || (hi <= pmv + 3);
+    const float* wd = &S.sg[0][0] + (j * kCH + r) * 8;
+    S.yrow[j][r] = (hi >= 0 && fits) ? make_float4(wd[pmv], wd[pmv + 1], wd[pmv + 2], wd[pmv + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r == st * kCT) S.pm[j][st] = (unsigned char)(hi < 0 ? 254 : (fits ? pmv : 255));
   }
   __syncthreads();
   // column runs: the first bin of a column never decreases with x, so columns of equal code are contiguous
@@ -609,9 +647,8 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
     const int st = tid - (kCThreads - kCS);
     unsigned m = 0;
     for (int j = 0; j < nb; ++j) {
-      bool anyr = false, anyc = false;
-#pragma unroll
-      for (int r = 0; r < kCT; ++r) anyr |= (__float_as_int(S.yrow[j][st * kCT + r].w) != 6);
+      const bool anyr = S.pm[j][st] != 254;
+      bool anyc = false;
 #pragma unroll
       for (int x = 0; x < kCW; ++x) anyc |= (__float_as_int(S.xcol[j][x].w) != 6);
       if (anyr && anyc) m |= 1u << j;
@@ -621,30 +658,42 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
   __syncthreads();
 }
 
-// rg[pw] = sum_ph Wy[ph][row] / count * g[ph][pw] for one tile row; gl = this lane's channel in the staged block
-// (49 floats, stride-49 across lanes: conflict-free).  The <= 3 bins of the row are addressed dynamically in shared
-// memory, so there is no per-first-bin code replication (the register-resident variant with a 5-way switch per row
-// was instruction-cache bound).
-__device__ __forceinline__ void cl_fold_row(const float* gl, const ClSmem& S, int j, int r, const float* wdense, float (&rg)[kP]) {
-  const float4 w = S.yrow[j][r];
-  const int code = __float_as_int(w.w);
-  if (code < 5) {
-    const float* gp = gl + code * kP;
+// rg[r][pw] = sum_ph Wy[ph][row r] / count * g[ph][pw] for the kCT rows of a sub-tile; gl = this lane's channel in the
+// staged block (49 floats, stride-49 across lanes: conflict-free).  The rows share one window of 4 bins, so 4 rows of
+// g are read once (28 LDS, dynamic base) and every row is a branch-free 4-term combination; sub-tiles whose rows span
+// more bins (bins narrower than a pixel) loop over all 7 bins with the dense weights from the workspace table.
+__device__ __forceinline__ void cl_fold_subtile(const float* gl, const ClSmem& S, int j, int st, const float* wdense,
+                                                float (&rg)[kCT][kP]) {
+  const int pmv = S.pm[j][st];
+  if (pmv < 254) {
+    const float* gp = gl + pmv * kP;
+    float g4[4][kP];
 #pragma unroll
-    for (int b = 0; b < kP; ++b) rg[b] = fmaf(w.y, gp[kP + b], w.x * gp[b]);
-    if (w.z != 0.f) {   // third bin only when the row really sits in three (bins narrower than two pixels)
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int b = 0; b < kP; ++b) rg[b] = fmaf(w.z, gp[2 * kP + b], rg[b]);
+      for (int b = 0; b < kP; ++b) g4[k][b] = gp[k * kP + b];
+#pragma unroll
+    for (int r = 0; r < kCT; ++r) {
+      const float4 w = S.yrow[j][st * kCT + r];
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rg[r][b] = fmaf(w.w, g4[3][b], fmaf(w.z, g4[2][b], fmaf(w.y, g4[1][b], w.x * g4[0][b])));
     }
   } else {
 #pragma unroll
-    for (int b = 0; b < kP; ++b) rg[b] = 0.f;
-    if (code == 5) {    // row inside more than 3 bins: dense
-#pragma unroll 1
-      for (int a = 0; a < kP; ++a) {
-        const float wa = __ldg(wdense + a);
+    for (int r = 0; r < kCT; ++r)
 #pragma unroll
-        for (int b = 0; b < kP; ++b) rg[b] = fmaf(wa, gl[a * kP + b], rg[b]);
+      for (int b = 0; b < kP; ++b) rg[r][b] = 0.f;
+#pragma unroll 1
+    for (int a = 0; a < kP; ++a) {
+      float ga[kP];
+#pragma unroll
+      for (int b = 0; b < kP; ++b) ga[b] = gl[a * kP + b];
+#pragma unroll
+      for (int r = 0; r < kCT; ++r) {
+        const uchar2 lh = S.lohi[j][st * kCT + r];   // rows outside the footprint have no table entry
+        const float wa = (lh.x <= lh.y) ? __ldg(wdense + r * kP + a) : 0.f;
+#pragma unroll
+        for (int b = 0; b < kP; ++b) rg[r][b] = fmaf(wa, ga[b], rg[r][b]);
       }
     }
   }
@@ -745,9 +794,7 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
           float rg[kCT][kP];
           const int2 org = S.org[j];
           const float* wtab = p.wfull + (int64_t)S.e[j].m * kWRoi;   // dense rows, only dereferenced for code-5 rows / columns
-#pragma unroll
-          for (int r = 0; r < kCT; ++r)
-            cl_fold_row(sg + lane * (kP * kP), S, j, st * kCT + r, wtab + (ty0 + st * kCT + r - org.x) * kP, rg[r]);
+          cl_fold_subtile(sg + lane * (kP * kP), S, j, st, wtab + (ty0 + st * kCT - org.x) * kP, rg);
           __syncwarp();   // every lane is done with the staged block: refill it while the columns are walked
           nj = cl_next_pair(S, st, m);
           if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
