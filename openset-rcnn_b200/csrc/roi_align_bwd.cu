@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_bwd_kernel(const __grid
 
 // =========================================================================================================
 // channels_last gather kernel: thread = CHANNEL (the mirror image of roi_align_fwd_nhwc_kernel).
-// One CTA per (image, level, 16x16-pixel tile, 128-channel slab), worked through as four 4x16 sub-tiles; warp w owns channels [32w, 32w+32) of the slab and a
+// One CTA per (image, level, 16x16-pixel tile), worked through 128 channels at a time as four 4x16 sub-tiles; warp w owns channels [32w, 32w+32) of the slab and a
 // private [pixel][lane] fp32 accumulator tile in shared memory (bank = lane: conflict-free).  Per RoI that meets the
 // tile (index order => fixed summation order) the warp
 //   1. copies its 32 x 49 block of grad_out (6272 contiguous bytes) into a private staging buffer with cp.async
@@ -751,15 +751,13 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
   const LevelDesc& lv = p.L.lv[level];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.L.C;
-  const int c0w = blockIdx.y * (kCWarps * 32) + warp * 32;   // first channel of this warp
-  const bool wactive = c0w < C;                              // C % 32 == 0 (host-checked)
+  const int nslab = ceil_div(C, kCWarps * 32);   // 128-channel slabs, walked one after the other with the same tables
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   float* acc = S.acc[warp];
   float* accl = acc + lane;
   float* sg = S.sg[warp];
   const bool vec = ((lv.sW & 3) == 0) && ((lv.sH & 3) == 0) && ((lv.sN & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
-  float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
   // write-out slot: lane -> (pixel column xs + 4 q, channels quad .. quad + 4): four 128-byte runs per 16-byte store
   const int quad = (lane & 7) * 4, xs = lane >> 3;
 
@@ -774,7 +772,10 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
       if (tid < kCS) S.stmask[tid] = 0;
       __syncthreads();
     }
-    if (wactive) {
+    for (int slab = 0; slab < nslab; ++slab) {
+      const int c0w = slab * (kCWarps * 32) + warp * 32;   // first channel of this warp; C % 32 == 0 (host-checked)
+      if (c0w >= C) break;
+      float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
       int nj = cl_next_pair(S, -1, 0);
       if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
       for (int st = 0; st < kCS; ++st) {
@@ -929,7 +930,7 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   if (cl) {
     const size_t smem = sizeof(ClSmem);
     OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(p.cl_tile_base[num_levels], osr::ceil_div(C, kCWarps * 32));
+    dim3 grid(p.cl_tile_base[num_levels], 1);
     roi_align_bwd_cl_kernel<<<grid, kCThreads, smem, s>>>(p);
     OSR_LAUNCH_CHECK();
     return 0;
