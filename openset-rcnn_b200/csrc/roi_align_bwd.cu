@@ -484,7 +484,7 @@ struct __align__(16) ClSmem {
   uchar2 lohi[kCNB][kCH];                   // scratch: (first, last) bin with weight of each tile row; first > last = none
   unsigned char pm[kCNB][kCS];              // first bin of the 4-bin window shared by the sub-tile's rows; 254 = no weight,
                                             // 255 = the rows span more than 4 bins (dense 7-bin fold)
-  uchar2 run[kCNB][8];                      // [k] = (first, last + 1) tile column whose code is k (k = 0..5)
+  __align__(16) uchar2 run[kCNB][8];        // [k] = (first, last + 1) tile column whose code is k (k = 0..5)
   BatchEntry e[kCNB];
   int2 org[kCNB];                           // (y0, x0) of the RoI's footprint: origin of its rows in the workspace table
   unsigned stmask[kCS];                     // bit j: RoI j of the batch puts weight on sub-tile st
@@ -800,12 +800,13 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
           nj = cl_next_pair(S, st, m);
           if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
           const float4* xcol = S.xcol[j];
-          cl_run<0>(xcol, S.run[j][0], accl, rg);
-          cl_run<1>(xcol, S.run[j][1], accl, rg);
-          cl_run<2>(xcol, S.run[j][2], accl, rg);
-          cl_run<3>(xcol, S.run[j][3], accl, rg);
-          cl_run<4>(xcol, S.run[j][4], accl, rg);
-          const uchar2 dn = S.run[j][5];      // columns that sit in more than 3 bins (bins narrower than half a pixel)
+          const uint4 rb = *reinterpret_cast<const uint4*>(S.run[j]);   // all run bounds of this RoI in one load
+          cl_run<0>(xcol, make_uchar2(rb.x & 0xff, (rb.x >> 8) & 0xff), accl, rg);
+          cl_run<1>(xcol, make_uchar2((rb.x >> 16) & 0xff, rb.x >> 24), accl, rg);
+          cl_run<2>(xcol, make_uchar2(rb.y & 0xff, (rb.y >> 8) & 0xff), accl, rg);
+          cl_run<3>(xcol, make_uchar2((rb.y >> 16) & 0xff, rb.y >> 24), accl, rg);
+          cl_run<4>(xcol, make_uchar2(rb.z & 0xff, (rb.z >> 8) & 0xff), accl, rg);
+          const uchar2 dn = make_uchar2((rb.z >> 16) & 0xff, rb.z >> 24);   // columns in more than 3 bins (bins narrower than half a pixel)
           for (int x = dn.x; x < dn.y; ++x) {
             if (__float_as_int(xcol[x].w) != 5) continue;
             const float* wd = wtab + kFW * kP + (tx0 + x - org.y) * kP;
