@@ -678,11 +678,24 @@ __global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __
     fast = !__any_sync(0xffffffffu, bad);
   }
   if (fast) {
+    // Tap window of each bin: TT = taps the row loop will execute (4 / 6 / 8 by the widest bin).  The window start is
+    // pulled left so that all TT taps stay inside the row (columns [0, wf)) and the weights are shifted right by the
+    // same amount: zero-weight taps then re-read real data of the SAME row, never uninitialised shared memory, and the
+    // CTA does not have to zero-fill its 96 KB ring (footprints narrower than TT still do).
+    const int TT = tmax <= 4 ? 4 : (tmax <= 6 ? 6 : 8);
     for (int i = lane; i < kP * 8; i += 32) {
       const int pw = i >> 3, q = i & 7;
-      rec[16 + i] = (q < T.nx[pw]) ? T.wx[pw * kRB + q] : 0.f;
+      const int nx = T.nx[pw];
+      const int first = nx > 0 ? T.xb[pw] - xmin : 0;
+      const int start = max(0, min(first, wf - TT));
+      const int qq = q - (first - start);
+      rec[16 + i] = (qq >= 0 && qq < nx) ? T.wx[pw * kRB + qq] : 0.f;
     }
-    if (lane < 8) reinterpret_cast<int*>(rec)[8 + lane] = (lane < kP && T.nx[lane] > 0) ? T.xb[lane] - xmin : 0;
+    if (lane < 8) {
+      const int nx = lane < kP ? T.nx[lane] : 0;
+      const int first = nx > 0 ? T.xb[lane] - xmin : 0;
+      reinterpret_cast<int*>(rec)[8 + lane] = max(0, min(first, wf - TT));
+    }
     if (lane == 0) reinterpret_cast<float4*>(rec)[1] = make_float4(1.0f / g.count, __int_as_float(tmax), __int_as_float(img), 0.f);
   }
   if (lane == 0) reinterpret_cast<int4*>(rec)[0] = make_int4((fast ? 1 : 0) | (level << 8), xmin, ymin, wf | (hf << 16));
@@ -853,8 +866,12 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   // unrolled and predicate-free; padded taps read finite data (the ring is zero-initialised once and only ever holds
   // feature values; 8 columns of slack follow the last stage).
   const bool fast_taps = (nxc == 1) && (tmax <= 8);   // tmax = widest bin in pixels: picks the 4-, 6- or 8-tap row loop
-  for (int i = tid; i < (p.ring_floats >> 2); i += kThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic zero-fill before async-proxy bulk writes
+  // Zero-weight padded taps must read finite data.  Records keep every tap inside the loaded row unless the footprint
+  // is narrower than the tap count; only then (and on the in-CTA table path) the ring is zero-filled first.
+  if (!pre || wf < 8) {
+    for (int i = tid; i < (p.ring_floats >> 2); i += kThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic zero-fill before async-proxy bulk writes
+  }
   __syncthreads();
   // producer prologue
   if (warp == 0) {
