@@ -282,25 +282,32 @@ def run_ours(args, rank, local_rank, world):
     # ---- north-star variant at N > 1: PLN loss over the global batch (NCCL all-gather of the embeddings) ---------
     gathered = None
     if world > 1:
-        for _ in range(3):
-            path.step(gather_pln=True)
-        torch.cuda.synchronize(dev)
-        barrier(world)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(10):
-            path.step(gather_pln=True)
-        g1.record()
-        torch.cuda.synchronize(dev)
-        g_ms = max_over_ranks(g0.elapsed_time(g1), world, dev) / 10
-        R_loc = N * cfg.rois_per_image
-        gathered = {"ms_per_step": g_ms, "value": world * N * 1e3 / g_ms, "steps": 10,
-                    "all_gather_bytes_received_per_rank": (world - 1) * R_loc * (cfg.emb_dim * 4 + 8),
-                    "note": "same step with the PLN loss evaluated over the global batch: the tcgen05 encoder GEMM's "
-                            "epilogue stores its tiles into every rank's symmetric-memory buffer over NVLink (fused "
-                            "all-gather, osr_pln_encode_gather_fwd), labels/ious by NCCL all_gather, every rank then "
-                            "runs the loss kernels on W*R rows (osr_b200/dist.py); the headline value keeps the "
-                            "reference's per-rank loss"}
+        try:
+            for _ in range(3):
+                path.step(gather_pln=True)
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(10):
+                path.step(gather_pln=True)
+            g1.record()
+            torch.cuda.synchronize(dev)
+            g_ms = max_over_ranks(g0.elapsed_time(g1), world, dev) / 10
+            R_loc = N * cfg.rois_per_image
+            fused = bool(path._fused_enc)
+            gathered = {"ms_per_step": g_ms, "value": world * N * 1e3 / g_ms, "steps": 10,
+                        "all_gather_bytes_received_per_rank": (world - 1) * R_loc * (cfg.emb_dim * 4 + 8),
+                        "fused_encoder_gather": fused,
+                        "note": ("same step with the PLN loss evaluated over the global batch: the tcgen05 encoder GEMM's "
+                                 "epilogue stores its tiles into every rank's symmetric-memory buffer over NVLink (fused "
+                                 "all-gather, osr_pln_encode_gather_fwd), " if fused else
+                                 "same step with the PLN loss evaluated over the global batch: NCCL all_gather_into_tensor "
+                                 "of the embeddings (symmetric memory unavailable: %s), " % path.fused_gather_error) +
+                                "labels/ious by NCCL all_gather, every rank then runs the loss kernels on W*R rows "
+                                "(osr_b200/dist.py); the headline value keeps the reference's per-rank loss"}
+        except Exception as e:  # noqa: BLE001 - the side measurement must never take the headline line down
+            gathered = {"error": repr(e)}
         barrier(world)
 
     # ---- end to end: inputs start in pinned host memory every step ----------------------------------

@@ -116,6 +116,7 @@ class RoiPathStep:
         self.count_col = sel.num_levels
         self.last: Dict[str, torch.Tensor] = {}
         self._fused_enc = None
+        self.fused_gather_error = None
         self.events: Optional[List[torch.cuda.Event]] = None
 
     # ------------------------------------------------------------------------------------------------
@@ -155,7 +156,12 @@ class RoiPathStep:
             # north-star variant, B200-native: the encoder GEMM's epilogue stores its tiles into every rank's buffer
             # over NVLink (fused all-gather), then the global-batch loss (dist.py)
             if self._fused_enc is None:
-                self._fused_enc = FusedEncoderGather(pi.roi_features.shape[0], cfg.emb_dim, self.device)
+                try:
+                    self._fused_enc = FusedEncoderGather(pi.roi_features.shape[0], cfg.emb_dim, self.device)
+                except Exception as e:  # noqa: BLE001 - no symmetric memory / P2P on this box: NCCL all-gather instead
+                    self._fused_enc = False
+                    self.fused_gather_error = repr(e)
+        if gather_pln and cfg.encoder_impl == "tcgen05" and self._fused_enc:
             loss, emb = fused_gathered_pln_loss(self._fused_enc, pi.roi_features, pi.enc_w, pi.enc_b, reps,
                                                 pi.gt_classes, pi.ious, **kw)
         else:
