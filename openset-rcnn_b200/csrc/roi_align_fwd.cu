@@ -825,14 +825,24 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     inv_count = 1.0f / g.count;
     __syncthreads();   // T.rw complete; T.nx / T.xb / T.wx read below
 #pragma unroll
+    for (int pw = 0; pw < kP; ++pw) tmax = max(tmax, T.nx[pw]);
+    // tap windows pulled inside the row, weights shifted by the same amount (see roi_fwd_prep_kernel)
+    const int TT = tmax <= 4 ? 4 : (tmax <= 6 ? 6 : 8);
+#pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
-      toff[pw] = (T.nx[pw] > 0 ? T.xb[pw] - xmin : 0) * C;
-      tmax = max(tmax, T.nx[pw]);
+      const int first = T.nx[pw] > 0 ? T.xb[pw] - xmin : 0;
+      toff[pw] = max(0, min(first, wf - TT)) * C;
     }
     if (tid < kP) {
+      const int nx = T.nx[tid];
+      const int first = nx > 0 ? T.xb[tid] - xmin : 0;
+      const int shift = first - max(0, min(first, wf - TT));
       float w8[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) w8[q] = (q < T.nx[tid]) ? T.wx[tid * kRB + q] : 0.f;
+      for (int q = 0; q < 8; ++q) {
+        const int qq = q - shift;
+        w8[q] = (qq >= 0 && qq < nx && qq < kRB) ? T.wx[tid * kRB + qq] : 0.f;
+      }
       T.wt[tid][0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
       T.wt[tid][1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
     }
@@ -855,7 +865,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
 
   // stage geometry: a stage holds one footprint row (chunk).  Narrow RoIs get more, smaller stages (deeper prefetch),
   // RoIs up to 48 pixels wide are still staged as whole rows, wider ones in 32-column chunks.
-  const int scols = wf <= kNhwcWide ? ((wf + 3) & ~3) : 32;
+  const int scols = wf <= kNhwcWide ? max(8, (wf + 3) & ~3) : 32;   // >= 8: every (padded) tap stays inside its own stage
   const int nstages = min(kNhwcMaxStages, kNhwcRingCols / scols);
   const int stage_floats = scols * C;
   const int nxc = ceil_div(wf, scols);
@@ -866,9 +876,9 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   // unrolled and predicate-free; padded taps read finite data (the ring is zero-initialised once and only ever holds
   // feature values; 8 columns of slack follow the last stage).
   const bool fast_taps = (nxc == 1) && (tmax <= 8);   // tmax = widest bin in pixels: picks the 4-, 6- or 8-tap row loop
-  // Zero-weight padded taps must read finite data.  Records keep every tap inside the loaded row unless the footprint
-  // is narrower than the tap count; only then (and on the in-CTA table path) the ring is zero-filled first.
-  if (!pre || wf < 8) {
+  // Zero-weight padded taps must read finite data.  The tap windows stay inside the loaded row unless the footprint is
+  // narrower than the tap count; only then the pad columns exist and the ring is zero-filled first.
+  if (wf < 8) {
     for (int i = tid; i < (p.ring_floats >> 2); i += kThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic zero-fill before async-proxy bulk writes
   }
