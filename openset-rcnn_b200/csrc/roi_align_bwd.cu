@@ -2,14 +2,18 @@
 // Replaces autograd's torchvision roi_align_backward (fp32 atomicAdd scatter, non-deterministic, plus a
 // separate zero-fill of every dense gradient map) at train.py:145.
 //
-//   prep kernel   one thread per RoI: FPN level + exact pixel bounding box of its footprint.
-//   gather kernel one CTA per (image, level, 16x16-pixel tile).  The CTA scans the RoIs of its image in index
-//                 order, keeps those whose box meets the tile (ordered => fixed accumulation order), builds
-//                 their separable weight tables restricted to the tile (same sample arithmetic as the
-//                 forward => exact adjoint), and then, 16 channels at a time, every thread (= one pixel)
-//                 accumulates   g[c][y][x] += Wy[ph][y] * Wx[pw][x] / count * grad_out[roi][c][ph][pw]
-//                 in registers over the RoI list and writes its pixel ONCE with a plain store - which also
-//                 provides the zero fill of untouched pixels.  No atomics, no memset, run-to-run bit-identical.
+//   prep kernel    one WARP per RoI: FPN level, exact pixel box of the footprint and (per axis, extents <= 64 px) the
+//                  dense weight rows Wy[row][bin] / count, Wx[col][bin] written once to the workspace.
+//   gather kernels one CTA per (image, level, 16x16-pixel tile).  The CTA scans the RoIs of its image in index order,
+//                  keeps those whose box meets the tile (ordered => fixed accumulation order), loads / derives their
+//                  separable weight tables restricted to the tile (same sample arithmetic as the forward => exact
+//                  adjoint) and accumulates
+//                      g[c][y][x] += Wy[ph][y] * Wx[pw][x] / count * grad_out[roi][c][ph][pw]
+//                  writing every pixel ONCE with a plain store - which is also the zero fill of untouched pixels.
+//                  No atomics, no memset, run-to-run bit-identical.
+//                  * roi_align_bwd_cl_kernel (channels_last gradients, C % 32 == 0): thread = channel, accumulators in
+//                    shared memory, separable in both directions - see the comment above that kernel;
+//                  * roi_align_bwd_kernel (any strides): thread = pixel, 32 channels at a time in registers.
 #include <cstdlib>
 
 #include "roi_geometry.cuh"
@@ -453,14 +457,16 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_bwd_kernel(const __grid
 
 // =========================================================================================================
 // channels_last gather kernel: thread = CHANNEL (the mirror image of roi_align_fwd_nhwc_kernel).
-// One CTA per (image, level, 16x16-pixel tile), worked through 128 channels at a time as four 4x16 sub-tiles; warp w owns channels [32w, 32w+32) of the slab and a
-// private [pixel][lane] fp32 accumulator tile in shared memory (bank = lane: conflict-free).  Per RoI that meets the
-// tile (index order => fixed summation order) the warp
+// One CTA per (image, level, 16x16-pixel tile), worked through 128 channels at a time (same RoI scan and tables for
+// every slab) as four 4x16 sub-tiles; warp w owns channels [32w, 32w+32) of the slab and a private [pixel][lane] fp32
+// accumulator sub-tile in shared memory (bank = lane: conflict-free).  Per (sub-tile, RoI) pair, in RoI index order
+// (=> fixed summation order), the warp
 //   1. copies its 32 x 49 block of grad_out (6272 contiguous bytes) into a private staging buffer with cp.async
 //      (lane = channel reads it at stride 49: conflict-free);
-//   2. per tile row folds the y weights:  rg[pw] = sum_ph Wy[ph][y]/count * g[ph][pw]   (<= 3 bins per row in the
-//      common case, addressed dynamically in the staged block; dense 7-bin fold otherwise); the staging buffer is
-//      then refilled with the next RoI's block while the columns are walked;
+//   2. folds the y weights of the 4 rows:  rg[r][pw] = sum_ph Wy[ph][y_r]/count * g[ph][pw]; the rows share one window
+//      of 4 consecutive bins, so 4 rows of g are read once and each row is a branch-free 4-term combination (dense
+//      7-bin fold when bins are narrower than a pixel); the staging buffer is then refilled with the next pair's block
+//      while the columns are walked;
 //   3. walks the tile columns the RoI touches:  acc[y][x] += sum_pw Wx[pw][x] * rg[y][pw]  (<= 3 bins per column; the
 //      first bin never decreases with x, so the columns split into <= 5 runs of equal first bin, each a branch-free
 //      loop with compile-time register indices; columns in > 3 bins take a dense 7-bin loop).
