@@ -582,10 +582,15 @@ __global__ void __launch_bounds__(kThreads, OSR_FWD_MINB) roi_align_fwd_kernel(c
 // =========================================================================================================
 // channels_last (NHWC) forward: the layout the north star asks for ("coalesced NHWC reads").  A footprint row of a
 // channels_last map is ONE contiguous run of wf*C floats (22 KB for a 22-pixel-wide RoI at C = 256), so it is streamed
-// with a single cp.async.bulk (UBLKCP) per row into a 2-stage shared-memory ring guarded by mbarriers; no address
-// arithmetic, no sector waste, tens of KB in flight per CTA.  Thread t owns channel t and keeps all 49 outputs of the RoI
-// in registers:  per row  U[pw] = sum_x Wx[pw][x] * row[x][c]   (conflict-free LDS: consecutive threads, consecutive floats)
-//                then     out[ph][pw] += Wy[ph][y] * U[pw]      for the <= 3 bins containing the row (uniform switch).
+// with a single cp.async.bulk (UBLKCP) per row into a shared-memory ring guarded by mbarriers (2..6 stages, sized to the
+// RoI); no address arithmetic, no sector waste, tens of KB in flight per CTA.  Thread t owns channel t and keeps all 49
+// outputs of the RoI in registers:
+//   per row  U[pw] = sum_x Wx[pw][x] * row[x][c]   (conflict-free LDS: consecutive threads, consecutive floats; the taps
+//                                                   of every bin padded with zero weights to 4 / 6 / 8 - chosen per RoI -
+//                                                   and the tap window pulled inside the row, so the loop is branch-free
+//                                                   and never reads outside its own stage)
+//   then     out[ph][pw] += Wy[ph][y] * U[pw]      for the <= 3 bins containing the row (uniform switch).
+// The per-RoI tables come from roi_fwd_prep_kernel's records in the common case (in-CTA derivation otherwise).
 // The 49 x C tile is transposed through shared memory and stored with 16-byte coalesced writes (C-major output).
 constexpr int kNhwcRingCols = 96;   // ring capacity in pixel columns (x C floats); split per RoI into 2..6 row stages
 constexpr int kNhwcMaxStages = 6;
