@@ -2,7 +2,8 @@
 
 This package is a device-agnostic, pure-torch restatement of the reference's
 post-backbone RoI path (CF-RPN proposal stage -> ROIPooler/ROIAlignV2 -> PLN
-loss).  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+loss) and of its neighbours (``sampling``: proposal<->GT matching + labelled
+sampling; ``rcnn_inference``: ROI-head inference post-processing).  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` may import it; the product package
 (``openset-rcnn_b200/osr_b200``) never does.
 
@@ -27,4 +28,4 @@ committed under ``tests/golden/`` with the generating script, and (2) the
 closed-form vectors of SURVEY.md Appendix C.
 """
 
-from . import structures, rpn, nms, roi_align, pln, bytes_model, pipeline  # noqa: F401
+from . import structures, rpn, nms, roi_align, pln, bytes_model, pipeline, sampling, rcnn_inference  # noqa: F401
