@@ -1,0 +1,53 @@
+"""Host-side logic that needs no GPU: sampling (subsample_labels is pure torch), sharding, the byte model's stage
+accounting, and the product's refusal to run its matching / inference ops on CPU tensors."""
+import pytest
+import torch
+
+from oracle import sampling as osamp
+
+
+def test_subsample_labels_matches_oracle_with_the_same_permutations():
+    from osr_b200.sampling import subsample_labels
+    g = torch.Generator().manual_seed(3)
+    labels = torch.where(torch.rand(700, generator=g) < 0.3, torch.randint(0, 20, (700,), generator=g), torch.full((700,), 80))
+    labels[::50] = -1
+
+    def stream(seed):
+        gg = torch.Generator().manual_seed(seed)
+        return lambda n: torch.randperm(n, generator=gg)
+
+    a = subsample_labels(labels, 512, 0.25, 80, stream(9))
+    b = osamp.subsample_labels(labels, 512, 0.25, 80, stream(9))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert len(a[0]) == min(128, int(((labels != -1) & (labels != 80)).sum())) and len(a[0]) + len(a[1]) == 512
+    assert bool((labels[a[0]] != 80).all()) and bool((labels[a[1]] == 80).all())
+
+
+def test_subsample_labels_few_negatives():
+    from osr_b200.sampling import subsample_labels
+    labels = torch.tensor([1, 2, 80, 3, 80, -1, 4])
+    fg, bg = subsample_labels(labels, 4, 0.5, 80, lambda n: torch.arange(n))
+    assert fg.tolist() == [0, 1] and bg.tolist() == [2, 4]
+
+
+def test_shard_range_covers_everything_once():
+    from osr_b200.dist import shard_range
+    for total, world in ((16, 8), (17, 4), (3, 8), (128, 3)):
+        seen = []
+        for r in range(world):
+            seen += list(shard_range(total, r, world))
+        assert seen == list(range(total))
+
+
+def test_matching_and_inference_ops_refuse_cpu_tensors():
+    from osr_b200 import _lib
+    from osr_b200.inference import inference
+    from osr_b200.sampling import match_proposals
+    from osr_b200.structures import Boxes, Instances
+    off = torch.tensor([0, 2], dtype=torch.int32)
+    with pytest.raises(_lib.OsrError):
+        match_proposals(torch.rand(2, 4), off, torch.rand(1, 4), torch.zeros(1, dtype=torch.int64),
+                        torch.tensor([0, 1], dtype=torch.int32), 2)
+    p = Instances((10, 10)); p.set("proposal_boxes", Boxes(torch.rand(2, 4))); p.set("objectness_logits", torch.rand(2))
+    with pytest.raises(_lib.OsrError):
+        inference((torch.rand(2, 4), torch.rand(2, 1)), [p], torch.rand(2, 8))
