@@ -151,3 +151,45 @@ def gathered_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tenso
         emb_all = all_gather_rows(emb.detach(), group)
         labels_all, ious_all = _gather_meta(labels, ious, group)
     return _loss_on_global_rows(emb, emb_all, reps, labels_all, ious_all, rank, world, loss_fn, **kw)
+
+
+class _MeanOverRanks(torch.autograd.Function):
+    """value: mean over ranks of the per-rank loss; backward: identity - the local loss keeps its full gradient, which is
+    exactly the gathered rule for the local rows (global 1/W times the W scale that feeds a DDP-averaged encoder)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.detach().clone()
+        dist.all_reduce(y, group=group)
+        return y / dist.get_world_size(group)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def reduced_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tensor, ious: torch.Tensor, *,
+                     group=None, loss_fn: Optional[Callable] = None, **kw) -> torch.Tensor:
+    """The gathered PLN loss WITHOUT gathering: same value and the same gradients as ``gathered_pln_loss``, from the
+    per-rank loss plus two tiny all-reduces.  Every row term of the loss depends only on (its embedding, the prototypes),
+    so  (1/W) sum_r L_r  ==  w/(W R_loc) (sum A_r + sum B_r + W C)  is the global-batch loss; the local embedding
+    gradient is the per-rank one, and ``representatives.grad`` is the rank mean of the per-rank gradients (all-reduced
+    in a hook, so it is identical on all ranks as with the gathered formulation).  Cost per rank: the loss kernels on
+    R_loc rows (not W R_loc) + all-reduce of 1 + K*D floats, instead of an all-gather of R_loc*D floats per peer."""
+    if loss_fn is None:
+        from .pln import pln_loss_from_emb as loss_fn  # CUDA kernels
+    R = emb.shape[0]
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return loss_fn(emb, reps, labels, ious, r_norm=float(max(R, 1)), center_weight=1.0, emb_grad_scale=1.0, **kw)
+    world = dist.get_world_size(group)
+    reps_local = reps.view_as(reps)   # a non-leaf alias: its gradient hook averages over ranks before it reaches `reps`
+
+    def _mean(g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, group=group)
+        return g / world
+
+    if reps_local.requires_grad:
+        reps_local.register_hook(_mean)
+    local = loss_fn(emb, reps_local, labels, ious, r_norm=float(max(R, 1)), center_weight=1.0, emb_grad_scale=1.0, **kw)
+    return _MeanOverRanks.apply(local, group)

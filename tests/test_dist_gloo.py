@@ -54,6 +54,13 @@ def _worker(rank, world, port, q):
     ok = (torch.allclose(loss.detach(), mean_loss, rtol=1e-5, atol=1e-7)
           and torch.allclose(emb.grad, emb_r.grad, rtol=1e-4, atol=1e-8)
           and torch.allclose(reps.grad, mean_reps_grad, rtol=1e-4, atol=1e-8))
+    # the same loss without gathering: per-rank loss + all-reduce of the value and of the prototype gradient
+    emb2 = emb.detach().clone().requires_grad_(True); reps2 = reps0.clone().requires_grad_(True)
+    loss2 = odist.reduced_pln_loss(emb2, reps2, pi.gt_classes, pi.ious, loss_fn=_oracle_loss_fn, **KW)
+    loss2.backward()
+    ok = ok and (torch.allclose(loss2.detach(), loss.detach(), rtol=1e-5, atol=1e-7)
+                 and torch.allclose(emb2.grad, emb.grad, rtol=1e-4, atol=1e-8)
+                 and torch.allclose(reps2.grad, reps.grad, rtol=1e-4, atol=1e-8))
     shards = [list(odist.shard_range(19, k, world)) for k in range(world)]
     ok = ok and sorted(sum(shards, [])) == list(range(19))
     q.put((rank, bool(ok), float(loss), float(mean_loss)))
