@@ -192,6 +192,100 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- GPU library baseline
+def gpu_baseline(path, cfg, iters: int = 5):
+    """The kernels the reference actually runs on a GPU, timed on this B200 on the SAME
+    inputs in the same process: torchvision-CUDA roi_align forward / backward (per level + index_put, as detectron2's
+    ROIPooler does, NCHW maps), ATen topk + the elementwise decode of ALL anchors, torchvision-CUDA nms, and the
+    torch op chain of PLN.loss.  Library calls only (nothing from oracle/); the reference's per-image Python loops and
+    host syncs are NOT included, so this flatters the reference."""
+    import torchvision
+    dev = path.device
+    N = cfg.num_images
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    # S1: decode every anchor (Box2BoxTransformLinear) + per-level topk + gather
+    def s1():
+        res = []
+        for a, d, c in zip(path.anchors, path.deltas, path.ctr):
+            d = torch.relu(d)
+            cx, cy = 0.5 * (a[:, 0] + a[:, 2]), 0.5 * (a[:, 1] + a[:, 3])
+            st = torch.stack([a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]] * 2, dim=1)
+            d = d * st
+            boxes = torch.stack((cx - d[..., 0], cy - d[..., 1], cx + d[..., 2], cy + d[..., 3]), dim=-1)
+            k = min(c.shape[1], cfg.pre_nms_topk)
+            v, i = c.topk(k, dim=1)
+            res.append(torch.gather(boxes, 1, i[..., None].expand(-1, -1, 4)))
+        return torch.cat(res, dim=1)
+    out["s1_decode_topk_ms"] = timed(s1)
+    # S3: detectron2 ROIPooler = per-level torchvision roi_align + index_put (NCHW maps), backward by autograd
+    from osr_b200 import synth
+    rois = path.last["rois"].detach()
+    lvl = path.last["level"].long()
+    feats = [f.detach().contiguous().requires_grad_(True) for f in path.feats]
+    idx = [torch.nonzero(lvl == l, as_tuple=True)[0] for l in range(4)]
+
+    def s3_fwd():
+        o = torch.zeros((rois.shape[0], cfg.channels, 7, 7), device=dev)
+        for l in range(4):
+            o.index_put_((idx[l],), torchvision.ops.roi_align(feats[l], rois[idx[l]], (7, 7), synth.POOL_SCALES[l], 0, True))
+        return o
+    out["s3_roialign_fwd_ms"] = timed(s3_fwd)
+    pooled = s3_fwd()
+    out["s3_roialign_bwd_ms"] = timed(lambda: torch.autograd.grad(pooled, feats, path.grad_pooled, retain_graph=True))
+    del pooled, feats
+    # NMS: one image's kept proposals (level-major, as the nominal mode / ROI-head sites see them), thr 0.7
+    sel = path.last["sel"]
+    c = int(sel.counts[0, sel.num_levels])
+    b, sc = sel.boxes[0, :c].contiguous(), sel.scores[0, :c].contiguous()
+    out["nms_boxes"] = c
+    out["nms_torchvision_ms"] = timed(lambda: torchvision.ops.nms(b, sc, 0.7))
+    from osr_b200 import nms as onms
+    out["nms_ours_ms"] = timed(lambda: onms.nms(b, sc, 0.7))
+    # S5: the torch op chain of PLN.loss (encoder Linear fp32 + loss) forward + backward
+    import torch.nn.functional as F
+    pi = path.pln
+
+    def s5():
+        x = pi.roi_features
+        w = pi.enc_w.detach().requires_grad_(True)
+        reps = pi.reps.detach().requires_grad_(True)
+        emb = F.linear(x, w, pi.enc_b)
+        nf, r = F.normalize(emb), F.normalize(reps)
+        fg = torch.nonzero((pi.gt_classes >= 0) & (pi.gt_classes < cfg.num_known) & (pi.ious > cfg.iou_threshold), as_tuple=True)[0]
+        dist = 1.0 - nf[fg] @ r.t()
+        ar = torch.arange(fg.numel(), device=dev)
+        intra = dist[ar, pi.gt_classes[fg]]
+        dist = dist.clone()
+        dist[ar, pi.gt_classes[fg]] = 1000
+        inter = dist.min(dim=1)[0]
+        cd = (1.0 - r @ r.t()).clone()
+        cd.fill_diagonal_(1000)
+        cmin = cd.min(dim=1)[0]
+        loss = ((intra - cfg.alpha).clamp(min=0).sum() + (cfg.beta - inter).clamp(min=0).sum() +
+                (cfg.beta + cfg.alpha - cmin).clamp(min=0).sum()) * cfg.loss_weight / x.shape[0]
+        return torch.autograd.grad(loss, [w, reps])
+    out["s5_pln_fwd_bwd_ms"] = timed(s5)
+    out["path_ms"] = out["s1_decode_topk_ms"] + out["s3_roialign_fwd_ms"] + out["s3_roialign_bwd_ms"] + out["s5_pln_fwd_bwd_ms"]
+    out["images_per_s"] = N * 1e3 / out["path_ms"]
+    out["note"] = ("torchvision 0.26 CUDA roi_align fwd/bwd (NCHW, per level + index_put), ATen topk + full decode, "
+                   "torchvision nms, torch PLN.loss op chain (fp32) on the same inputs; Python per-image loops / host syncs "
+                   "of the reference excluded")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, local_rank, world):
     from osr_b200 import _lib, roofline, synth
@@ -266,6 +360,15 @@ def run_ours(args, rank, local_rank, world):
             "path_aggregate": {"alg_bytes": path_bytes, "ms": path_ms, "gbs": path_bytes / (path_ms * 1e-3) / 1e9,
                                "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak},
             "stages": per_stage, "touched_feature_pixels": U}
+
+    # ---- the library kernels the reference runs on a GPU, same inputs, same process ---------------------
+    gbase = None
+    if rank == 0 and not args.no_gpu_baseline:
+        try:
+            gbase = gpu_baseline(path, cfg)
+        except Exception as e:  # noqa: BLE001 - a side measurement must never take the headline line down
+            gbase = {"error": repr(e)}
+        torch.cuda.empty_cache()
 
     # ---- the other feature layout, short run (same inputs, same code path selection rules) --------------
     alt = None
@@ -356,7 +459,7 @@ def run_ours(args, rank, local_rank, world):
                                    "fwd/bwd, S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))",
                    "parallelism": f"dp{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-        "stage_ms": stages, "alt_layout": alt,
+        "stage_ms": stages, "alt_layout": alt, "gpu_baseline": gbase,
     }
     if gathered is not None:
         line["gathered_pln"] = gathered
@@ -375,6 +478,7 @@ def main():
                     help="feed NCHW-contiguous FPN maps (the reference's layout) instead of channels_last (the north star's "
                          "'coalesced NHWC reads'; what a channels_last backbone emits); the other layout is reported under 'alt_layout'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

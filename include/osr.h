@@ -39,6 +39,22 @@ const char* osr_last_error(void);
 /* Number of kernel launches issued by this process since the last call to osr_reset_launch_count(). */
 long long osr_launch_count(void);
 void osr_reset_launch_count(void);
+/* Kernel-variant switches for A/B measurements (bench.py, tools/): NOT part of the drop-in surface.  Each key starts
+ * at its default (0 = the shipped kernel), or at the value of the environment variable OSR_TUNE_<KEY> read ONCE when
+ * the library is loaded - no entry point calls getenv.  Returns the previous value, or OSR_E_ARG for an unknown key.
+ *   OSR_TUNE_BWD_VARIANT   0 shared-memory accumulators (shipped) | 1 register accumulators, dense columns |
+ *                          2 register accumulators, 3-bin column switch | 3 pixel-per-thread kernel
+ *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records
+ *   OSR_TUNE_PLN_VARIANT   0 default | see csrc/pln_fused.cu
+ *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu */
+#define OSR_TUNE_BWD_VARIANT 0
+#define OSR_TUNE_FWD_VARIANT 1
+#define OSR_TUNE_PLN_VARIANT 2
+#define OSR_TUNE_RPN_VARIANT 3
+#define OSR_TUNE_NMS_VARIANT 4
+#define OSR_TUNE_COUNT 5
+int osr_set_tuning(int key, int value);
+int osr_get_tuning(int key);
 
 /* ------------------------------------------------------------------------------------------
  * (1) CF-RPN proposal stage

@@ -496,11 +496,13 @@ struct __align__(16) ClSmem {
   unsigned stmask[kCS];                     // bit j: RoI j of the batch puts weight on sub-tile st
   int warp_cnt[kCWarps + 1];
   int nb, next_pos;
+  static constexpr bool kDenseCols = false;
 };
 
 static_assert((kCNB * kCH + kCThreads) * 8 <= kCWarps * kGBlk, "table scratch must fit in the staging buffers");
 
-__device__ __forceinline__ void cl_collect(const BwdParams& p, ClSmem& S, int level, int tx0, int ty0, int pos, int r1) {
+template <class SM>
+__device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level, int tx0, int ty0, int pos, int r1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int hit[4], cnt = 0;
 #pragma unroll
@@ -560,7 +562,8 @@ __device__ __forceinline__ float4 cl_pack3(const float* w) {
   return make_float4(w[p0], w[p0 + 1], w[p0 + 2], __int_as_float(p0));
 }
 
-__device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, const LevelDesc& lv, int tx0, int ty0) {
+template <class SM>
+__device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const LevelDesc& lv, int tx0, int ty0) {
   const int tid = threadIdx.x;
   const int nb = S.nb;
   // one thread per (RoI, tile row | tile column): fetch its 7 bin weights (precomputed per RoI by the prep kernel;
@@ -612,6 +615,10 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
       S.lohi[j][r] = make_uchar2((unsigned char)lo, (unsigned char)hi);
     } else {
       S.xcol[j][r - kCH] = cl_pack3(wd);
+      if constexpr (SM::kDenseCols) {   // register-accumulator kernel: all 7 bin weights of the column stay resident
+        S.xd0[j][r - kCH] = make_float4(wd[0], wd[1], wd[2], wd[3]);
+        S.xd1[j][r - kCH] = make_float4(wd[4], wd[5], wd[6], 0.f);
+      }
     }
   }
   __syncthreads();
@@ -668,7 +675,8 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, ClSmem& S, c
 // staged block (49 floats, stride-49 across lanes: conflict-free).  The rows share one window of 4 bins, so 4 rows of
 // g are read once (28 LDS, dynamic base) and every row is a branch-free 4-term combination; sub-tiles whose rows span
 // more bins (bins narrower than a pixel) loop over all 7 bins with the dense weights from the workspace table.
-__device__ __forceinline__ void cl_fold_subtile(const float* gl, const ClSmem& S, int j, int st, const float* wdense,
+template <class SM>
+__device__ __forceinline__ void cl_fold_subtile(const float* gl, const SM& S, int j, int st, const float* wdense,
                                                 float (&rg)[kCT][kP]) {
   const int pmv = S.pm[j][st];
   if (pmv < 254) {
@@ -734,7 +742,8 @@ __device__ __forceinline__ void cl_stage(const BwdParams& p, float* sg, int m, i
 }
 
 // next (sub-tile, RoI) pair after sub-tile st with remaining mask m; returns the RoI slot or -1
-__device__ __forceinline__ int cl_next_pair(const ClSmem& S, int st, unsigned m) {
+template <class SM>
+__device__ __forceinline__ int cl_next_pair(const SM& S, int st, unsigned m) {
   while (m == 0) {
     if (++st >= kCS) return -1;
     m = S.stmask[st];
@@ -872,6 +881,177 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
   }
 }
 
+
+// =========================================================================================================
+// channels_last gather kernel, REGISTER accumulators (round 2; default).  Same decomposition as
+// roi_align_bwd_cl_kernel (CTA = (image, level, 16x16 tile); warp = 32 channels of a 128-channel slab; four 4x16
+// sub-tiles; per (sub-tile, RoI): staged grad_out block -> y fold -> x expansion, RoIs in index order), but the 4x16
+// accumulator sub-tile of a lane lives in 64 REGISTERS instead of shared memory: the x expansion is unrolled over the
+// 16 tile columns so every accumulator has a compile-time index.  That removes the accumulator read-modify-write (8 of
+// the 9 shared-memory operations per 4 pixels of the shared-memory version - the L1/shared pipe was its limiter: 142 M
+// wavefronts per launch) and the write-out staging: a finished sub-tile leaves straight from registers (lane =
+// channel: one 128-byte row segment per store instruction).
+//   MODE 0  per column: (w0, w1, w2, first bin) in one broadcast LDS.128, warp-uniform switch on the first bin (0..4),
+//           12 FFMA with compile-time register indices; RoIs that have a column in more than 3 bins (bins narrower than
+//           half a pixel) take MODE 1's body.
+//   MODE 1  per column all 7 bin weights (two LDS.128), 28 FFMA, branch-free.
+struct __align__(16) RegSmem {
+  float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
+  float4 yrow[kCNB][kCH];
+  float4 xcol[kCNB][kCW];                   // (w(p0), w(p0+1), w(p0+2), code): code 0..4 = p0, 5 = dense, 6 = empty
+  float4 xd0[kCNB][kCW], xd1[kCNB][kCW];    // all 7 bin weights of the column (w0..w3 | w4..w6, 0)
+  uchar2 lohi[kCNB][kCH];
+  unsigned char pm[kCNB][kCS];
+  __align__(16) uchar2 run[kCNB][8];
+  BatchEntry e[kCNB];
+  int2 org[kCNB];
+  unsigned stmask[kCS];
+  int warp_cnt[kCWarps + 1];
+  int nb, next_pos;
+  static constexpr bool kDenseCols = true;
+};
+
+template <int K>
+__device__ __forceinline__ void clr_fma3(float (&acc)[kCT][kCW], int x, const float4 w, const float (&rg)[kCT][kP]) {
+#pragma unroll
+  for (int r = 0; r < kCT; ++r) acc[r][x] = fmaf(w.z, rg[r][K + 2], fmaf(w.y, rg[r][K + 1], fmaf(w.x, rg[r][K], acc[r][x])));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
+
+  int t = (int)(gridDim.x - 1 - blockIdx.x), level = 0;   // coarsest level first (longest CTAs start early)
+  while (level + 1 < p.L.num_levels && t >= p.cl_tile_base[level + 1]) ++level;
+  t -= p.cl_tile_base[level];
+  const int per_img = p.cl_tiles_x[level] * p.cl_tiles_y[level];
+  const int n = t / per_img;
+  t -= n * per_img;
+  const int ty0 = (t / p.cl_tiles_x[level]) * kCH, tx0 = (t % p.cl_tiles_x[level]) * kCW;
+  const LevelDesc& lv = p.L.lv[level];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.L.C;
+  const int nslab = ceil_div(C, kCWarps * 32);
+  const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
+  float* sg = S.sg[warp];
+  const bool vec = ((lv.sW & 3) == 0) && ((lv.sH & 3) == 0) && ((lv.sN & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
+  const int quad = (lane & 7) * 4, xs = lane >> 3;   // zero-fill slot: lane -> (pixel column xs + 4 q, 4 channels)
+  const int ncol = min(kCW, lv.W - tx0);             // tile columns inside the map
+
+  int pos = r0;
+  bool first = true;
+  while (true) {
+    cl_collect(p, S, level, tx0, ty0, pos, r1);
+    const int nb = S.nb, next = S.next_pos;
+    if (nb > 0) {
+      cl_build_tables(p, S, lv, tx0, ty0);
+    } else {
+      if (tid < kCS) S.stmask[tid] = 0;
+      __syncthreads();
+    }
+    for (int slab = 0; slab < nslab; ++slab) {
+      const int c0w = slab * (kCWarps * 32) + warp * 32;
+      if (c0w >= C) break;
+      float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
+      int nj = cl_next_pair(S, -1, 0);
+      if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
+      for (int st = 0; st < kCS; ++st) {
+        unsigned m = S.stmask[st];
+        const bool any = (m != 0);
+        const int ys = ty0 + st * kCT;
+        if (!any) {   // nothing lands on this sub-tile: zero fill (first batch only)
+          if (!first) continue;
+          const int ny = min(kCT, lv.H - ys);
+          if (vec) {
+            float* gp = gimg + (int64_t)ys * lv.sH + (int64_t)(tx0 + xs) * lv.sW + quad;
+            const int64_t step = 4 * lv.sW;
+            for (int yy = 0; yy < ny; ++yy) {
+#pragma unroll
+              for (int q = 0; q < kCW / 4; ++q)
+                if (xs + 4 * q < ncol) *reinterpret_cast<float4*>(gp + q * step) = make_float4(0.f, 0.f, 0.f, 0.f);
+              gp += lv.sH;
+            }
+          } else {
+            for (int yy = 0; yy < ny; ++yy)
+              for (int x = 0; x < ncol; ++x) gimg[(int64_t)(ys + yy) * lv.sH + (int64_t)(tx0 + x) * lv.sW + lane] = 0.f;
+          }
+          continue;
+        }
+        float acc[kCT][kCW];
+#pragma unroll
+        for (int r = 0; r < kCT; ++r)
+#pragma unroll
+          for (int x = 0; x < kCW; ++x) acc[r][x] = 0.f;
+        while (m != 0) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          cp_async_wait<0>();
+          __syncwarp();
+          float rg[kCT][kP];
+          const int2 org = S.org[j];
+          const float* wtab = p.wfull + (int64_t)S.e[j].m * kWRoi;   // dense y rows: only read when bins are narrower than a pixel
+          cl_fold_subtile(sg + lane * (kP * kP), S, j, st, wtab + (ty0 + st * kCT - org.x) * kP, rg);
+          __syncwarp();   // every lane is done with the staged block: refill it while the columns are expanded
+          nj = cl_next_pair(S, st, m);
+          if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
+          const uint4 rb = *reinterpret_cast<const uint4*>(S.run[j]);
+          const bool dense = (MODE == 1) || (((rb.z >> 16) & 0xff) < (rb.z >> 24));   // some column sits in > 3 bins
+          if (!dense) {
+            const float4* xcol = S.xcol[j];
+#pragma unroll
+            for (int x = 0; x < kCW; ++x) {
+              const float4 w = xcol[x];
+              switch (__float_as_int(w.w)) {
+                case 0: clr_fma3<0>(acc, x, w, rg); break;
+                case 1: clr_fma3<1>(acc, x, w, rg); break;
+                case 2: clr_fma3<2>(acc, x, w, rg); break;
+                case 3: clr_fma3<3>(acc, x, w, rg); break;
+                case 4: clr_fma3<4>(acc, x, w, rg); break;
+                default: break;   // 6: the RoI puts no weight on this column
+              }
+            }
+          } else {
+            const float4* xd0 = S.xd0[j];
+            const float4* xd1 = S.xd1[j];
+#pragma unroll
+            for (int x = 0; x < kCW; ++x) {
+              const float4 a = xd0[x], b = xd1[x];
+#pragma unroll
+              for (int r = 0; r < kCT; ++r) {
+                float v = acc[r][x];
+                v = fmaf(a.x, rg[r][0], v); v = fmaf(a.y, rg[r][1], v); v = fmaf(a.z, rg[r][2], v); v = fmaf(a.w, rg[r][3], v);
+                v = fmaf(b.x, rg[r][4], v); v = fmaf(b.y, rg[r][5], v); v = fmaf(b.z, rg[r][6], v);
+                acc[r][x] = v;
+              }
+            }
+          }
+        }
+        // write-out straight from registers: one 128-byte row segment (32 channels of one pixel) per store instruction
+        const int ny = min(kCT, lv.H - ys);
+        float* gp = gimg + (int64_t)ys * lv.sH + (int64_t)tx0 * lv.sW + lane;
+#pragma unroll
+        for (int r = 0; r < kCT; ++r) {
+          if (r < ny) {
+#pragma unroll
+            for (int x = 0; x < kCW; ++x) {
+              if (x < ncol) {
+                float* dst = gp + (int64_t)r * lv.sH + (int64_t)x * lv.sW;
+                *dst = first ? acc[r][x] : (*dst + acc[r][x]);
+              }
+            }
+          }
+        }
+      }
+    }
+    first = false;
+    pos = next;
+    if (pos >= r1) break;
+    __syncthreads();   // tables are rebuilt by the next batch
+  }
+}
+
 int fill_bwd(BwdParams& p, const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int P,
              int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level) {
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
@@ -932,13 +1112,24 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
     OSR_LAUNCH_CHECK();
   }
   // channels_last gradient maps with whole 32-channel groups: thread-per-channel kernel
-  bool cl = (C % 32 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) && !getenv("OSR_ROIALIGN_BWD_PIXEL");
+  bool cl = (C % 32 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) && osr::tuning(osr::kTuneBwdVariant) != 3;
   for (int l = 0; l < num_levels; ++l) cl = cl && (p.L.lv[l].sC == 1);
   if (cl) {
-    const size_t smem = sizeof(ClSmem);
-    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.cl_tile_base[num_levels], 1);
-    roi_align_bwd_cl_kernel<<<grid, kCThreads, smem, s>>>(p);
+    const int variant = osr::tuning(osr::kTuneBwdVariant);
+    if (variant == 0) {          // shared-memory accumulators (shipped: fastest measured)
+      const size_t smem = sizeof(ClSmem);
+      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_bwd_cl_kernel<<<grid, kCThreads, smem, s>>>(p);
+    } else if (variant == 1) {   // register accumulators, dense 7-bin columns
+      const size_t smem = sizeof(RegSmem);
+      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_bwd_clr_kernel<1><<<grid, kCThreads, smem, s>>>(p);
+    } else {                     // variant 2: register accumulators, 3-bin columns behind a per-column switch
+      const size_t smem = sizeof(RegSmem);
+      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      roi_align_bwd_clr_kernel<0><<<grid, kCThreads, smem, s>>>(p);
+    }
     OSR_LAUNCH_CHECK();
     return 0;
   }

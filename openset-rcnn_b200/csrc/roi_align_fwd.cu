@@ -1187,7 +1187,7 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
       p.order = order;
     }
   }
-  // TMA staging is opt-in (OSR_ROIALIGN_TMA=1): on NCHW maps a footprint row is only ~50-130 bytes, and the TMA unit's
+  // TMA staging is opt-in (OSR_TUNE_FWD_VARIANT=1): on NCHW maps a footprint row is only ~50-130 bytes, and the TMA unit's
   // per-row request rate makes it slower than the LDG path (2.20 ms vs 1.71 ms at cfg2 on B200).
   // channels_last maps (sC == 1, a pixel's C channels contiguous, 16-byte aligned) take the bulk-copy NHWC kernel
   bool nhwc = (C <= kThreads) && (C % 4 == 0);
@@ -1196,7 +1196,7 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
     nhwc = lv.sC == 1 && lv.sW == C && lv.sH == (int64_t)lv.W * C && (lv.sN % 4 == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
   }
   if (nhwc) {
-    if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && !getenv("OSR_ROIALIGN_NO_PREP")) {
+    if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && osr::tuning(osr::kTuneFwdVariant) != 2) {
       p.rec = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 2 * osr::align256((size_t)M * 4));
       roi_fwd_prep_kernel<<<osr::ceil_div(M, kPrepWarpsF), kPrepWarpsF * 32, 0, s>>>(p);
       OSR_LAUNCH_CHECK();
@@ -1218,8 +1218,7 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
   }
   FwdTma tm;
   memset(&tm, 0, sizeof(tm));
-  const char* env = getenv("OSR_ROIALIGN_TMA");
-  const bool use_tma = env && env[0] == '1';
+  const bool use_tma = osr::tuning(osr::kTuneFwdVariant) == 1;
   for (int l = 0; l < num_levels; ++l)
     p.tma_ok[l] = use_tma ? encode_level_map(&tm.map[l], p.L.lv[l], num_images, C) : 0;
   p.ring_floats = use_tma ? kRingFloats : kWarps * kWarpTile;

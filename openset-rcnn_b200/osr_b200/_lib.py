@@ -41,6 +41,8 @@ SIGNATURES = {
     "osr_last_error": (C.c_char_p, []),
     "osr_launch_count": (C.c_longlong, []),
     "osr_reset_launch_count": (None, []),
+    "osr_set_tuning": (C.c_int, [C.c_int, C.c_int]),
+    "osr_get_tuning": (C.c_int, [C.c_int]),
     "osr_rpn_kmax": (C.c_int64, [C.POINTER(RpnLevel), C.c_int, C.c_int]),
     "osr_rpn_select_decode_workspace": (C.c_size_t, [C.POINTER(RpnLevel), C.c_int, C.c_int, C.c_int]),
     "osr_rpn_select_decode": (C.c_int, [
@@ -150,3 +152,15 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib().osr_reset_launch_count()
+
+
+TUNE_KEYS = {"bwd": 0, "fwd": 1, "pln": 2, "rpn": 3, "nms": 4}
+
+
+def set_tuning(key: str, value: int) -> int:
+    """Kernel-variant switch for A/B measurements (include/osr.h: osr_set_tuning); returns the previous value."""
+    return int(lib().osr_set_tuning(TUNE_KEYS[key], int(value)))
+
+
+def get_tuning(key: str) -> int:
+    return int(lib().osr_get_tuning(TUNE_KEYS[key]))

@@ -14,6 +14,17 @@ FWD_RTOL, FWD_ATOL = 1e-5, 2e-5   # features are N(0,1); outputs are means of <=
 BWD_RTOL, BWD_ATOL = 1e-4, 1e-4   # gradients accumulate up to ~hundreds of RoIs per pixel (fp32, different order)
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["bwd_smem", "bwd_reg_dense", "bwd_reg_switch"])
+def bwd_variant(request):
+    """Every channels_last backward test runs on the three thread-per-channel kernels (include/osr.h OSR_TUNE_BWD_VARIANT):
+    0 = shared-memory accumulators (shipped), 1 = register accumulators / dense columns, 2 = register accumulators /
+    per-column switch."""
+    from osr_b200 import _lib
+    prev = _lib.set_tuning("bwd", request.param)
+    yield request.param
+    _lib.set_tuning("bwd", prev)
+
+
 def _pooler_pair():
     from osr_b200.poolers import ROIPooler
     from osr_b200 import synth
@@ -210,7 +221,7 @@ def test_forward_channels_last_kernel_matches_torchvision(hw, n, per_img, C):
     torch.testing.assert_close(out, out_nchw, rtol=FWD_RTOL, atol=FWD_ATOL)
 
 
-def test_backward_channels_last_grads():
+def test_backward_channels_last_grads(bwd_variant):
     from osr_b200 import synth
     ours, ref = _pooler_pair()
     feats = synth.make_features(2, (320, 480), 32, seed=4, device="cuda:0", channels_last=True)
@@ -227,7 +238,7 @@ def test_backward_channels_last_grads():
 
 @pytest.mark.parametrize("hw,n,per_img,C", [((800, 1333), 2, 256, 256), ((320, 480), 3, 200, 96), ((224, 224), 1, 64, 32),
                                              ((224, 224), 1, 64, 40)])
-def test_backward_channels_last_kernel_matches_torchvision(hw, n, per_img, C):
+def test_backward_channels_last_kernel_matches_torchvision(hw, n, per_img, C, bwd_variant):
     """channels_last gradient maps with C % 32 == 0 take the thread-per-channel gather kernel (96 = a partly filled
     128-channel slab; 40 falls back to the pixel-per-thread kernel)."""
     from osr_b200 import synth
@@ -248,7 +259,7 @@ def test_backward_channels_last_kernel_matches_torchvision(hw, n, per_img, C):
         torch.testing.assert_close(a, c, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
 
 
-def test_backward_channels_last_dense_tile_tiny_rois_deterministic_adjoint():
+def test_backward_channels_last_dense_tile_tiny_rois_deterministic_adjoint(bwd_variant):
     """> kCNB RoIs on one tile (multi-batch path), sub-pixel bins (dense 7-bin fold), run-to-run bit-identical,
     and <pool(F), G> == <F, pool^T(G)>."""
     from osr_b200 import synth
@@ -274,7 +285,7 @@ def test_backward_channels_last_dense_tile_tiny_rois_deterministic_adjoint():
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-2, (float(lhs), float(rhs))
 
 
-def test_channels_last_width_sweep_stage_geometry():
+def test_channels_last_width_sweep_stage_geometry(bwd_variant):
     """Footprints 25..56 feature pixels wide at level 2: whole-row stages (<= 48 px, 2-3 stages) and the 32-column
     chunked path (> 48 px) of the channels_last forward, plus the matching backward tiles."""
     from osr_b200 import synth

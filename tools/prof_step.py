@@ -14,7 +14,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--images", type=int, default=16)
 ap.add_argument("--nchw", action="store_true")
+ap.add_argument("--tune", action="append", default=[], help="key=value of an OSR_TUNE_* switch (bwd, fwd, pln, rpn, nms)")
 a = ap.parse_args()
+from osr_b200 import _lib  # noqa: E402
+for kv in a.tune:
+    k, v = kv.split("=")
+    _lib.set_tuning(k, int(v))
 path = RoiPathStep(PathConfig(num_images=a.images, channels_last=not a.nchw, seed=3234), "cuda:0")
 for _ in range(a.steps):
     path.step()
