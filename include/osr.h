@@ -12,6 +12,9 @@
  *   - every call is asynchronous on the cudaStream_t passed as `stream` (void*), never syncs,
  *     never touches the default stream implicitly; all exports are re-entrant.
  *   - pointers are DEVICE pointers unless the name starts with h_ (host).
+ *   - no `device` argument: every entry point launches on the device that OWNS its output / workspace pointer
+ *     (cudaPointerGetAttributes; the caller's current device is restored on return), so tensors on cuda:1 work while
+ *     the current device is cuda:0 and from autograd worker threads; `stream` must belong to that device.
  *   - fp32 everywhere at the boundary (the reference has no AMP); boxes are xyxy absolute pixels.
  *
  * Each entry point cites the reference interface it replaces (paths relative to the
@@ -42,8 +45,8 @@ void osr_reset_launch_count(void);
 /* Kernel-variant switches for A/B measurements (bench.py, tools/): NOT part of the drop-in surface.  Each key starts
  * at its default (0 = the shipped kernel), or at the value of the environment variable OSR_TUNE_<KEY> read ONCE when
  * the library is loaded - no entry point calls getenv.  Returns the previous value, or OSR_E_ARG for an unknown key.
- *   OSR_TUNE_BWD_VARIANT   0 shared-memory accumulators (shipped) | 1 register accumulators, dense columns |
- *                          2 register accumulators, 3-bin column switch | 3 pixel-per-thread kernel
+ *   OSR_TUNE_BWD_VARIANT   0 register accumulators + packed fp32x2 FMAs (shipped) | 2 shared-memory accumulators
+ *                          (round-1 kernel) | 3 pixel-per-thread kernel
  *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records
  *   OSR_TUNE_PLN_VARIANT   0 default | see csrc/pln_fused.cu
  *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu */

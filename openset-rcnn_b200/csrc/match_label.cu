@@ -85,6 +85,7 @@ extern "C" int osr_match_label(const float* boxes, const int32_t* box_offsets, c
                                int max_boxes_per_image, float iou_threshold, int64_t background_label,
                                int32_t* matched_idx, float* matched_iou, int32_t* matched_label,
                                int64_t* matched_class, void* stream) {
+  osr::DeviceGuard device_guard(matched_idx);
   if (num_images < 0 || max_boxes_per_image < 0) return osr::fail_arg(OSR_E_ARG, "match_label: negative size");
   if (num_images == 0 || max_boxes_per_image == 0) return 0;
   if (!boxes || !box_offsets || !gt_offsets || !matched_idx || !matched_iou || !matched_label || !matched_class)

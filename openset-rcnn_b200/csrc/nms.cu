@@ -194,6 +194,7 @@ int osr_nms_segmented(const float* boxes, const float* scores, int64_t total_box
                       const int32_t* seg_len, int num_segments, int max_segment_len, float iou_threshold,
                       int presorted, int64_t* keep_idx, int32_t* keep_counts, uint8_t* keep_mask, void* workspace,
                       size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(boxes);
   if (num_segments < 0 || max_segment_len < 0 || total_boxes < 0) return osr::fail_arg(OSR_E_ARG, "nms: negative sizes");
   if (num_segments == 0) return 0;
   if (num_segments > 65535) return osr::fail_arg(OSR_E_SHAPE, "nms: more than 65535 segments in one call");

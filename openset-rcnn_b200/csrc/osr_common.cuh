@@ -47,6 +47,28 @@ inline int fail_arg(int code, const char* fmt, ...) {
     osr::count_launch();                                                                  \
   } while (0)
 
+// Launch on the device that OWNS the data: every entry point opens with `osr::DeviceGuard guard(<first device pointer>)`,
+// so a caller whose current device differs from the tensors' device (multi-GPU in one process, autograd worker threads)
+// gets correct launches and per-device function attributes; the previous current device is restored on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(const void* p) {
+    cudaPointerAttributes a;
+    if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice && cudaGetDevice(&prev) == cudaSuccess &&
+        a.device != prev) {
+      changed = cudaSetDevice(a.device) == cudaSuccess;
+    } else {
+      (void)cudaGetLastError();   // an unregistered pointer is not an error here; the entry point validates its arguments
+    }
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
   return (a + b - 1) / b;

@@ -288,6 +288,7 @@ int osr_pln_encode_gather_fwd(const float* x, const float* W, const float* bias,
 
 static int encode_launch(const float* x, const float* W, const float* bias, int R, int F, int E, float* const* outs,
                          int num_outs, int64_t row_off, float* mc, void* workspace, size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(workspace);
   float* emb = outs[0];
   if (R < 0 || F <= 0 || E <= 0) return osr::fail_arg(OSR_E_ARG, "pln_encode: bad R/F/E");
   if (F % BK != 0 || E % BN != 0)

@@ -425,6 +425,7 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
                      float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
                      float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep,
                      void* workspace, size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(emb);
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
   if (!reps || !loss_terms || !rep_inv_norm || !center_rep || !workspace ||
@@ -457,6 +458,7 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
                      const int32_t* center_rep, const float* grad_loss, int R, int D, int K, int reps_per_class,
                      float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
                      void* workspace, size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(emb);
   (void)labels;
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
@@ -493,6 +495,7 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
 
 int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, float unk_thr,
                     int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist, void* stream) {
+  osr::DeviceGuard device_guard(emb);
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
   if (R == 0) return 0;

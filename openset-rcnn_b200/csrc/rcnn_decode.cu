@@ -66,6 +66,7 @@ extern "C" int osr_rcnn_decode_score(const float* proposal_boxes, const float* d
                                      int num_images, int max_boxes_per_image, float wx, float wy, float ww, float wh,
                                      float scale_clamp, int geometric_mean, float score_thresh, float* out_boxes,
                                      float* out_scores, float* out_effective_scores, void* stream) {
+  osr::DeviceGuard device_guard(out_boxes);
   if (num_images < 0 || max_boxes_per_image < 0) return osr::fail_arg(OSR_E_ARG, "rcnn_decode: negative size");
   if (num_images == 0 || max_boxes_per_image == 0) return 0;
   if (!proposal_boxes || !deltas || !ious || !centerness || !box_offsets || !image_hw || !out_boxes || !out_scores ||

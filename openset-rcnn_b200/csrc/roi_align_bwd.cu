@@ -640,7 +640,12 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const
     const int pmv = min(lo, kP - 4);
     const bool fits = (hi < 0) || (hi <= pmv + 3);
     const float* wd = &S.sg[0][0] + (j * kCH + r) * 8;
-    S.yrow[j][r] = (hi >= 0 && fits) ? make_float4(wd[pmv], wd[pmv + 1], wd[pmv + 2], wd[pmv + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 yw = (hi >= 0 && fits) ? make_float4(wd[pmv], wd[pmv + 1], wd[pmv + 2], wd[pmv + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    S.yrow[j][r] = yw;
+    if constexpr (SM::kDenseCols) {   // row pairs, window weights interleaved for the packed FMAs
+      float* d = reinterpret_cast<float*>(&S.yrow2[j][r >> 1][0]) + (r & 1);
+      d[0] = yw.x; d[2] = yw.y; d[4] = yw.z; d[6] = yw.w;
+    }
     if (r == st * kCT) S.pm[j][st] = (unsigned char)(hi < 0 ? 254 : (fits ? pmv : 255));
   }
   __syncthreads();
@@ -655,6 +660,18 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const
         hi = x + 1;
       }
     S.run[j][k] = make_uchar2((unsigned char)lo, (unsigned char)hi);
+  }
+  if constexpr (SM::kDenseCols) {
+    for (int j = tid; j < nb; j += kCThreads) {
+      int lo = kCW, hi = 0;
+#pragma unroll
+      for (int x = 0; x < kCW; ++x)
+        if (__float_as_int(S.xcol[j][x].w) != 6) {
+          lo = min(lo, x);
+          hi = x + 1;
+        }
+      S.xr[j] = make_uchar2((unsigned char)lo, (unsigned char)hi);
+    }
   }
   if (tid >= kCThreads - kCS) {   // which RoIs put weight on each sub-tile
     const int st = tid - (kCThreads - kCS);
@@ -883,26 +900,33 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
 
 
 // =========================================================================================================
-// channels_last gather kernel, REGISTER accumulators (round 2; default).  Same decomposition as
+// channels_last gather kernel, REGISTER accumulators + packed fp32x2 FMAs (round 2).  Same decomposition as
 // roi_align_bwd_cl_kernel (CTA = (image, level, 16x16 tile); warp = 32 channels of a 128-channel slab; four 4x16
-// sub-tiles; per (sub-tile, RoI): staged grad_out block -> y fold -> x expansion, RoIs in index order), but the 4x16
-// accumulator sub-tile of a lane lives in 64 REGISTERS instead of shared memory: the x expansion is unrolled over the
-// 16 tile columns so every accumulator has a compile-time index.  That removes the accumulator read-modify-write (8 of
-// the 9 shared-memory operations per 4 pixels of the shared-memory version - the L1/shared pipe was its limiter: 142 M
-// wavefronts per launch) and the write-out staging: a finished sub-tile leaves straight from registers (lane =
-// channel: one 128-byte row segment per store instruction).
-//   MODE 0  per column: (w0, w1, w2, first bin) in one broadcast LDS.128, warp-uniform switch on the first bin (0..4),
-//           12 FFMA with compile-time register indices; RoIs that have a column in more than 3 bins (bins narrower than
-//           half a pixel) take MODE 1's body.
-//   MODE 1  per column all 7 bin weights (two LDS.128), 28 FFMA, branch-free.
+// sub-tiles; per (sub-tile, RoI): staged grad_out block -> y fold -> x expansion, RoIs in index order), but
+//   * the 4x16 accumulator sub-tile of a lane lives in 64 REGISTERS, not in shared memory: the x expansion is unrolled
+//     over the 16 tile columns so every accumulator has a compile-time index.  That removes the accumulator
+//     read-modify-write (8 of the 9 shared-memory operations per 4 pixels of the shared-memory kernel, whose limiter
+//     was the L1/shared pipe: 142 M wavefronts per launch) and the write-out staging;
+//   * rows are held as PAIRS (float2 = rows 2q, 2q+1 of a column) and all arithmetic is Blackwell's packed
+//     fma.rn.f32x2 (SASS FFMA2 with a scalar-broadcast operand): half the FMA instructions of the scalar form - the
+//     kernel is issue-bound, not FP32-pipe-bound;
+//   * the x expansion is dense over the 7 bins (14 FFMA2 per column, branch-free, weights in two broadcast LDS.128);
+//     4-column groups the RoI does not touch are skipped.  [A 3-bin form behind a per-column switch on the first bin
+//     was measured at 1.36 ms: 16 indirect branches per (sub-tile, RoI) and 5.6 k SASS instructions - instruction-
+//     fetch bound; DESIGN.md section 4.]
+//   * a finished sub-tile leaves straight from registers: lane = channel, one 128-byte row segment per store.
+// Bit-identical summation order to nothing else - but deterministic (fixed RoI order, fixed FMA order) and the exact
+// adjoint arithmetic of the forward tables.
 struct __align__(16) RegSmem {
   float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
-  float4 yrow[kCNB][kCH];
-  float4 xcol[kCNB][kCW];                   // (w(p0), w(p0+1), w(p0+2), code): code 0..4 = p0, 5 = dense, 6 = empty
+  float4 yrow[kCNB][kCH];                   // builder scratch / dense-fold bookkeeping (as in ClSmem)
+  float4 yrow2[kCNB][kCH / 2][2];           // row PAIR (2q, 2q+1): window weights interleaved (w0a,w0b,w1a,w1b | w2a,w2b,w3a,w3b)
+  float4 xcol[kCNB][kCW];                   // (w(p0), w(p0+1), w(p0+2), code) - only the code is used here (6 = empty)
   float4 xd0[kCNB][kCW], xd1[kCNB][kCW];    // all 7 bin weights of the column (w0..w3 | w4..w6, 0)
   uchar2 lohi[kCNB][kCH];
   unsigned char pm[kCNB][kCS];
   __align__(16) uchar2 run[kCNB][8];
+  uchar2 xr[kCNB];                          // [first, last + 1) tile column with weight
   BatchEntry e[kCNB];
   int2 org[kCNB];
   unsigned stmask[kCS];
@@ -911,13 +935,66 @@ struct __align__(16) RegSmem {
   static constexpr bool kDenseCols = true;
 };
 
-template <int K>
-__device__ __forceinline__ void clr_fma3(float (&acc)[kCT][kCW], int x, const float4 w, const float (&rg)[kCT][kP]) {
-#pragma unroll
-  for (int r = 0; r < kCT; ++r) acc[r][x] = fmaf(w.z, rg[r][K + 2], fmaf(w.y, rg[r][K + 1], fmaf(w.x, rg[r][K], acc[r][x])));
+// v * s + c on both halves (SASS: FFMA2 Rd, Rv.F32x2, Rs.F32, Rc.F32x2)
+__device__ __forceinline__ float2 ffma2(float2 v, float s, float2 c) {
+  unsigned long long rv, rs, rc, rd;
+  const float2 sb = make_float2(s, s);
+  rv = *reinterpret_cast<const unsigned long long*>(&v);
+  rs = *reinterpret_cast<const unsigned long long*>(&sb);
+  rc = *reinterpret_cast<const unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(rv), "l"(rs), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 v, float s) {
+  unsigned long long rv, rs, rd;
+  const float2 sb = make_float2(s, s);
+  rv = *reinterpret_cast<const unsigned long long*>(&v);
+  rs = *reinterpret_cast<const unsigned long long*>(&sb);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(rv), "l"(rs));
+  return *reinterpret_cast<float2*>(&rd);
 }
 
-template <int MODE>
+// rg2[q][b] = (rg[2q][b], rg[2q+1][b]) with rg[r][b] = sum_ph Wy[ph][row r] / count * g[ph][b]
+__device__ __forceinline__ void clr_fold_subtile(const float* gl, const RegSmem& S, int j, int st, const float* wdense,
+                                                 float2 (&rg2)[kCT / 2][kP]) {
+  const int pmv = S.pm[j][st];
+  if (pmv < 254) {   // the 4 rows share one window of 4 bins: 28 LDS, 56 FFMA2
+    const float* gp = gl + pmv * kP;
+    float g4[4][kP];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int b = 0; b < kP; ++b) g4[k][b] = gp[k * kP + b];
+#pragma unroll
+    for (int q = 0; q < kCT / 2; ++q) {
+      const float4 wa = S.yrow2[j][st * (kCT / 2) + q][0], wb = S.yrow2[j][st * (kCT / 2) + q][1];
+      const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rg2[q][b] = ffma2(w3, g4[3][b], ffma2(w2, g4[2][b], ffma2(w1, g4[1][b], fmul2(w0, g4[0][b]))));
+    }
+  } else {           // bins narrower than a pixel: dense 7-bin fold with the weights from the workspace table (rare)
+#pragma unroll
+    for (int q = 0; q < kCT / 2; ++q)
+#pragma unroll
+      for (int b = 0; b < kP; ++b) rg2[q][b] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int a = 0; a < kP; ++a) {
+      float ga[kP];
+#pragma unroll
+      for (int b = 0; b < kP; ++b) ga[b] = gl[a * kP + b];
+#pragma unroll
+      for (int q = 0; q < kCT / 2; ++q) {
+        const uchar2 l0 = S.lohi[j][st * kCT + 2 * q], l1 = S.lohi[j][st * kCT + 2 * q + 1];
+        const float2 wa = make_float2((l0.x <= l0.y) ? __ldg(wdense + (2 * q) * kP + a) : 0.f,
+                                      (l1.x <= l1.y) ? __ldg(wdense + (2 * q + 1) * kP + a) : 0.f);
+#pragma unroll
+        for (int b = 0; b < kP; ++b) rg2[q][b] = ffma2(wa, ga[b], rg2[q][b]);
+      }
+    }
+  }
+}
+
+template <int kSW>   // kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time
 __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
@@ -935,8 +1012,9 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_clr_kernel(const _
   const int nslab = ceil_div(C, kCWarps * 32);
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   float* sg = S.sg[warp];
-  const bool vec = ((lv.sW & 3) == 0) && ((lv.sH & 3) == 0) && ((lv.sN & 3) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
+  const int64_t sW = kSW > 0 ? (int64_t)kSW : lv.sW;
+  const int64_t sH = lv.sH;
+  const bool vec = ((sW & 3) == 0) && ((sH & 3) == 0) && ((lv.sN & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
   const int quad = (lane & 7) * 4, xs = lane >> 3;   // zero-fill slot: lane -> (pixel column xs + 4 q, 4 channels)
   const int ncol = min(kCW, lv.W - tx0);             // tile columns inside the map
 
@@ -959,86 +1037,91 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_clr_kernel(const _
       if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
       for (int st = 0; st < kCS; ++st) {
         unsigned m = S.stmask[st];
-        const bool any = (m != 0);
         const int ys = ty0 + st * kCT;
-        if (!any) {   // nothing lands on this sub-tile: zero fill (first batch only)
+        const int ny = min(kCT, lv.H - ys);
+        if (m == 0) {   // nothing lands on this sub-tile: zero fill (first batch only)
           if (!first) continue;
-          const int ny = min(kCT, lv.H - ys);
           if (vec) {
-            float* gp = gimg + (int64_t)ys * lv.sH + (int64_t)(tx0 + xs) * lv.sW + quad;
-            const int64_t step = 4 * lv.sW;
+            float* gp = gimg + (int64_t)ys * sH + (int64_t)(tx0 + xs) * sW + quad;
+            const int64_t step = 4 * sW;
             for (int yy = 0; yy < ny; ++yy) {
 #pragma unroll
               for (int q = 0; q < kCW / 4; ++q)
                 if (xs + 4 * q < ncol) *reinterpret_cast<float4*>(gp + q * step) = make_float4(0.f, 0.f, 0.f, 0.f);
-              gp += lv.sH;
+              gp += sH;
             }
           } else {
             for (int yy = 0; yy < ny; ++yy)
-              for (int x = 0; x < ncol; ++x) gimg[(int64_t)(ys + yy) * lv.sH + (int64_t)(tx0 + x) * lv.sW + lane] = 0.f;
+              for (int x = 0; x < ncol; ++x) gimg[(int64_t)(ys + yy) * sH + (int64_t)(tx0 + x) * sW + lane] = 0.f;
           }
           continue;
         }
-        float acc[kCT][kCW];
+        float2 acc[kCT / 2][kCW];   // acc[q][x] = rows (2q, 2q+1) of column x
 #pragma unroll
-        for (int r = 0; r < kCT; ++r)
+        for (int q = 0; q < kCT / 2; ++q)
 #pragma unroll
-          for (int x = 0; x < kCW; ++x) acc[r][x] = 0.f;
+          for (int x = 0; x < kCW; ++x) acc[q][x] = make_float2(0.f, 0.f);
         while (m != 0) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
           cp_async_wait<0>();
           __syncwarp();
-          float rg[kCT][kP];
+          float2 rg2[kCT / 2][kP];
           const int2 org = S.org[j];
           const float* wtab = p.wfull + (int64_t)S.e[j].m * kWRoi;   // dense y rows: only read when bins are narrower than a pixel
-          cl_fold_subtile(sg + lane * (kP * kP), S, j, st, wtab + (ty0 + st * kCT - org.x) * kP, rg);
+          clr_fold_subtile(sg + lane * (kP * kP), S, j, st, wtab + (ty0 + st * kCT - org.x) * kP, rg2);
           __syncwarp();   // every lane is done with the staged block: refill it while the columns are expanded
           nj = cl_next_pair(S, st, m);
           if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
-          const uint4 rb = *reinterpret_cast<const uint4*>(S.run[j]);
-          const bool dense = (MODE == 1) || (((rb.z >> 16) & 0xff) < (rb.z >> 24));   // some column sits in > 3 bins
-          if (!dense) {
-            const float4* xcol = S.xcol[j];
+          const uchar2 xr = S.xr[j];
+          const float4* xd0 = S.xd0[j];
+          const float4* xd1 = S.xd1[j];
 #pragma unroll
-            for (int x = 0; x < kCW; ++x) {
-              const float4 w = xcol[x];
-              switch (__float_as_int(w.w)) {
-                case 0: clr_fma3<0>(acc, x, w, rg); break;
-                case 1: clr_fma3<1>(acc, x, w, rg); break;
-                case 2: clr_fma3<2>(acc, x, w, rg); break;
-                case 3: clr_fma3<3>(acc, x, w, rg); break;
-                case 4: clr_fma3<4>(acc, x, w, rg); break;
-                default: break;   // 6: the RoI puts no weight on this column
-              }
-            }
-          } else {
-            const float4* xd0 = S.xd0[j];
-            const float4* xd1 = S.xd1[j];
+          for (int gq = 0; gq < kCW / 4; ++gq) {
+            if ((int)xr.x < 4 * gq + 4 && (int)xr.y > 4 * gq) {   // warp-uniform: the RoI touches this 4-column group
 #pragma unroll
-            for (int x = 0; x < kCW; ++x) {
-              const float4 a = xd0[x], b = xd1[x];
+              for (int xx = 0; xx < 4; ++xx) {
+                const int x = 4 * gq + xx;
+                const float4 a = xd0[x], b = xd1[x];
 #pragma unroll
-              for (int r = 0; r < kCT; ++r) {
-                float v = acc[r][x];
-                v = fmaf(a.x, rg[r][0], v); v = fmaf(a.y, rg[r][1], v); v = fmaf(a.z, rg[r][2], v); v = fmaf(a.w, rg[r][3], v);
-                v = fmaf(b.x, rg[r][4], v); v = fmaf(b.y, rg[r][5], v); v = fmaf(b.z, rg[r][6], v);
-                acc[r][x] = v;
+                for (int q = 0; q < kCT / 2; ++q) {
+                  float2 v = acc[q][x];
+                  v = ffma2(rg2[q][0], a.x, v); v = ffma2(rg2[q][1], a.y, v); v = ffma2(rg2[q][2], a.z, v); v = ffma2(rg2[q][3], a.w, v);
+                  v = ffma2(rg2[q][4], b.x, v); v = ffma2(rg2[q][5], b.y, v); v = ffma2(rg2[q][6], b.z, v);
+                  acc[q][x] = v;
+                }
               }
             }
           }
         }
         // write-out straight from registers: one 128-byte row segment (32 channels of one pixel) per store instruction
-        const int ny = min(kCT, lv.H - ys);
-        float* gp = gimg + (int64_t)ys * lv.sH + (int64_t)tx0 * lv.sW + lane;
+        float* gp = gimg + (int64_t)ys * sH + (int64_t)tx0 * sW + lane;
+        if (first && ncol == kCW && ny == kCT) {   // interior tile, first batch: 64 unconditional stores
 #pragma unroll
-        for (int r = 0; r < kCT; ++r) {
-          if (r < ny) {
+          for (int q = 0; q < kCT / 2; ++q) {
+            float* g0 = gp + (int64_t)(2 * q) * sH;
+            float* g1 = g0 + sH;
 #pragma unroll
             for (int x = 0; x < kCW; ++x) {
-              if (x < ncol) {
-                float* dst = gp + (int64_t)r * lv.sH + (int64_t)x * lv.sW;
-                *dst = first ? acc[r][x] : (*dst + acc[r][x]);
+              g0[(int64_t)x * sW] = acc[q][x].x;
+              g1[(int64_t)x * sW] = acc[q][x].y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < kCT / 2; ++q) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = 2 * q + h;
+              if (r < ny) {
+#pragma unroll
+                for (int x = 0; x < kCW; ++x) {
+                  if (x < ncol) {
+                    float* dst = gp + (int64_t)r * sH + (int64_t)x * sW;
+                    const float v = h ? acc[q][x].y : acc[q][x].x;
+                    *dst = first ? v : (*dst + v);
+                  }
+                }
               }
             }
           }
@@ -1090,6 +1173,7 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
                       const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
                       int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
                       void* workspace, size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(workspace);
   BwdParams p;
   int rc = fill_bwd(p, h_grad_levels, num_levels, num_images, C, P, sampling_ratio, aligned, canonical_box_size,
                     canonical_level, min_level);
@@ -1117,18 +1201,21 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   if (cl) {
     dim3 grid(p.cl_tile_base[num_levels], 1);
     const int variant = osr::tuning(osr::kTuneBwdVariant);
-    if (variant == 0) {          // shared-memory accumulators (shipped: fastest measured)
+    if (variant == 2) {          // shared-memory accumulators (round-1 kernel)
       const size_t smem = sizeof(ClSmem);
       OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       roi_align_bwd_cl_kernel<<<grid, kCThreads, smem, s>>>(p);
-    } else if (variant == 1) {   // register accumulators, dense 7-bin columns
+    } else {                     // register accumulators + packed fp32x2 FMAs (shipped)
       const size_t smem = sizeof(RegSmem);
-      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_bwd_clr_kernel<1><<<grid, kCThreads, smem, s>>>(p);
-    } else {                     // variant 2: register accumulators, 3-bin columns behind a per-column switch
-      const size_t smem = sizeof(RegSmem);
-      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_bwd_clr_kernel<0><<<grid, kCThreads, smem, s>>>(p);
+      bool sw256 = true;
+      for (int l = 0; l < num_levels; ++l) sw256 = sw256 && (p.L.lv[l].sW == 256);
+      if (sw256) {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_bwd_clr_kernel<256><<<grid, kCThreads, smem, s>>>(p);
+      } else {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_bwd_clr_kernel<0><<<grid, kCThreads, smem, s>>>(p);
+      }
     }
     OSR_LAUNCH_CHECK();
     return 0;

@@ -1161,6 +1161,7 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
                       int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
                       int min_level, float* out, int32_t* out_level, void* workspace, size_t workspace_bytes,
                       void* stream) {
+  osr::DeviceGuard device_guard(out);
   FwdParams p;
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);

@@ -411,6 +411,7 @@ int osr_rpn_select_decode(const osr_rpn_level_t* h_levels, int num_levels, int n
                           float min_box_size, const int32_t* image_hw, float* out_boxes, float* out_scores,
                           int32_t* out_level, int32_t* out_index, int32_t* out_counts, void* workspace,
                           size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(out_counts);
   RpnParams p;
   int rc = fill_params(p, h_levels, num_levels, num_images, pre_nms_topk);
   if (rc) return rc;

@@ -44,25 +44,52 @@ def shard_range(total: int, rank: int, world: int) -> range:
 
 
 def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
-    """(R, ...) -> (W*R, ...) in rank order; equal R on every rank (the sampled-RoI count is fixed)."""
+    """(R, ...) -> (W*R, ...) in rank order; R MUST be equal on every rank (see ``gather_row_counts`` /
+    ``all_gather_rows_padded`` for the ragged case)."""
     world = dist.get_world_size(group)
     out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(out, x.contiguous(), group=group)
     return out
 
 
-def _loss_on_global_rows(emb, emb_all_const, reps, labels_all, ious_all, rank, world, loss_fn, **kw):
+def gather_row_counts(n: int, device, group=None) -> list:
+    """Row count of every rank (one tiny all-gather + host read).  detectron2's ``subsample_labels`` returns fewer than
+    ``batch_size_per_image`` rows when an image has too few negatives, so R can differ between ranks."""
+    world = dist.get_world_size(group)
+    mine = torch.tensor([int(n)], dtype=torch.int64, device=device)
+    out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return [int(v) for v in out.tolist()]
+
+
+def all_gather_rows_padded(x: torch.Tensor, rmax: int, group=None, fill=0) -> torch.Tensor:
+    """(R_r, ...) -> (W*rmax, ...): every rank's rows padded with ``fill`` to ``rmax`` rows, rank r at [r*rmax, ...)."""
+    if x.shape[0] < rmax:
+        pad = torch.full((rmax - x.shape[0],) + tuple(x.shape[1:]), fill, dtype=x.dtype, device=x.device)
+        x = torch.cat((x, pad), dim=0)
+    return all_gather_rows(x, group)
+
+
+def _loss_on_global_rows(emb, emb_all_const, reps, labels_all, ious_all, rank, world, loss_fn, *, slot_rows=None,
+                         global_rows=None, **kw):
     """Global-batch loss given the gathered rows: local rows keep their autograd edge, remote rows are constants
-    (their gradient lives on their own rank)."""
+    (their gradient lives on their own rank).  ``slot_rows`` = rows per rank slot in the gathered layout (> R when the
+    ranks' counts differ: the tail of a slot is padding with label -1 / iou 0, which the loss skips), ``global_rows`` =
+    number of REAL rows over all ranks (the normaliser)."""
     R = emb.shape[0]
+    slot = R if slot_rows is None else int(slot_rows)
     emb_all = emb_all_const.clone()
-    emb_all[rank * R:(rank + 1) * R] = emb
-    return loss_fn(emb_all, reps, labels_all, ious_all, r_norm=float(max(world * R, 1)),
+    emb_all[rank * slot:rank * slot + R] = emb
+    n = world * R if global_rows is None else int(global_rows)
+    return loss_fn(emb_all, reps, labels_all, ious_all, r_norm=float(max(n, 1)),
                    center_weight=float(world), emb_grad_scale=float(world), **kw)
 
 
-def _gather_meta(labels, ious, group):
+def _gather_meta(labels, ious, group, rmax=None):
     meta = torch.stack((labels.to(torch.float32), ious.to(torch.float32)), dim=1)  # labels < 2^24: exact in fp32
+    if rmax is not None and meta.shape[0] < rmax:   # padding rows: label -1 (never foreground), iou 0
+        pad = torch.tensor([[-1.0, 0.0]], device=meta.device).expand(rmax - meta.shape[0], 2)
+        meta = torch.cat((meta, pad), dim=0)
     meta_all = all_gather_rows(meta, group)
     return meta_all[:, 0].to(torch.int64), meta_all[:, 1].contiguous()
 
@@ -136,10 +163,18 @@ def fused_gathered_pln_loss(enc: "FusedEncoderGather", x, weight, bias, reps, la
 
 
 def gathered_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tensor, ious: torch.Tensor, *,
-                      group=None, loss_fn: Optional[Callable] = None, **kw) -> torch.Tensor:
+                      group=None, loss_fn: Optional[Callable] = None, rows_per_rank=None, **kw) -> torch.Tensor:
     """Global-batch PLN loss.  ``loss_fn(emb_all, reps, labels_all, ious_all, r_norm=, center_weight=,
     emb_grad_scale=, **kw)`` defaults to the CUDA op; tests pass a CPU implementation to exercise this
-    host logic under gloo."""
+    host logic under gloo.
+
+    ``rows_per_rank``: the row count of every rank if the caller knows it (a fixed-size sampler: pass
+    ``[R] * world`` and no extra collective or host sync happens); ``None`` = exchange the counts first
+    (``gather_row_counts``).  When the counts differ (``subsample_labels`` ran out of negatives on some rank) every rank
+    pads to the largest count with label -1 / iou 0 rows, which the loss skips, and the normaliser is the number of
+    REAL rows: the result is the loss of the global batch (every RoI weighs the same).  It equals the DDP mean of the
+    reference's per-rank losses exactly when all counts are equal - with unequal counts that mean weighs the RoIs of a
+    short rank more, which no single ``r_norm`` can express."""
     if loss_fn is None:
         from .pln import pln_loss_from_emb as loss_fn  # CUDA kernels
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -147,10 +182,32 @@ def gathered_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tenso
     if world == 1:
         return loss_fn(emb, reps, labels, ious, r_norm=float(max(R, 1)), center_weight=1.0, emb_grad_scale=1.0, **kw)
     rank = dist.get_rank(group)
+    counts = list(rows_per_rank) if rows_per_rank is not None else gather_row_counts(R, emb.device, group)
+    if len(counts) != world or counts[rank] != R:
+        raise ValueError(f"gathered_pln_loss: rows_per_rank {counts} does not describe this rank ({rank}: {R} rows, world {world})")
+    rmax = max(counts)
     with torch.no_grad():
-        emb_all = all_gather_rows(emb.detach(), group)
-        labels_all, ious_all = _gather_meta(labels, ious, group)
-    return _loss_on_global_rows(emb, emb_all, reps, labels_all, ious_all, rank, world, loss_fn, **kw)
+        if min(counts) == rmax:
+            emb_all = all_gather_rows(emb.detach(), group)
+            labels_all, ious_all = _gather_meta(labels, ious, group)
+        else:
+            emb_all = all_gather_rows_padded(emb.detach(), rmax, group)
+            labels_all, ious_all = _gather_meta(labels, ious, group, rmax)
+    return _loss_on_global_rows(emb, emb_all, reps, labels_all, ious_all, rank, world, loss_fn, slot_rows=rmax,
+                                global_rows=sum(counts), **kw)
+
+
+def check_uniform_requires_grad(t: torch.Tensor, group=None) -> None:
+    """Raise on every rank if ``t.requires_grad`` differs between ranks (precondition of ``reduced_pln_loss``)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flag = torch.tensor([1.0 if t.requires_grad else 0.0], device=t.device)
+    lo, hi = flag.clone(), flag.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if float(lo) != float(hi):
+        raise RuntimeError("reduced_pln_loss: representatives.requires_grad differs between ranks; the gradient "
+                           "all-reduce in its hook would deadlock")
 
 
 class _MeanOverRanks(torch.autograd.Function):
@@ -175,7 +232,14 @@ def reduced_pln_loss(emb: torch.Tensor, reps: torch.Tensor, labels: torch.Tensor
     so  (1/W) sum_r L_r  ==  w/(W R_loc) (sum A_r + sum B_r + W C)  is the global-batch loss; the local embedding
     gradient is the per-rank one, and ``representatives.grad`` is the rank mean of the per-rank gradients (all-reduced
     in a hook, so it is identical on all ranks as with the gathered formulation).  Cost per rank: the loss kernels on
-    R_loc rows (not W R_loc) + all-reduce of 1 + K*D floats, instead of an all-gather of R_loc*D floats per peer."""
+    R_loc rows (not W R_loc) + all-reduce of 1 + K*D floats, instead of an all-gather of R_loc*D floats per peer.
+
+    Requirements (collectives inside autograd): EVERY rank must call this with ``reps.requires_grad`` set the same way
+    and must backpropagate through ``reps`` in the same step - the all-reduce of the prototype gradient runs in a tensor
+    hook, so a rank that skips the loss, freezes ``reps`` or differentiates w.r.t. ``emb`` only would leave the others
+    waiting (``check_uniform_requires_grad`` below is the cheap guard; call it once, not per step).  The row counts may
+    differ between ranks: each rank normalises by its own count, i.e. this is the DDP mean of the per-rank losses.  If
+    the module is ALSO wrapped in DDP the prototype gradient is averaged a second time, which leaves it unchanged."""
     if loss_fn is None:
         from .pln import pln_loss_from_emb as loss_fn  # CUDA kernels
     R = emb.shape[0]

@@ -44,6 +44,32 @@ class PathConfig:
     channels_last: bool = True    # FPN maps in channels_last (NHWC) memory format; False = NCHW as the reference
     encoder_impl: str = "tcgen05"   # PLN encoder: bf16 tensor cores (fp32 accumulate) | "fp32" = nn.Linear as the reference
     seed: int = 1234
+    # inference-only path (BASELINE.json configs[3]) / nominal proposal mode
+    post_nms_topk: int = 1000
+    rpn_nms_thresh: float = 0.7
+    unk_thr: float = 0.23
+    gt_per_image: int = 8
+    name: str = "cfg2"
+
+
+def make_config(name: str = "cfg2", world: int = 1, **over) -> PathConfig:
+    """BASELINE.json ``configs`` 2-5 (SURVEY.md section 8(d) "Config -> concrete sizes"); per-GPU sizes."""
+    if name == "cfg2":    # R50-FPN VOC-COCO training step, 16 images / GPU, k = 2000, 512 RoIs / image, K = 20
+        cfg = PathConfig(name=name)
+    elif name == "cfg3":  # GraspNet: 720x1280 -> 750x1333, 8 images / GPU, K = 28, cross-image PLN all-gather at N > 1
+        cfg = PathConfig(name=name, num_images=8, image_hw=(750, 1333), num_known=28, num_classes=88, alpha=0.05, beta=0.95,
+                         loss_weight=2.0, unk_thr=0.09)
+    elif name == "cfg4":  # inference-only: 32 images, k = 1000 / level, NMS -> 1000 proposals / image
+        cfg = PathConfig(name=name, num_images=32, pre_nms_topk=1000, post_nms_topk=1000)
+    elif name == "cfg5":  # stress: 1333x1333, k = 4000 / level, 1024 RoIs / image, 128 images over the GPUs
+        cfg = PathConfig(name=name, num_images=max(1, 128 // max(world, 1)), image_hw=(1333, 1333), pre_nms_topk=4000,
+                         rois_per_image=1024)
+    else:
+        raise ValueError(f"unknown config {name!r} (cfg2 | cfg3 | cfg4 | cfg5)")
+    for k, v in over.items():
+        if v is not None:
+            setattr(cfg, k, v)
+    return cfg
 
 
 class RoiPathStep:
@@ -170,7 +196,9 @@ class RoiPathStep:
             else:
                 emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
             if gather_pln:   # encoder, then NCCL all-gather of (emb, label, iou), global-batch loss
-                loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, **kw)
+                import torch.distributed as tdist
+                w = tdist.get_world_size() if tdist.is_initialized() else 1
+                loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, rows_per_rank=[emb.shape[0]] * w, **kw)
             else:            # the reference's semantics: per-rank loss
                 loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, **kw)
         g_emb, g_reps = torch.autograd.grad(loss, [emb, reps])
@@ -213,3 +241,183 @@ class RoiPathStep:
 
     def d2h_bytes(self) -> int:
         return self.h_result.numel() * 4
+
+    def alg_bytes(self) -> Dict[str, int]:
+        """Algorithmic bytes per stage of the last step (needs one step to have run)."""
+        from . import roofline
+        cfg = self.cfg
+        N = cfg.num_images
+        level_shapes = self.grid_sizes[:4]
+        M = N * cfg.rois_per_image
+        self.touched = roofline.touched_pixels(level_shapes, synth.POOL_SCALES, self.last["rois"], self.last["level"], N)
+        return {
+            "s1_proposals": N * roofline.s1_bytes_per_image(self.grid_sizes, cfg.pre_nms_topk),
+            "s3_roialign_fwd": roofline.s3_fwd_bytes(M, cfg.channels, 7, self.touched),
+            "s3_roialign_bwd": roofline.s3_bwd_bytes(M, cfg.channels, 7, N, level_shapes),
+            "s5_pln_fwd_bwd": roofline.s5_fwd_bytes(M, cfg.feat_dim, cfg.emb_dim, cfg.num_known) +
+                              roofline.s5_bwd_bytes(M, cfg.emb_dim, cfg.num_known),
+        }
+
+
+# =====================================================================================================================
+class ApiTrainStep:
+    """The same training step through the DROP-IN API, object for object what the reference's ``GeneralizedRCNN`` does
+    between the RPN head and the box head (``classification_free_rpn.py:545``, ``osrcnn_roi_heads.py:268-316``):
+
+        proposals = ClsFreeRPNProposals.predict_proposals(anchors, deltas, centerness, image_sizes)   -> List[Instances]
+        sampled   = label_and_sample_proposals(proposals, targets)       (matcher + torch.randperm on the device)
+        pooled    = ROIPooler.forward(features, [x.proposal_boxes for x in sampled])
+        _, _, l   = PLN.loss(box_features, sampled)                       (labels / ious are the MATCHER's, not synthetic)
+        backward  : PLN loss -> (embedding, prototypes);  pooled -> feature maps
+
+    ``Instances`` construction, the proposal-count host sync and the sampler's ``nonzero`` syncs are inside the step -
+    this is what ``e2e_api`` in the bench line times.  Box-head FC: a fixed (R, 1024) tensor stands in (as in
+    ``RoiPathStep``)."""
+
+    STAGES = ("s1_proposals", "s2_label_and_sample", "s3_roialign_fwd", "s5_pln_fwd_bwd", "s3_roialign_bwd")
+
+    def __init__(self, cfg: PathConfig, device="cuda:0"):
+        from .pln import PLN
+        from .proposals import ClsFreeRPNProposals
+        from .structures import Boxes, Instances
+        self.cfg = cfg
+        self.device = dev = torch.device(device)
+        N = cfg.num_images
+        ho = synth.make_head_outputs(N, cfg.image_hw, seed=cfg.seed)
+        self.image_sizes = ho.image_sizes
+        self.anchors = [Boxes(a.to(dev)) for a in ho.anchors]
+        self.deltas = [d.to(dev) for d in ho.deltas]
+        self.ctr = [c.to(dev) for c in ho.centerness]
+        self.feats = synth.make_features(N, cfg.image_hw, cfg.channels, seed=cfg.seed + 1, device=dev,
+                                         channels_last=cfg.channels_last)
+        self.rpn = ClsFreeRPNProposals(pre_nms_topk=(cfg.pre_nms_topk, cfg.pre_nms_topk),
+                                       post_nms_topk=(cfg.post_nms_topk, cfg.post_nms_topk), nms_thresh=(1.0, 1.0))
+        self.pooler = ROIPooler(7, synth.POOL_SCALES, 0, "ROIAlignV2")
+        self.pln = PLN(cfg.num_classes, cfg.num_known, cfg.feat_dim, cfg.emb_dim, "COS", 1, cfg.alpha, cfg.beta,
+                       cfg.loss_weight, "synthetic", cfg.iou_threshold, cfg.unk_thr, True, device=dev,
+                       encoder_impl=cfg.encoder_impl)
+        gtb, gtc, goff = synth.make_gt(N, cfg.gt_per_image, cfg.image_hw, num_known=cfg.num_known, seed=cfg.seed + 5, device=dev)
+        self.targets = []
+        for n in range(N):
+            t = Instances(tuple(self.image_sizes[n]))
+            t.set("gt_boxes", Boxes(gtb[n * cfg.gt_per_image:(n + 1) * cfg.gt_per_image]))
+            t.set("gt_classes", gtc[n * cfg.gt_per_image:(n + 1) * cfg.gt_per_image])
+            self.targets.append(t)
+        R = N * cfg.rois_per_image
+        g = torch.Generator(device=dev).manual_seed(cfg.seed + 3)
+        self.box_features = torch.relu(torch.randn(R, cfg.feat_dim, device=dev, generator=g))
+        self.grad_pooled = torch.randn(R, cfg.channels, 7, 7, device=dev, generator=g)
+        self.events = None
+        self.last = {}
+
+    def _mark(self, i):
+        if self.events is not None:
+            self.events[i].record()
+
+    def step(self, stage_events: bool = False):
+        from .sampling import label_and_sample_proposals
+        cfg = self.cfg
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if stage_events else None
+        self._mark(0)
+        proposals = self.rpn.train().predict_proposals(self.anchors, self.deltas, self.ctr, self.image_sizes)
+        self._mark(1)
+        sampled = label_and_sample_proposals(proposals, self.targets, num_classes=cfg.num_classes,
+                                             batch_size_per_image=cfg.rois_per_image, positive_fraction=0.25,
+                                             iou_threshold=0.5, proposal_append_gt=True)
+        self._mark(2)
+        feats = [f.requires_grad_(True) for f in self.feats]
+        pooled = self.pooler(feats, [x.proposal_boxes for x in sampled])
+        self._mark(3)
+        M = pooled.shape[0]
+        emb, rec, loss = self.pln.loss(self.box_features[:M], sampled)
+        grads = torch.autograd.grad(loss, [self.pln.representatives, self.pln.encoder.weight])
+        self._mark(4)
+        g_feats = torch.autograd.grad(pooled, feats, self.grad_pooled[:M])
+        self._mark(5)
+        self.last = dict(proposals=proposals, sampled=sampled, pooled=pooled, loss=loss, grads=grads, g_feats=g_feats)
+        return loss
+
+
+class InferencePathStep:
+    """Inference-only RoI path (BASELINE.json configs[3]) through the drop-in API:
+
+        S1  predict_proposals(mode="nominal", training=False): top-k / level + decode + per-level NMS + best post_nms_topk
+            (``classification_free_rpn.py:558-589`` with the block at ``find_top_proposals.py:112-120`` switched on - the
+            only configuration that yields "1000 post-NMS proposals / image")
+        S3  ROIPooler.forward on all kept proposals (<= 32 000 RoIs, ``osrcnn_roi_heads.py:306``)
+        S6  ROI-head post-processing: box decode + objectness + NMS(1.0) + top-1000 (``osrcnn_fast_rcnn.py:380-404``),
+            ``PLN.inference`` (``prototype_learning_network.py:189-230``), ``SoftMaxClassifier.inference`` per-class NMS
+            (``softmax_classifier.py:287-346``) - fixed tensors stand in for the box head / predictor outputs."""
+
+    STAGES = ("s1_proposals_nms", "s3_roialign_fwd", "s6_roi_head_postprocess")
+
+    def __init__(self, cfg: PathConfig, device="cuda:0"):
+        from .pln import PLN
+        from .structures import Boxes
+        self.cfg = cfg
+        self.device = dev = torch.device(device)
+        N = cfg.num_images
+        ho = synth.make_head_outputs(N, cfg.image_hw, seed=cfg.seed)
+        self.grid_sizes = ho.grid_sizes
+        self.image_sizes = ho.image_sizes
+        self.anchors = [Boxes(a.to(dev)) for a in ho.anchors]
+        self.deltas = [d.to(dev) for d in ho.deltas]
+        self.ctr = [c.to(dev) for c in ho.centerness]
+        self.feats = synth.make_features(N, cfg.image_hw, cfg.channels, seed=cfg.seed + 1, device=dev,
+                                         channels_last=cfg.channels_last)
+        self.pooler = ROIPooler(7, synth.POOL_SCALES, 0, "ROIAlignV2")
+        self.pln = PLN(cfg.num_classes, cfg.num_known, cfg.feat_dim, cfg.emb_dim, "COS", 1, cfg.alpha, cfg.beta,
+                       cfg.loss_weight, "synthetic", cfg.iou_threshold, cfg.unk_thr, True, device=dev).eval()
+        Rmax = N * cfg.post_nms_topk
+        g = torch.Generator(device=dev).manual_seed(cfg.seed + 3)
+        self.box_features = torch.relu(torch.randn(Rmax, cfg.feat_dim, device=dev, generator=g))
+        self.pred_deltas = torch.randn(Rmax, 4, device=dev, generator=g) * 0.5
+        self.pred_iou = torch.rand(Rmax, 1, device=dev, generator=g)
+        self.cls_score = torch.nn.Linear(cfg.feat_dim, cfg.num_known + 1, device=dev)
+        with torch.no_grad():   # prototypes near some embeddings so that PLN.inference yields known AND unknown detections
+            e = self.pln.encoder(self.box_features[:cfg.num_known * 37:37])
+            self.pln.representatives.copy_(e + 0.1 * torch.randn(e.shape, device=dev, generator=g) * e.norm(dim=1, keepdim=True) / 16)
+            self.cls_score.weight.mul_(20.0)
+        self.events = None
+        self.last = {}
+
+    def _mark(self, i):
+        if self.events is not None:
+            self.events[i].record()
+
+    @torch.no_grad()
+    def step(self, stage_events: bool = False):
+        from .inference import inference, softmax_classifier_inference
+        from .proposals import predict_proposals
+        cfg = self.cfg
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if stage_events else None
+        self._mark(0)
+        proposals = predict_proposals(self.anchors, self.deltas, self.ctr, self.image_sizes, nms_thresh=cfg.rpn_nms_thresh,
+                                      pre_nms_topk=cfg.pre_nms_topk, post_nms_topk=cfg.post_nms_topk, training=False,
+                                      mode="nominal")
+        self._mark(1)
+        boxes = [x.proposal_boxes for x in proposals]
+        pooled, lvl = self.pooler.forward_with_levels(self.feats, boxes)
+        self._mark(2)
+        M = pooled.shape[0]
+        fg, _ = inference((self.pred_deltas[:M], self.pred_iou[:M]), proposals, self.box_features[:M], score_thresh=0.05,
+                          nms_thresh=1.0, topk_per_image=1000)
+        fg = self.pln.inference(fg)
+        dets = softmax_classifier_inference(fg, self.cls_score, unknown_id=80, known_score_thresh=0.05, known_nms_thresh=0.5,
+                                            known_topk=50, unknown_score_thresh=0.0, unknown_nms_thresh=0.5, unknown_topk=50)
+        self._mark(3)
+        self.last = dict(proposals=proposals, pooled=pooled, level=lvl, dets=dets, M=M)
+        return pooled
+
+    def alg_bytes(self) -> Dict[str, int]:
+        from . import roofline
+        cfg = self.cfg
+        N = cfg.num_images
+        M = int(self.last["M"])
+        rois = torch.cat([torch.cat((torch.full((len(p), 1), float(n), device=self.device), p.proposal_boxes.tensor), dim=1)
+                          for n, p in enumerate(self.last["proposals"])])
+        self.touched = roofline.touched_pixels(self.grid_sizes[:4], synth.POOL_SCALES, rois, self.last["level"], N)
+        return {
+            "s1_proposals_nms": N * roofline.s1_bytes_per_image(self.grid_sizes, cfg.pre_nms_topk, nominal_post_k=cfg.post_nms_topk),
+            "s3_roialign_fwd": roofline.s3_fwd_bytes(M, cfg.channels, 7, self.touched),
+        }

@@ -81,3 +81,62 @@ def test_gathered_pln_loss_world2_gloo():
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
     assert abs(res[0][2] - res[1][2]) < 1e-9  # identical global loss on both ranks
+
+
+def _worker_ragged(rank, world, port, q):
+    """Unequal row counts per rank (detectron2's subsample_labels can return fewer than batch_size_per_image rows):
+    the gathered loss must equal the single-process loss over the concatenated batch, value and gradients."""
+    for p in (ROOT, os.path.join(ROOT, "openset-rcnn_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from osr_b200 import dist as odist, synth
+    from oracle import pln as opln
+    odist.init_from_env("gloo")
+    counts = [64, 41]
+    pis = [synth.make_pln_inputs(counts[k], seed=300 + k) for k in range(world)]
+    enc_w = synth.make_pln_inputs(4, seed=1).enc_w
+    reps0 = synth.make_pln_inputs(4, seed=1).reps
+    embs = [(p.roi_features @ enc_w.t()) for p in pis]
+    emb = embs[rank].clone().requires_grad_(True)
+    reps = reps0.clone().requires_grad_(True)
+    pi = pis[rank]
+    loss = odist.gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, loss_fn=_oracle_loss_fn, **KW)   # counts exchanged inside
+    loss.backward()
+    # single-process reference: the global batch in one call; local-row gradients scaled by W (DDP averages them)
+    e_all = torch.cat(embs).requires_grad_(True)
+    r_all = reps0.clone().requires_grad_(True)
+    ref = opln.pln_loss_from_emb(e_all, r_all, torch.cat([p.gt_classes for p in pis]), torch.cat([p.ious for p in pis]),
+                                 r_norm=float(sum(counts)), center_weight=float(world), **KW)
+    ref.backward()
+    o = sum(counts[:rank])
+    ok = (torch.allclose(loss.detach(), ref.detach(), rtol=1e-5, atol=1e-7)
+          and torch.allclose(emb.grad, world * e_all.grad[o:o + counts[rank]], rtol=1e-4, atol=1e-8)
+          and torch.allclose(reps.grad, r_all.grad, rtol=1e-4, atol=1e-8))
+    # a wrong explicit count list is rejected before any collective on the rows
+    try:
+        odist.gathered_pln_loss(emb.detach(), reps0, pi.gt_classes, pi.ious, loss_fn=_oracle_loss_fn,
+                                rows_per_rank=[counts[rank] + 1] * world, **KW)
+        ok = False
+    except ValueError:
+        pass
+    odist.check_uniform_requires_grad(reps)
+    q.put((rank, bool(ok), float(loss), float(ref)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gathered_pln_loss_unequal_rows_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40)
+    procs = [ctx.Process(target=_worker_ragged, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert abs(res[0][2] - res[1][2]) < 1e-9
