@@ -501,6 +501,7 @@ struct __align__(16) ClSmem {
 
 static_assert((kCNB * kCH + kCThreads) * 8 <= kCWarps * kGBlk, "table scratch must fit in the staging buffers");
 
+
 template <class SM>
 __device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level, int tx0, int ty0, int pos, int r1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -614,10 +615,15 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const
         }
       S.lohi[j][r] = make_uchar2((unsigned char)lo, (unsigned char)hi);
     } else {
-      S.xcol[j][r - kCH] = cl_pack3(wd);
       if constexpr (SM::kDenseCols) {   // register-accumulator kernel: all 7 bin weights of the column stay resident
         S.xd0[j][r - kCH] = make_float4(wd[0], wd[1], wd[2], wd[3]);
         S.xd1[j][r - kCH] = make_float4(wd[4], wd[5], wd[6], 0.f);
+        unsigned bits = 0;
+#pragma unroll
+        for (int b = 0; b < kP; ++b) bits |= (wd[b] != 0.f) ? (1u << b) : 0u;
+        S.xne[j][r - kCH] = (unsigned char)bits;
+      } else {
+        S.xcol[j][r - kCH] = cl_pack3(wd);
       }
     }
   }
@@ -641,49 +647,63 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const
     const bool fits = (hi < 0) || (hi <= pmv + 3);
     const float* wd = &S.sg[0][0] + (j * kCH + r) * 8;
     const float4 yw = (hi >= 0 && fits) ? make_float4(wd[pmv], wd[pmv + 1], wd[pmv + 2], wd[pmv + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    S.yrow[j][r] = yw;
     if constexpr (SM::kDenseCols) {   // row pairs, window weights interleaved for the packed FMAs
       float* d = reinterpret_cast<float*>(&S.yrow2[j][r >> 1][0]) + (r & 1);
       d[0] = yw.x; d[2] = yw.y; d[4] = yw.z; d[6] = yw.w;
+    } else {
+      S.yrow[j][r] = yw;
     }
     if (r == st * kCT) S.pm[j][st] = (unsigned char)(hi < 0 ? 254 : (fits ? pmv : 255));
   }
   __syncthreads();
-  // column runs: the first bin of a column never decreases with x, so columns of equal code are contiguous
-  for (int q = tid; q < nb * 6; q += kCThreads) {
-    const int j = q / 6, k = q - j * 6;
-    int lo = kCW, hi = 0;
-#pragma unroll
-    for (int x = 0; x < kCW; ++x)
-      if (__float_as_int(S.xcol[j][x].w) == k) {
-        lo = min(lo, x);
-        hi = x + 1;
-      }
-    S.run[j][k] = make_uchar2((unsigned char)lo, (unsigned char)hi);
-  }
   if constexpr (SM::kDenseCols) {
+    // [first, last + 1) tile column the RoI puts weight on
     for (int j = tid; j < nb; j += kCThreads) {
       int lo = kCW, hi = 0;
 #pragma unroll
       for (int x = 0; x < kCW; ++x)
-        if (__float_as_int(S.xcol[j][x].w) != 6) {
+        if (S.xne[j][x]) {
           lo = min(lo, x);
           hi = x + 1;
         }
       S.xr[j] = make_uchar2((unsigned char)lo, (unsigned char)hi);
-    }
-  }
-  if (tid >= kCThreads - kCS) {   // which RoIs put weight on each sub-tile
-    const int st = tid - (kCThreads - kCS);
-    unsigned m = 0;
-    for (int j = 0; j < nb; ++j) {
-      const bool anyr = S.pm[j][st] != 254;
-      bool anyc = false;
 #pragma unroll
-      for (int x = 0; x < kCW; ++x) anyc |= (__float_as_int(S.xcol[j][x].w) != 6);
-      if (anyr && anyc) m |= 1u << j;
+      for (int g4 = 0; g4 < kCW / 4; ++g4)
+        S.xgm[j][g4] = S.xne[j][4 * g4] | S.xne[j][4 * g4 + 1] | S.xne[j][4 * g4 + 2] | S.xne[j][4 * g4 + 3];
     }
-    S.stmask[st] = m;
+    __syncthreads();
+    if (tid >= kCThreads - kCS) {   // which RoIs put weight on each sub-tile
+      const int st = tid - (kCThreads - kCS);
+      unsigned m = 0;
+      for (int j = 0; j < nb; ++j)
+        if (S.pm[j][st] != 254 && S.xr[j].x < S.xr[j].y) m |= 1u << j;
+      S.stmask[st] = m;
+    }
+  } else {
+    // column runs: the first bin of a column never decreases with x, so columns of equal code are contiguous
+    for (int q = tid; q < nb * 6; q += kCThreads) {
+      const int j = q / 6, k = q - j * 6;
+      int lo = kCW, hi = 0;
+#pragma unroll
+      for (int x = 0; x < kCW; ++x)
+        if (__float_as_int(S.xcol[j][x].w) == k) {
+          lo = min(lo, x);
+          hi = x + 1;
+        }
+      S.run[j][k] = make_uchar2((unsigned char)lo, (unsigned char)hi);
+    }
+    if (tid >= kCThreads - kCS) {   // which RoIs put weight on each sub-tile
+      const int st = tid - (kCThreads - kCS);
+      unsigned m = 0;
+      for (int j = 0; j < nb; ++j) {
+        const bool anyr = S.pm[j][st] != 254;
+        bool anyc = false;
+#pragma unroll
+        for (int x = 0; x < kCW; ++x) anyc |= (__float_as_int(S.xcol[j][x].w) != 6);
+        if (anyr && anyc) m |= 1u << j;
+      }
+      S.stmask[st] = m;
+    }
   }
   __syncthreads();
 }
@@ -919,13 +939,12 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
 // adjoint arithmetic of the forward tables.
 struct __align__(16) RegSmem {
   float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
-  float4 yrow[kCNB][kCH];                   // builder scratch / dense-fold bookkeeping (as in ClSmem)
   float4 yrow2[kCNB][kCH / 2][2];           // row PAIR (2q, 2q+1): window weights interleaved (w0a,w0b,w1a,w1b | w2a,w2b,w3a,w3b)
-  float4 xcol[kCNB][kCW];                   // (w(p0), w(p0+1), w(p0+2), code) - only the code is used here (6 = empty)
   float4 xd0[kCNB][kCW], xd1[kCNB][kCW];    // all 7 bin weights of the column (w0..w3 | w4..w6, 0)
   uchar2 lohi[kCNB][kCH];
   unsigned char pm[kCNB][kCS];
-  __align__(16) uchar2 run[kCNB][8];
+  unsigned char xne[kCNB][kCW];             // column has weight: bit b = bin b
+  unsigned char xgm[kCNB][kCW / 4];         // OR of xne over the 4 columns of a group: bins the group's expansion must visit
   uchar2 xr[kCNB];                          // [first, last + 1) tile column with weight
   BatchEntry e[kCNB];
   int2 org[kCNB];
@@ -994,8 +1013,8 @@ __device__ __forceinline__ void clr_fold_subtile(const float* gl, const RegSmem&
   }
 }
 
-template <int kSW>   // kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time
-__global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
+template <int kSW, int kMinB>   // kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time.  kMinB: CTAs / SM the register allocation targets
+__global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
 
@@ -1073,22 +1092,27 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_clr_kernel(const _
           __syncwarp();   // every lane is done with the staged block: refill it while the columns are expanded
           nj = cl_next_pair(S, st, m);
           if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
-          const uchar2 xr = S.xr[j];
+          const unsigned gm = *reinterpret_cast<const unsigned*>(S.xgm[j]);   // 4 x 7-bit bin masks, one per 4-column group
           const float4* xd0 = S.xd0[j];
           const float4* xd1 = S.xd1[j];
 #pragma unroll
           for (int gq = 0; gq < kCW / 4; ++gq) {
-            if ((int)xr.x < 4 * gq + 4 && (int)xr.y > 4 * gq) {   // warp-uniform: the RoI touches this 4-column group
+            const unsigned bm = (gm >> (8 * gq)) & 0x7fu;
+            if (bm != 0) {   // warp-uniform: the RoI touches this 4-column group
+              float wv[4][8];
 #pragma unroll
               for (int xx = 0; xx < 4; ++xx) {
-                const int x = 4 * gq + xx;
-                const float4 a = xd0[x], b = xd1[x];
+                const float4 a = xd0[4 * gq + xx], b = xd1[4 * gq + xx];
+                wv[xx][0] = a.x; wv[xx][1] = a.y; wv[xx][2] = a.z; wv[xx][3] = a.w;
+                wv[xx][4] = b.x; wv[xx][5] = b.y; wv[xx][6] = b.z; wv[xx][7] = 0.f;
+              }
 #pragma unroll
-                for (int q = 0; q < kCT / 2; ++q) {
-                  float2 v = acc[q][x];
-                  v = ffma2(rg2[q][0], a.x, v); v = ffma2(rg2[q][1], a.y, v); v = ffma2(rg2[q][2], a.z, v); v = ffma2(rg2[q][3], a.w, v);
-                  v = ffma2(rg2[q][4], b.x, v); v = ffma2(rg2[q][5], b.y, v); v = ffma2(rg2[q][6], b.z, v);
-                  acc[q][x] = v;
+              for (int b = 0; b < kP; ++b) {
+                if (bm & (1u << b)) {   // bins none of the 4 columns sits in are skipped (typically 3-4 of 7 remain)
+#pragma unroll
+                  for (int xx = 0; xx < 4; ++xx)
+#pragma unroll
+                    for (int q = 0; q < kCT / 2; ++q) acc[q][4 * gq + xx] = ffma2(rg2[q][b], wv[xx][b], acc[q][4 * gq + xx]);
                 }
               }
             }
@@ -1209,12 +1233,15 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
       const size_t smem = sizeof(RegSmem);
       bool sw256 = true;
       for (int l = 0; l < num_levels; ++l) sw256 = sw256 && (p.L.lv[l].sW == 256);
-      if (sw256) {
-        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roi_align_bwd_clr_kernel<256><<<grid, kCThreads, smem, s>>>(p);
+      if (sw256 && variant == 1) {   // A/B: 128 registers, 4 CTAs / SM
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_bwd_clr_kernel<256, 4><<<grid, kCThreads, smem, s>>>(p);
+      } else if (sw256) {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_bwd_clr_kernel<256, 3><<<grid, kCThreads, smem, s>>>(p);
       } else {
-        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roi_align_bwd_clr_kernel<0><<<grid, kCThreads, smem, s>>>(p);
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_bwd_clr_kernel<0, 3><<<grid, kCThreads, smem, s>>>(p);
       }
     }
     OSR_LAUNCH_CHECK();

@@ -57,6 +57,24 @@ __global__ void k_ffma(float* out, int iters, float w) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+template <int NACC>
+__global__ void k_ffma2(float* out, int iters, float w) {
+  unsigned long long c[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) c[i] = (unsigned long long)i * 0x3f8000003f800000ull;
+  const float2 wb = make_float2(w, w);
+  const float2 ob = make_float2(1.f, 1.f);
+  const unsigned long long ww = *reinterpret_cast<const unsigned long long*>(&wb), one = *reinterpret_cast<const unsigned long long*>(&ob);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i]) : "l"(ww), "l"(one));
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) s ^= c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (float)(s & 0xffff);
+}
+
 template <class F>
 float time_ms(F&& launch) {
   cudaEvent_t e0, e1;
@@ -87,6 +105,9 @@ int main() {
     double ff = (double)sms * warps * iters * 16;
     printf(", \"ffma_w%d\": {\"ms\": %.3f, \"warp_ffma_per_ns_per_sm\": %.4f, \"tflops\": %.1f}", warps, ms,
            ff / (ms * 1e6) / sms, ff * 64.0 / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { k_ffma2<16><<<sms, threads>>>(out, iters, 0.999f); });
+    printf(", \"ffma2_w%d\": {\"ms\": %.3f, \"warp_ffma2_per_ns_per_sm\": %.4f, \"tflops\": %.1f}", warps, ms,
+           ff / (ms * 1e6) / sms, ff * 128.0 / (ms * 1e-3) / 1e12);
   }
   printf("}\n");
   return 0;

@@ -1,20 +1,22 @@
-"""Top stall lines of a kernel from an .ncu-rep source page (needs -lineinfo + --import-source on).
-usage: python tools/ncu_hot.py rep kernel_regex [N]"""
+"""Top SASS instructions by stall samples (with neighbours) of one kernel in an .ncu-rep.  usage: ncu_hot.py rep regex [N]"""
 import csv, io, subprocess, sys
 rep, kre = sys.argv[1], sys.argv[2]
-N = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}", "--print-source", "sass"], capture_output=True, text=True).stdout
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}", "--print-source", "sass"],
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[hi]
-ci = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[hi + 1:] if len(r) == len(hdr) and r[0] != "Address"]
-tot = sum(int(r[ci["# Samples"]] or 0) for r in body)
-inst = sum(int(r[ci["Instructions Executed"]] or 0) for r in body)
-print(f"total samples {tot}, warp instructions {inst}")
-body.sort(key=lambda r: -int(r[ci["# Samples"]] or 0))
-for r in body[:N]:
-    s = int(r[ci["# Samples"]] or 0)
-    st = {k: int(r[ci[k]] or 0) for k in ("stall_long_sb", "stall_short_sb", "stall_wait", "stall_barrier", "stall_mio", "stall_math", "stall_not_selected", "stall_lg", "stall_branch_resolving")}
-    top = sorted(st.items(), key=lambda kv: -kv[1])[:2]
-    print(f"{100*s/tot:5.1f}%  ex={int(r[ci['Instructions Executed']] or 0):>10d}  {r[ci['Source']][:90]:90s} {top}")
+hdr = None; ins = []
+for r in rows:
+    if r and "Instructions Executed" in r:
+        hdr = {h: i for i, h in enumerate(r)}; continue
+    if hdr is None or len(r) < len(hdr): continue
+    try:
+        ex = int(r[hdr["Instructions Executed"]] or 0); sm = int(r[hdr["# Samples"]] or 0)
+    except (ValueError, KeyError):
+        continue
+    ins.append((r[hdr["Address"]] if "Address" in hdr else "", r[hdr["Source"]].strip(), ex, sm))
+tot = sum(i[3] for i in ins)
+order = sorted(range(len(ins)), key=lambda i: -ins[i][3])[:N]
+for i in sorted(order):
+    a, s, ex, sm = ins[i]
+    print(f"{i:5d} {100*sm/max(tot,1):5.2f}% smp {ex:10d} ex  {s[:100]}")
