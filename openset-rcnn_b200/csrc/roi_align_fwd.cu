@@ -67,6 +67,9 @@ struct Tables {
   int own_b[kP], own_e[kP];
   int ymin, hf, shared_ok;
   float4 wt[kP][2];   // x-tap weights of each bin padded to 8 taps (NHWC kernel)
+  // the same weights for the packed-fp32x2 row loop: bins are processed as PAIRS (0,1) (2,3) (4,5) (6,-);
+  // wt2[pp][t2] = (w[2pp][2 t2], w[2pp+1][2 t2], w[2pp][2 t2 + 1], w[2pp+1][2 t2 + 1]); the missing 8th bin has zero weights
+  float4 wt2[4][4];
 };
 
 // fold one loaded value into bins PH, PH+1, PH+2 (indices are compile-time after unrolling; guards keep them in range)
@@ -601,6 +604,20 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// packed fp32x2 arithmetic (SASS FFMA2 / FMUL2): both halves of a register pair in one instruction
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2_fma_s(float2 a, float s, float2 c) { return f2_fma(a, make_float2(s, s), c); }
+
 // ---------------------------------------------------------------------------------------------------------
 // Per-RoI table records for the channels_last kernel, written once by a warp-per-RoI prep kernel so that the 256-thread
 // RoI CTAs do not spend the first quarter of their life deriving tables with 14 active threads.  A record is only
@@ -724,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   int level, img, xmin, ymin, wf, hf, tmax = 0;
   float inv_count;
   int toff[kP];
-  bool pre = false;
+  bool pre = false, early = false;
   int4 h0 = make_int4(0, 0, 0, 0);
   const float* rec = nullptr;
   if (p.rec != nullptr) {
@@ -740,10 +757,38 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     tmax = __float_as_int(h1.y);
     img = __float_as_int(h1.z);
     if (tid == 0) p.out_level[m] = level;
+    // Early issue: the first rows only need the header, so one thread arms the barriers and starts the bulk copies NOW;
+    // the table loads below (x taps, row weights: ~1 us of dependent global loads) overlap with the rows' flight time
+    // instead of preceding it.  (Footprints narrower than 8 columns zero-fill the ring first and keep the late issue.)
+    early = (wf >= 8);
+    if (early && tid == 0) {
+      const LevelDesc& lve = p.L.lv[level];
+      const float* ibase = lve.data + (int64_t)img * lve.sN;
+      for (int i = 0; i < kNhwcMaxStages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], kWarps);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const int scols_e = wf <= kNhwcWide ? max(8, (wf + 3) & ~3) : 32;
+      const int nst_e = min(kNhwcMaxStages, kNhwcRingCols / scols_e);
+      const int total_e = ceil_div(wf, scols_e) * hf;
+      for (int t = 0; t < min(nst_e, total_e); ++t) {
+        const int xc = t / hf, r = t - xc * hf;
+        const int ncols = min(scols_e, wf - xc * scols_e);
+        const uint32_t bytes = (uint32_t)(ncols * C * 4);
+        mbar_expect_tx(&full_bar[t], bytes);
+        bulk_load_1d(ring + t * (scols_e * C), ibase + ((int64_t)(ymin + r) * lve.sH + (int64_t)(xmin + xc * scols_e) * lve.sW), bytes, &full_bar[t]);
+      }
+    }
     const int4 o0 = __ldg(reinterpret_cast<const int4*>(rec) + 2), o1 = __ldg(reinterpret_cast<const int4*>(rec) + 3);
     toff[0] = o0.x * C; toff[1] = o0.y * C; toff[2] = o0.z * C; toff[3] = o0.w * C;
     toff[4] = o1.x * C; toff[5] = o1.y * C; toff[6] = o1.z * C;
     if (tid < 2 * kP) reinterpret_cast<float4*>(&T.wt[0][0])[tid] = __ldg(reinterpret_cast<const float4*>(rec + 16) + tid);
+    if (tid >= 64 && tid < 128) {   // pair-interleaved copy for the packed row loop: element (pp, t2, k) with k = (tap & 1) * 2 + (bin & 1)
+      const int e = tid - 64, pp = e >> 4, t2 = (e >> 2) & 3, k = e & 3;
+      const int pw = 2 * pp + (k & 1), tap = 2 * t2 + (k >> 1);
+      reinterpret_cast<float*>(&T.wt2[0][0])[e] = pw < kP ? __ldg(rec + 16 + pw * 8 + tap) : 0.f;
+    }
     for (int r = tid; r < hf; r += kThreads) T.rw[r] = __ldg(reinterpret_cast<const float4*>(rec + 72) + r);
   } else {
   const float* roi = p.rois + (int64_t)m * 5;
@@ -850,11 +895,17 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
       }
       T.wt[tid][0] = make_float4(w8[0], w8[1], w8[2], w8[3]);
       T.wt[tid][1] = make_float4(w8[4], w8[5], w8[6], w8[7]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) reinterpret_cast<float*>(&T.wt2[0][0])[(tid >> 1) * 16 + (q >> 1) * 4 + (q & 1) * 2 + (tid & 1)] = w8[q];
+      if (tid == kP - 1) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) reinterpret_cast<float*>(&T.wt2[0][0])[3 * 16 + (q >> 1) * 4 + (q & 1) * 2 + 1] = 0.f;
+      }
     }
   }
   const LevelDesc& lv = p.L.lv[level];
   const float* img_base = lv.data + (int64_t)img * lv.sN;
-  if (tid == 0) {
+  if (tid == 0 && !early) {
     for (int i = 0; i < kNhwcMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], kWarps);
@@ -862,11 +913,12 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
-  float acc[kP][kP];
+  // accumulators as bin PAIRS: acc2[ph][pp] = (out[ph][2 pp], out[ph][2 pp + 1]); pp = 3 carries bin 6 and a dummy
+  float2 acc2[kP][4];
 #pragma unroll
   for (int a = 0; a < kP; ++a)
 #pragma unroll
-    for (int b = 0; b < kP; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < 4; ++b) acc2[a][b] = make_float2(0.f, 0.f);
 
   // stage geometry: a stage holds one footprint row (chunk).  Narrow RoIs get more, smaller stages (deeper prefetch),
   // RoIs up to 48 pixels wide are still staged as whole rows, wider ones in 32-column chunks.
@@ -888,8 +940,8 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic zero-fill before async-proxy bulk writes
   }
   __syncthreads();
-  // producer prologue
-  if (warp == 0) {
+  // producer prologue (already issued by thread 0 when `early`)
+  if (warp == 0 && !early) {
     if (elect_one()) {
       for (int t = 0; t < min(nstages, total); ++t) {
         const int xc = t / hf, r = t - xc * hf;
@@ -914,52 +966,45 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     mbar_wait(&full_bar[slot], parity);
     const float* row = ring + slot * stage_floats + c;
     const int x_lo = xmin + xc * scols, x_hi = min(xmin + wf, x_lo + scols);
-    // x contraction of this row (chunk): U[pw] = sum_x Wx[pw][x] * row[x][c]
-    float U[kP];
+    // x contraction of this row (chunk): U[pw] = sum_x Wx[pw][x] * row[x][c], two bins per packed FMA
+    float2 U2[4];
     if (fast_taps) {
       const float* rowc = ring + slot * stage_floats + min(c, C - 1);
+#define OSR_NHWC_TAPS(NT2)                                                                                         \
+  _Pragma("unroll") for (int pp = 0; pp < 3; ++pp) {                                                                \
+    const float* ra = rowc + toff[2 * pp];                                                                          \
+    const float* rb = rowc + toff[2 * pp + 1];                                                                      \
+    float2 u = make_float2(0.f, 0.f);                                                                               \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+      const float4 w = T.wt2[pp][t2];                                                                               \
+      const float2 d0 = make_float2(ra[(2 * t2) * C], rb[(2 * t2) * C]);                                            \
+      const float2 d1 = make_float2(ra[(2 * t2 + 1) * C], rb[(2 * t2 + 1) * C]);                                    \
+      u = (t2 == 0) ? f2_mul(d0, make_float2(w.x, w.y)) : f2_fma(d0, make_float2(w.x, w.y), u);                     \
+      u = f2_fma(d1, make_float2(w.z, w.w), u);                                                                     \
+    }                                                                                                               \
+    U2[pp] = u;                                                                                                     \
+  }                                                                                                                 \
+  {                                                                                                                 \
+    const float* ra = rowc + toff[kP - 1];                                                                          \
+    float u = 0.f;                                                                                                  \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+      const float4 w = T.wt2[3][t2];                                                                                \
+      u = fmaf(w.x, ra[(2 * t2) * C], u);                                                                           \
+      u = fmaf(w.z, ra[(2 * t2 + 1) * C], u);                                                                       \
+    }                                                                                                               \
+    U2[3] = make_float2(u, 0.f);                                                                                    \
+  }
       if (tmax <= 4) {          // CTA-uniform: widest bin of this RoI spans <= 4 pixels
-#pragma unroll
-        for (int pw = 0; pw < kP; ++pw) {
-          const float* rp = rowc + toff[pw];
-          const float4 wa = T.wt[pw][0];
-          float u = wa.x * rp[0];
-          u = fmaf(wa.y, rp[1 * C], u);
-          u = fmaf(wa.z, rp[2 * C], u);
-          u = fmaf(wa.w, rp[3 * C], u);
-          U[pw] = u;
-        }
+        OSR_NHWC_TAPS(2)
       } else if (tmax <= 6) {
-#pragma unroll
-        for (int pw = 0; pw < kP; ++pw) {
-          const float* rp = rowc + toff[pw];
-          const float4 wa = T.wt[pw][0];
-          const float2 wb = *reinterpret_cast<const float2*>(&T.wt[pw][1]);
-          float u = wa.x * rp[0];
-          u = fmaf(wa.y, rp[1 * C], u);
-          u = fmaf(wa.z, rp[2 * C], u);
-          u = fmaf(wa.w, rp[3 * C], u);
-          u = fmaf(wb.x, rp[4 * C], u);
-          u = fmaf(wb.y, rp[5 * C], u);
-          U[pw] = u;
-        }
+        OSR_NHWC_TAPS(3)
       } else {
-#pragma unroll
-        for (int pw = 0; pw < kP; ++pw) {
-          const float* rp = rowc + toff[pw];
-          const float4 wa = T.wt[pw][0], wb = T.wt[pw][1];
-          float u = wa.x * rp[0];
-          u = fmaf(wa.y, rp[1 * C], u);
-          u = fmaf(wa.z, rp[2 * C], u);
-          u = fmaf(wa.w, rp[3 * C], u);
-          u = fmaf(wb.x, rp[4 * C], u);
-          u = fmaf(wb.y, rp[5 * C], u);
-          u = fmaf(wb.z, rp[6 * C], u);
-          u = fmaf(wb.w, rp[7 * C], u);
-          U[pw] = u;
-        }
+        OSR_NHWC_TAPS(4)
       }
+#undef OSR_NHWC_TAPS
     } else {
+      float U[kP + 1];
+      U[kP] = 0.f;
 #pragma unroll
       for (int pw = 0; pw < kP; ++pw) {
         float u = 0.f;
@@ -968,6 +1013,8 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
         for (int q = q0; q < q1; ++q) u = fmaf(T.wx[pw * kRB + q], cin ? row[(xb + q - x_lo) * C] : 0.f, u);
         U[pw] = u;
       }
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp) U2[pp] = make_float2(U[2 * pp], U[2 * pp + 1]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);
@@ -988,10 +1035,10 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     switch (__float_as_int(w.w)) {
 #define OSR_NHWC_CASE(PH)                                                                                   \
   case PH:                                                                                                  \
-    _Pragma("unroll") for (int pw = 0; pw < kP; ++pw) {                                                     \
-      acc[PH][pw] = fmaf(w.x, U[pw], acc[PH][pw]);                                                          \
-      if (PH + 1 < kP) acc[PH + 1 < kP ? PH + 1 : 0][pw] = fmaf(w.y, U[pw], acc[PH + 1 < kP ? PH + 1 : 0][pw]); \
-      if (PH + 2 < kP) acc[PH + 2 < kP ? PH + 2 : 0][pw] = fmaf(w.z, U[pw], acc[PH + 2 < kP ? PH + 2 : 0][pw]); \
+    _Pragma("unroll") for (int pp = 0; pp < 4; ++pp) {                                                      \
+      acc2[PH][pp] = f2_fma_s(U2[pp], w.x, acc2[PH][pp]);                                                   \
+      if (PH + 1 < kP) acc2[PH + 1 < kP ? PH + 1 : 0][pp] = f2_fma_s(U2[pp], w.y, acc2[PH + 1 < kP ? PH + 1 : 0][pp]); \
+      if (PH + 2 < kP) acc2[PH + 2 < kP ? PH + 2 : 0][pp] = f2_fma_s(U2[pp], w.z, acc2[PH + 2 < kP ? PH + 2 : 0][pp]); \
     }                                                                                                       \
     break;
       OSR_NHWC_CASE(0) OSR_NHWC_CASE(1) OSR_NHWC_CASE(2) OSR_NHWC_CASE(3) OSR_NHWC_CASE(4) OSR_NHWC_CASE(5) OSR_NHWC_CASE(6)
@@ -1003,7 +1050,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
           const int rr = y - T.yb[ph];
           const float wy = (rr >= 0 && rr < T.ny[ph]) ? T.wy[ph * kRB + rr] : 0.f;
 #pragma unroll
-          for (int pw = 0; pw < kP; ++pw) acc[ph][pw] = fmaf(wy, U[pw], acc[ph][pw]);
+          for (int pp = 0; pp < 4; ++pp) acc2[ph][pp] = f2_fma_s(U2[pp], wy, acc2[ph][pp]);
         }
         break;
       }
@@ -1020,7 +1067,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
 #pragma unroll
     for (int a = 0; a < kP; ++a)
 #pragma unroll
-      for (int b = 0; b < kP; ++b) o[a * kP + b] = acc[a][b] * inv_count;
+      for (int b = 0; b < kP; ++b) o[a * kP + b] = ((b & 1) ? acc2[a][b >> 1].y : acc2[a][b >> 1].x) * inv_count;
   }
   __syncthreads();
   const int n4 = (C * kP * kP) >> 2;
