@@ -35,7 +35,13 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "roi_path_images_per_sec"
 UNIT = "images/s"
-WORKLOAD = "cfg2_R50FPN_train_16img_per_gpu_800x1333_k2000_512rois_K20"
+WORKLOADS = {
+    "cfg2": "cfg2_R50FPN_train_16img_per_gpu_800x1333_k2000_512rois_K20",
+    "cfg3": "cfg3_GraspNet_train_8img_per_gpu_750x1333_k2000_512rois_K28_gathered_PLN",
+    "cfg4": "cfg4_inference_32img_per_gpu_800x1333_k1000_nms_to_1000_proposals",
+    "cfg5": "cfg5_stress_128img_total_1333x1333_k4000_1024rois",
+}
+WORKLOAD = WORKLOADS["cfg2"]
 
 
 def measured_peak():
@@ -296,12 +302,17 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.lib()  # fail loudly if the extension is missing
-    cfg = PathConfig(channels_last=not args.nchw, seed=1234 + 1000 * 2 + rank)
+    from osr_b200.pipeline import ApiTrainStep, InferencePathStep, make_config
+    cfg = make_config(args.config, world, channels_last=not args.nchw, seed=1234 + 1000 * int(args.config[3:]) + rank,
+                      num_images=args.images)
     N = cfg.num_images
-    path = RoiPathStep(cfg, dev)
+    infer = args.config == "cfg4"
+    gather_headline = (args.config == "cfg3") and world > 1   # cfg 3 IS the gathered-PLN configuration
+    path = InferencePathStep(cfg, dev) if infer else RoiPathStep(cfg, dev)
+    step_kw = {"gather_pln": True} if gather_headline else {}
 
     for _ in range(max(args.warmup, 3)):
-        path.step()
+        path.step(**step_kw)
     torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -310,20 +321,57 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize(dev)
     if sampler:
         sampler.start()
+    # ---- eager launches: K timed steps with CUDA events between the stages --------------------------------------------
     _lib.reset_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        path.step(stage_events=True)
+        path.step(stage_events=True, **step_kw)
         stage_events.append(path.events)
     ev1.record()
     torch.cuda.synchronize(dev)
     launches = _lib.launch_count()
-    clocks = sampler.stop() if sampler else None
     barrier(world)
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1), world, dev)
-    ms_step = ms_total / args.steps
+    eager_ms = max_over_ranks(ev0.elapsed_time(ev1), world, dev) / args.steps
+    eager = {"ms_per_step": eager_ms, "value": world * N * 1e3 / eager_ms}
+    ms_step = eager_ms
+
+    # ---- one CUDA graph replay per step: the fixed-shape device-resident step is captured once; the
+    # headline is the graph-launched step when the capture succeeds, the eager one otherwise ------------------------------
+    graph, graph_err = None, None
+    if not args.no_graph and not infer and not gather_headline:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                path.step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                path.step()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            g1.record()
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            ms_step = max_over_ranks(g0.elapsed_time(g1), world, dev) / args.steps
+        except Exception as e:  # noqa: BLE001 - keep the eager number, say so in the line
+            graph, graph_err = None, repr(e)[:300]
+            try:
+                torch.cuda.synchronize(dev)
+            except Exception:  # noqa: BLE001
+                pass
+    clocks = sampler.stop() if sampler else None
     value = world * N * 1e3 / ms_step
+    if graph is None:
+        eager = None
 
     # per-stage device time (CUDA events on the launch stream, averaged over the timed steps)
     stages = {}
@@ -332,24 +380,16 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = measured_peak()
-    level_shapes = path.grid_sizes[:4]
-    M = N * cfg.rois_per_image
-    U = roofline.touched_pixels(level_shapes, synth.POOL_SCALES, path.last["rois"], path.last["level"], N)
-    alg = {
-        "s1_proposals": N * roofline.s1_bytes_per_image(path.grid_sizes, cfg.pre_nms_topk),
-        "s3_roialign_fwd": roofline.s3_fwd_bytes(M, cfg.channels, 7, U),
-        "s3_roialign_bwd": roofline.s3_bwd_bytes(M, cfg.channels, 7, N, level_shapes),
-        "s5_pln_fwd_bwd": roofline.s5_fwd_bytes(M, cfg.feat_dim, cfg.emb_dim, cfg.num_known) +
-                          roofline.s5_bwd_bytes(M, cfg.emb_dim, cfg.num_known),
-    }
+    alg = path.alg_bytes()
+    U = path.touched
     per_stage = {k: {"ms": stages[k], "alg_bytes": alg[k], "gbs": alg[k] / (stages[k] * 1e-3) / 1e9,
                      "frac": alg[k] / (stages[k] * 1e-3) / 1e9 / peak} for k in alg}
     dom = max(alg, key=lambda k: stages[k])
     path_bytes = sum(alg.values())
     path_ms = sum(stages[k] for k in alg)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic.json")
-    if cfg.channels_last and os.path.exists(tpath):   # ncu capture of the same workload (per launch), committed
+    tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    if cfg.channels_last and args.config == "cfg2" and os.path.exists(tpath):   # ncu capture of the same workload (per launch), committed
         with open(tpath) as f:
             tj = json.load(f)
         if dom in tj:
@@ -363,7 +403,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- the library kernels the reference runs on a GPU, same inputs, same process ---------------------
     gbase = None
-    if rank == 0 and not args.no_gpu_baseline:
+    if rank == 0 and not args.no_gpu_baseline and not infer:
         try:
             gbase = gpu_baseline(path, cfg)
         except Exception as e:  # noqa: BLE001 - a side measurement must never take the headline line down
@@ -372,7 +412,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- the other feature layout, short run (same inputs, same code path selection rules) --------------
     alt = None
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not infer and not args.quick:
         alt_feats = [f.contiguous() if cfg.channels_last else f.contiguous(memory_format=torch.channels_last) for f in path.feats]
         for _ in range(3):
             path.step(feats=alt_feats)
@@ -390,7 +430,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- north-star variant at N > 1: PLN loss over the global batch (NCCL all-gather of the embeddings) ---------
     gathered = None
-    if world > 1:
+    if world > 1 and not infer and not gather_headline:
         try:
             for _ in range(3):
                 path.step(gather_pln=True)
@@ -419,6 +459,44 @@ def run_ours(args, rank, local_rank, world):
             gathered = {"error": repr(e)}
         barrier(world)
 
+    # ---- the same training step through the drop-in API objects (Instances, matcher labels feeding PLN) -------------
+    api = None
+    if not infer and not args.quick:
+        try:
+            del graph
+            api_path = ApiTrainStep(cfg, dev)
+            for _ in range(3):
+                api_path.step()
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            api_events = []
+            a0.record()
+            for _ in range(10):
+                api_path.step(stage_events=True)
+                api_events.append(api_path.events)
+            a1.record()
+            torch.cuda.synchronize(dev)
+            api_ms = max_over_ranks(a0.elapsed_time(a1), world, dev) / 10
+            api = {"ms_per_step": api_ms, "value": world * N * 1e3 / api_ms, "steps": 10,
+                   "stage_ms": {name: sum(ev[i].elapsed_time(ev[i + 1]) for ev in api_events) / len(api_events)
+                                for i, name in enumerate(api_path.STAGES)},
+                   "sampled_rois": int(api_path.last["pooled"].shape[0]),
+                   "note": "predict_proposals -> label_and_sample_proposals (matcher + device randperm) -> ROIPooler.forward("
+                           "list, list) -> PLN.loss(box_features, sampled) with the matcher's labels / IoUs -> backward; "
+                           "Instances construction, the proposal-count sync and the sampler's nonzero syncs are inside"}
+            del api_path
+        except Exception as e:  # noqa: BLE001
+            api = {"error": repr(e)}
+        barrier(world)
+
+    if infer or args.quick:
+        if rank == 0:
+            line = _line(args, world, cfg, N, value, ms_step, clocks, None, launches, roof, stages, None, None, None, None,
+                         eager, graph_err, api)
+            print(json.dumps(line), flush=True)
+        return
+
     # ---- end to end: inputs start in pinned host memory every step ----------------------------------
     del path
     torch.cuda.empty_cache()
@@ -446,26 +524,48 @@ def run_ours(args, rank, local_rank, world):
 
     if rank != 0:
         return
+    line = _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stages, alt, gbase, gathered,
+                 cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None, eager, graph_err, api)
+    print(json.dumps(line), flush=True)
+
+
+def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stages, alt, gbase, gathered, cpu, eager,
+          graph_err, api):
+    infer = args.config == "cfg4"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pln_encoder": "bf16 tcgen05, fp32 accumulate (all other arithmetic fp32)", "images_per_gpu": N, "global_batch": world * N, "image_hw": list(cfg.image_hw),
+        "config": {"workload": WORKLOADS[args.config],
+                   "pln_encoder": "bf16 tcgen05, fp32 accumulate (all other arithmetic fp32)",
+                   "images_per_gpu": N, "global_batch": world * N, "image_hw": list(cfg.image_hw),
                    "pre_nms_topk_per_level": cfg.pre_nms_topk, "rois_per_image": cfg.rois_per_image,
                    "feature_layout": "channels_last" if cfg.channels_last else "NCHW",
-                   "proposal_mode": "as_shipped (find_top_proposals.py:112-120 commented out)",
-                   "l2": "inputs larger than L2 (FPN maps 1.46 GB + 0.41 GB pooled grads per step vs 126 MB L2)",
-                   "timed_stages": "S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, S5 encoder+PLN loss "
-                                   "fwd/bwd, S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))",
+                   "proposal_mode": ("nominal (per-level NMS %.2f + best %d per image: the block at find_top_proposals.py:112-120 "
+                                     "switched on)" % (cfg.rpn_nms_thresh, cfg.post_nms_topk)) if infer else
+                                    "as_shipped (find_top_proposals.py:112-120 commented out)",
+                   "l2": "inputs larger than L2 (FPN maps %.2f GB per step vs 126 MB L2)" % (N * 0.0914),
+                   "launch": "one CUDA graph replay per step" if (eager is not None) else "eager launches",
+                   "timed_stages": ("S1 proposals + NMS, S3 ROIAlign fwd, S6 ROI-head post-processing (decode + NMS + PLN.inference + "
+                                    "classifier NMS); box head / predictor outputs are fixed tensors") if infer else
+                                   ("S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, "
+                                    "S5 encoder+PLN loss fwd/bwd" + (" over the GLOBAL batch (fused encoder + all-gather)" if (args.config == "cfg3" and world > 1) else "") +
+                                    ", S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))"),
                    "parallelism": f"dp{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
         "stage_ms": stages, "alt_layout": alt, "gpu_baseline": gbase,
     }
+    if eager is not None:
+        line["eager"] = eager
+    if graph_err is not None:
+        line["cuda_graph_error"] = graph_err
+    if api is not None:
+        line["api_step"] = api
     if gathered is not None:
         line["gathered_pln"] = gathered
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg)
-    print(json.dumps(line), flush=True)
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    return line
 
 
 def main():
@@ -479,6 +579,11 @@ def main():
                          "'coalesced NHWC reads'; what a channels_last backbone emits); the other layout is reported under 'alt_layout'")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json configs[1..4]; cfg2 is the headline (the driver's default)")
+    ap.add_argument("--images", type=int, default=None, help="images per GPU (default: the config's)")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph replay per step")
+    ap.add_argument("--quick", action="store_true", help="device-resident measurement only (skip alt layout, API step, e2e, baselines)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 from . import _lib, synth
 from .poolers import ROIPooler
-from .pln import pln_encode_tc, pln_loss_from_emb
+from .pln import pln_encode_tc, pln_loss_from_emb, pln_loss_fwd_bwd
 from .proposals import rpn_select_decode
 from .sampling import match_proposals
 from .dist import FusedEncoderGather, fused_gathered_pln_loss, gathered_pln_loss
@@ -169,13 +169,14 @@ class RoiPathStep:
         boxes = sel.boxes.view(-1, 4).index_select(0, self.sample_idx)
         rois = torch.cat((self.img_col, boxes), dim=1)
         self._mark(2)
-        # S3 forward
-        feats_g = [f.requires_grad_(True) for f in feats]
-        pooled, lvl = self.pooler.pool_rois(feats_g, rois, self.roi_offsets)
+        # S3 forward (kernels are called directly, without autograd: no engine thread hop, capturable in a CUDA graph;
+        # tests/test_gpu_pipeline.py checks this path against the autograd one)
+        with torch.no_grad():
+            pooled, lvl = self.pooler.pool_rois([f.detach() for f in feats], rois, self.roi_offsets)
         self._mark(3)
-        # S5: encoder (nn.Linear) + prototype loss forward + backward to (emb, representatives)
+        # S5: encoder + prototype loss forward + backward to (emb, representatives)
         pi = self.pln
-        reps = pi.reps.requires_grad_(True)
+        reps = pi.reps
         kw = dict(num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,
                   iou_threshold=cfg.iou_threshold)
         if gather_pln and cfg.encoder_impl == "tcgen05":
@@ -187,24 +188,30 @@ class RoiPathStep:
                 except Exception as e:  # noqa: BLE001 - no symmetric memory / P2P on this box: NCCL all-gather instead
                     self._fused_enc = False
                     self.fused_gather_error = repr(e)
-        if gather_pln and cfg.encoder_impl == "tcgen05" and self._fused_enc:
-            loss, emb = fused_gathered_pln_loss(self._fused_enc, pi.roi_features, pi.enc_w, pi.enc_b, reps,
-                                                pi.gt_classes, pi.ious, **kw)
-        else:
-            if cfg.encoder_impl == "tcgen05":
-                emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+        if gather_pln:
+            reps = reps.requires_grad_(True)
+            if cfg.encoder_impl == "tcgen05" and self._fused_enc:
+                loss, emb = fused_gathered_pln_loss(self._fused_enc, pi.roi_features, pi.enc_w, pi.enc_b, reps,
+                                                    pi.gt_classes, pi.ious, **kw)
             else:
-                emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
-            if gather_pln:   # encoder, then NCCL all-gather of (emb, label, iou), global-batch loss
+                if cfg.encoder_impl == "tcgen05":
+                    emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+                else:
+                    emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
                 import torch.distributed as tdist
                 w = tdist.get_world_size() if tdist.is_initialized() else 1
                 loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, rows_per_rank=[emb.shape[0]] * w, **kw)
-            else:            # the reference's semantics: per-rank loss
-                loss = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, **kw)
-        g_emb, g_reps = torch.autograd.grad(loss, [emb, reps])
+            g_emb, g_reps = torch.autograd.grad(loss, [emb, reps])
+        else:            # the reference's semantics: per-rank loss
+            with torch.no_grad():
+                if cfg.encoder_impl == "tcgen05":
+                    emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b)
+                else:
+                    emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b)
+            loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
         self._mark(4)
         # S3 backward
-        g_feats = torch.autograd.grad(pooled, feats_g, self.grad_pooled)
+        g_feats = self.pooler.backward_rois(self.grad_pooled, feats, rois, self.roi_offsets)
         self._mark(5)
         self.last = dict(sel=sel, match=match, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
                          g_feats=g_feats)

@@ -23,58 +23,86 @@ from . import _lib
 from .structures import Instances
 
 
+def _pln_fwd(emb, reps, labels, ious, cfg):
+    """osr_pln_loss_fwd: returns (loss scalar tensor, saved tuple for ``_pln_bwd``)."""
+    (K, rpc, alpha, beta, loss_weight, iou_thr, r_norm, center_weight, emb_grad_scale) = cfg
+    lib = _lib.lib()
+    _lib.require_cuda(emb, reps, labels, ious)
+    emb_c = emb.contiguous().float()
+    reps_c = reps.contiguous().float()
+    labels_c = labels.contiguous().to(torch.int64)
+    ious_c = ious.contiguous().float()
+    R, D = emb_c.shape
+    dev = emb_c.device
+    Kr = K * rpc
+    assert reps_c.shape == (Kr, D)
+    terms = torch.empty(4, dtype=torch.float32, device=dev)
+    emb_inv = torch.empty(R, dtype=torch.float32, device=dev)
+    rep_inv = torch.empty(Kr, dtype=torch.float32, device=dev)
+    intra = torch.empty(R, dtype=torch.int32, device=dev)
+    inter = torch.empty(R, dtype=torch.int32, device=dev)
+    center = torch.empty(Kr, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
+    rn = float(R) if r_norm is None else float(r_norm)
+    rc = lib.osr_pln_loss_fwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(),
+                              R, D, K, rpc, alpha, beta, loss_weight, iou_thr, rn, center_weight,
+                              terms.data_ptr(), emb_inv.data_ptr(), rep_inv.data_ptr(), intra.data_ptr(),
+                              inter.data_ptr(), center.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _lib.stream_ptr(dev))
+    _lib.check(rc, "osr_pln_loss_fwd")
+    saved = (emb_c, reps_c, labels_c, emb_inv, rep_inv, intra, inter, center)
+    return terms[0], saved, (K, rpc, loss_weight, rn, center_weight, emb_grad_scale)
+
+
+def _pln_bwd(saved, bcfg, grad_loss):
+    """osr_pln_loss_bwd (closed form): returns (grad_emb, grad_reps)."""
+    lib = _lib.lib()
+    emb, reps, labels, emb_inv, rep_inv, intra, inter, center = saved
+    K, rpc, loss_weight, rn, center_weight, emb_grad_scale = bcfg
+    R, D = emb.shape
+    dev = emb.device
+    gl = grad_loss.reshape(1).contiguous().float()
+    grad_emb = torch.empty_like(emb)
+    grad_reps = torch.empty_like(reps)
+    ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
+    rc = lib.osr_pln_loss_bwd(emb.data_ptr(), reps.data_ptr(), labels.data_ptr(), emb_inv.data_ptr(),
+                              rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
+                              gl.data_ptr(), R, D, K, rpc, loss_weight, rn, center_weight,
+                              grad_emb.data_ptr(), grad_reps.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _lib.stream_ptr(dev))
+    _lib.check(rc, "osr_pln_loss_bwd")
+    if emb_grad_scale != 1.0:
+        grad_emb = grad_emb * emb_grad_scale
+    return grad_emb, grad_reps
+
+
 class _PlnLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, reps, labels, ious, cfg):
-        (K, rpc, alpha, beta, loss_weight, iou_thr, r_norm, center_weight, emb_grad_scale) = cfg
-        lib = _lib.lib()
-        _lib.require_cuda(emb, reps, labels, ious)
-        emb_c = emb.contiguous().float()
-        reps_c = reps.contiguous().float()
-        labels_c = labels.contiguous().to(torch.int64)
-        ious_c = ious.contiguous().float()
-        R, D = emb_c.shape
-        dev = emb_c.device
-        Kr = K * rpc
-        assert reps_c.shape == (Kr, D)
-        terms = torch.empty(4, dtype=torch.float32, device=dev)
-        emb_inv = torch.empty(R, dtype=torch.float32, device=dev)
-        rep_inv = torch.empty(Kr, dtype=torch.float32, device=dev)
-        intra = torch.empty(R, dtype=torch.int32, device=dev)
-        inter = torch.empty(R, dtype=torch.int32, device=dev)
-        center = torch.empty(Kr, dtype=torch.int32, device=dev)
-        ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
-        rn = float(R) if r_norm is None else float(r_norm)
-        rc = lib.osr_pln_loss_fwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(),
-                                  R, D, K, rpc, alpha, beta, loss_weight, iou_thr, rn, center_weight,
-                                  terms.data_ptr(), emb_inv.data_ptr(), rep_inv.data_ptr(), intra.data_ptr(),
-                                  inter.data_ptr(), center.data_ptr(), ws.data_ptr(), ws.numel(),
-                                  _lib.stream_ptr(dev))
-        _lib.check(rc, "osr_pln_loss_fwd")
-        ctx.save_for_backward(emb_c, reps_c, labels_c, emb_inv, rep_inv, intra, inter, center)
-        ctx.cfg = (K, rpc, loss_weight, rn, center_weight, emb_grad_scale)
-        return terms[0]
+        loss, saved, bcfg = _pln_fwd(emb, reps, labels, ious, cfg)
+        ctx.save_for_backward(*saved)
+        ctx.cfg = bcfg
+        return loss
 
     @staticmethod
     def backward(ctx, grad_loss):
-        lib = _lib.lib()
-        emb, reps, labels, emb_inv, rep_inv, intra, inter, center = ctx.saved_tensors
-        K, rpc, loss_weight, rn, center_weight, emb_grad_scale = ctx.cfg
-        R, D = emb.shape
-        dev = emb.device
-        gl = grad_loss.reshape(1).contiguous().float()
-        grad_emb = torch.empty_like(emb)
-        grad_reps = torch.empty_like(reps)
-        ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
-        rc = lib.osr_pln_loss_bwd(emb.data_ptr(), reps.data_ptr(), labels.data_ptr(), emb_inv.data_ptr(),
-                                  rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
-                                  gl.data_ptr(), R, D, K, rpc, loss_weight, rn, center_weight,
-                                  grad_emb.data_ptr(), grad_reps.data_ptr(), ws.data_ptr(), ws.numel(),
-                                  _lib.stream_ptr(dev))
-        _lib.check(rc, "osr_pln_loss_bwd")
-        if emb_grad_scale != 1.0:
-            grad_emb = grad_emb * emb_grad_scale
+        grad_emb, grad_reps = _pln_bwd(ctx.saved_tensors, ctx.cfg, grad_loss)
         return grad_emb, grad_reps, None, None, None
+
+
+def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_per_class: int = 1, alpha: float = 0.1,
+                     beta: float = 0.9, loss_weight: float = 0.5, iou_threshold: float = 0.5, r_norm: Optional[float] = None,
+                     center_weight: float = 1.0, emb_grad_scale: float = 1.0, grad_loss: Optional[torch.Tensor] = None):
+    """Loss and its closed-form gradients in one call, WITHOUT autograd: ``(loss, d loss / d emb, d loss / d reps)``.
+    Same kernels as ``pln_loss_from_emb`` + ``backward()``; used by the device-resident training step (no autograd engine
+    hop, capturable in a CUDA graph)."""
+    cfg = (int(num_known_classes), int(reps_per_class), float(alpha), float(beta), float(loss_weight),
+           float(iou_threshold), r_norm, float(center_weight), float(emb_grad_scale))
+    with torch.no_grad():
+        loss, saved, bcfg = _pln_fwd(emb, reps, labels, ious, cfg)
+        gl = torch.ones(1, dtype=torch.float32, device=loss.device) if grad_loss is None else grad_loss
+        g_emb, g_reps = _pln_bwd(saved, bcfg, gl)
+    return loss, g_emb, g_reps
 
 
 class _EncodeTcFn(torch.autograd.Function):

@@ -78,25 +78,31 @@ class _ROIAlignFPN(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out, _grad_lvl):
-        lib = _lib.lib()
         rois, offsets = ctx.saved_tensors
-        scales, P, sampling_ratio, canon_size, canon_level, min_level = ctx.cfg
-        dev = grad_out.device
-        grad_out = grad_out.contiguous()
-        grads = []
-        for shp, cl in zip(ctx.shapes, ctx.channels_last):
-            g = torch.empty(shp, dtype=torch.float32, device=dev,
-                            memory_format=torch.channels_last if cl else torch.contiguous_format)
-            grads.append(g)
-        arr, N, C = _feat_levels(grads, scales)
-        M = rois.shape[0]
-        ws_bytes = int(lib.osr_roi_align_bwd_workspace(arr, len(grads), N, C, M))
-        ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
-        rc = lib.osr_roi_align_bwd(arr, len(grads), N, C, grad_out.data_ptr(), rois.data_ptr(), offsets.data_ptr(),
-                                   M, P, sampling_ratio, 1, canon_size, canon_level, min_level,
-                                   ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
-        _lib.check(rc, "osr_roi_align_bwd")
+        grads = roi_align_backward(grad_out, rois, offsets, ctx.shapes, ctx.channels_last, ctx.cfg)
         return (None, None, None) + tuple(grads)
+
+
+def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, offsets: torch.Tensor, shapes, channels_last, cfg):
+    """``osr_roi_align_bwd`` without autograd: dense gradient maps (one per level, fully written - no memset) for pooled
+    gradients ``grad_out`` (M, C, P, P).  ``shapes`` / ``channels_last``: shape and memory format of each level's map."""
+    lib = _lib.lib()
+    scales, P, sampling_ratio, canon_size, canon_level, min_level = cfg
+    dev = grad_out.device
+    grad_out = grad_out.contiguous()
+    grads = []
+    for shp, cl in zip(shapes, channels_last):
+        grads.append(torch.empty(tuple(shp), dtype=torch.float32, device=dev,
+                                 memory_format=torch.channels_last if cl else torch.contiguous_format))
+    arr, N, C = _feat_levels(grads, scales)
+    M = rois.shape[0]
+    ws_bytes = int(lib.osr_roi_align_bwd_workspace(arr, len(grads), N, C, M))
+    ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
+    rc = lib.osr_roi_align_bwd(arr, len(grads), N, C, grad_out.data_ptr(), rois.data_ptr(), offsets.data_ptr(),
+                               M, P, sampling_ratio, 1, canon_size, canon_level, min_level,
+                               ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "osr_roi_align_bwd")
+    return grads
 
 
 class ROIPooler(torch.nn.Module):
@@ -155,3 +161,8 @@ class ROIPooler(torch.nn.Module):
 
     def forward(self, x: List[torch.Tensor], box_lists: List[Boxes]) -> torch.Tensor:
         return self.forward_with_levels(x, box_lists)[0]
+
+    def backward_rois(self, grad_pooled: torch.Tensor, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor):
+        """Gradient of ``pool_rois`` w.r.t. the maps ``x`` (only their shapes / layouts are read), without autograd."""
+        cl = [f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous() for f in x]
+        return roi_align_backward(grad_pooled, rois.contiguous().float(), offsets, [tuple(f.shape) for f in x], cl, self._cfg())
