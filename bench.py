@@ -484,16 +484,60 @@ def run_ours(args, rank, local_rank, world):
                    "sampled_rois": int(api_path.last["pooled"].shape[0]),
                    "note": "predict_proposals -> label_and_sample_proposals (matcher + device randperm) -> ROIPooler.forward("
                            "list, list) -> PLN.loss(box_features, sampled) with the matcher's labels / IoUs -> backward; "
-                           "Instances construction, the proposal-count sync and the sampler's nonzero syncs are inside"}
+                           "Instances construction and the two host reads (proposal counts, sample counts) are inside"}
             del api_path
         except Exception as e:  # noqa: BLE001
             api = {"error": repr(e)}
         barrier(world)
 
+    # ---- S4 on the path: ROIAlign writes bf16, fc1 / fc2 run on tcgen05 and feed the PLN ---------------
+    bh = None
+    if not infer and not args.quick and cfg.channels_last:
+        try:
+            import dataclasses
+            bh_path = RoiPathStep(dataclasses.replace(cfg, box_head=True), dev)
+            for _ in range(3):
+                bh_path.step()
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            bh_events = []
+            b0.record()
+            for _ in range(10):
+                bh_path.step(stage_events=True)
+                bh_events.append(bh_path.events)
+            b1.record()
+            torch.cuda.synchronize(dev)
+            bh_ms = max_over_ranks(b0.elapsed_time(b1), world, dev) / 10
+            st = {name: sum(ev[i].elapsed_time(ev[i + 1]) for ev in bh_events) / len(bh_events) for i, name in enumerate(bh_path.STAGES)}
+            fl = bh_path.box_head_flops()
+            # the library GEMMs on the same operands (what nn.Linear under bf16 autocast would run)
+            x1 = bh_path.last["pooled"].view(bh_path.last["pooled"].shape[0], -1)
+            for _ in range(2):
+                torch.relu(torch.relu(x1 @ bh_path.fc1_w.t()) @ bh_path.fc2_w.t())
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(5):
+                torch.relu(torch.relu(x1 @ bh_path.fc1_w.t()) @ bh_path.fc2_w.t())
+            c1.record()
+            torch.cuda.synchronize(dev)
+            lib_ms = c0.elapsed_time(c1) / 5
+            bh = {"ms_per_step": bh_ms, "value": world * N * 1e3 / bh_ms, "steps": 10, "stage_ms": st, "s4_flops": fl,
+                  "s4_tflops": fl / (st["s4_box_head_fc_fwd"] * 1e-3) / 1e12, "s4_cublas_bf16_ms": lib_ms,
+                  "pooled_bytes_bf16": int(x1.numel() * 2),
+                  "note": "same step with S4 on the path: osr_roi_align_fwd_bf16 writes the pooled tile in bf16, fc1 (12544->1024) and "
+                          "fc2 (1024->1024) + bias + ReLU run on tcgen05 (osr_linear_bf16_fwd) and their output feeds the PLN encoder; the "
+                          "FC backward GEMMs are library calls outside the path (fixed pooled gradient as in the headline)"}
+            del bh_path, x1
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            bh = {"error": repr(e)[:300]}
+        barrier(world)
+
     if infer or args.quick:
         if rank == 0:
             line = _line(args, world, cfg, N, value, ms_step, clocks, None, launches, roof, stages, None, None, None, None,
-                         eager, graph_err, api)
+                         eager, graph_err, api, bh)
             print(json.dumps(line), flush=True)
         return
 
@@ -525,12 +569,12 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     line = _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stages, alt, gbase, gathered,
-                 cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None, eager, graph_err, api)
+                 cpu_baseline(cfg) if (world == 1 and not args.no_cpu_baseline) else None, eager, graph_err, api, bh)
     print(json.dumps(line), flush=True)
 
 
 def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stages, alt, gbase, gathered, cpu, eager,
-          graph_err, api):
+          graph_err, api, bh=None):
     infer = args.config == "cfg4"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -561,6 +605,8 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
         line["cuda_graph_error"] = graph_err
     if api is not None:
         line["api_step"] = api
+    if bh is not None:
+        line["with_box_head"] = bh
     if gathered is not None:
         line["gathered_pln"] = gathered
     if cpu is not None:

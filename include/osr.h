@@ -162,6 +162,24 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (3b) Box-head fully connected layers on tensor cores
+ * Replaces detectron2 FastRCNNConvFCHead.forward (flatten -> fc1 -> ReLU -> fc2 -> ReLU), called at
+ *   openset_rcnn/modeling/roi_heads/osrcnn_roi_heads.py:308  (built :119-121; cfg ROI_BOX_HEAD NUM_FC 2, FC_DIM 1024)
+ * osr_roi_align_fwd_bf16: same as osr_roi_align_fwd but the pooled tile is written as bf16 (round to nearest even), C-major
+ *   (M, C, P, P) - the A operand of fc1 - instead of fp32; dense channels_last maps, C % 8 == 0, C <= 256.
+ * osr_linear_bf16_fwd:  out[R, N] = act(A[R, K] . W[N, K]^T + bias), A / W bf16 row-major, fp32 accumulate (tcgen05 + TMEM),
+ *   bias fp32 or NULL, relu 0 / 1, out bf16 (out_is_bf16 = 1) or fp32; K % 64 == 0, N % 256 == 0.
+ * osr_cast_bf16: fp32 -> bf16 copy (weights, once per optimizer step), n % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int osr_roi_align_fwd_bf16(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                           int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
+                           int min_level, void* out_bf16, int32_t* out_level, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int osr_linear_bf16_fwd(const void* a_bf16, const void* w_bf16, const float* bias, int R, int K, int N, int relu, void* out,
+                        int out_is_bf16, void* stream);
+int osr_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (4) PLN prototype loss (COS distance) forward / backward
  * Replaces PLN.loss lines 134,137-187 of
  *   openset_rcnn/modeling/roi_heads/prototype_learning_network.py

@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>  // CUtensorMap types only; cuTensorMapEncodeTiled is resolved at run time (no libcuda link dependency)
 
+#include <cuda_bf16.h>
+
 #include "roi_geometry.cuh"
 
 namespace {
@@ -35,6 +37,7 @@ struct FwdParams {
   const float* rois;
   int M;
   float* out;
+  unsigned short* out_bf16;   // non-null: write the pooled tile as bf16 (round to nearest even) INSTEAD of fp32 (NHWC kernel)
   int32_t* out_level;
   const int32_t* order;  // (M) processing order (RoIs sorted by image, level, y band) or nullptr
   float* rec;            // (M, kRecFloats) per-RoI table records written by roi_fwd_prep_kernel, or nullptr
@@ -737,6 +740,11 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* out_roi = p.out + (int64_t)m * C * (kP * kP);
+  unsigned short* out_bf = p.out_bf16 ? p.out_bf16 + (int64_t)m * C * (kP * kP) : nullptr;
+  auto store_out = [&](int o, float v) {   // rare paths (empty / oversized RoIs): scalar stores in the requested type
+    if (out_bf) out_bf[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    else out_roi[o] = v;
+  };
   // ---- prologue: tables either from the prep kernel's record (common case) or derived here ----------------------
   int level, img, xmin, ymin, wf, hf, tmax = 0;
   float inv_count;
@@ -827,7 +835,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   }
   wf = xmax - xmin + 1; hf = ymax - ymin + 1;
   if (zero || (!overflow && (xmax < 0 || ymax < 0))) {
-    for (int o = tid; o < C * kP * kP; o += kThreads) out_roi[o] = 0.f;
+    for (int o = tid; o < C * kP * kP; o += kThreads) store_out(o, 0.f);
     return;
   }
   if (overflow || hf > kMaxRows) {
@@ -847,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
           s += bilinear_sample(plane, lv.sH, lv.sW, lv.H, lv.W, y, x);
         }
       }
-      out_roi[o] = s / g.count;
+      store_out(o, s / g.count);
     }
     return;
   }
@@ -1071,7 +1079,17 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   }
   __syncthreads();
   const int n4 = (C * kP * kP) >> 2;
-  if ((((uintptr_t)out_roi) & 15) == 0 && ((C * kP * kP) & 3) == 0) {
+  if (out_bf) {   // bf16 pooled output for the tensor-core box head: 8 values per 16-byte store (C % 8 == 0 host-checked)
+    for (int i = tid; i < (n4 >> 1); i += kThreads) {
+      const float4 a = reinterpret_cast<const float4*>(ring)[2 * i], b = reinterpret_cast<const float4*>(ring)[2 * i + 1];
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(a.x, a.y), b1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(b.x, b.y), b3 = __floats2bfloat162_rn(b.z, b.w);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+      o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+      reinterpret_cast<uint4*>(out_bf)[i] = o;
+    }
+  } else if ((((uintptr_t)out_roi) & 15) == 0 && ((C * kP * kP) & 3) == 0) {
     for (int i = tid; i < n4; i += kThreads) reinterpret_cast<float4*>(out_roi)[i] = reinterpret_cast<const float4*>(ring)[i];
   } else {
     for (int i = tid; i < C * kP * kP; i += kThreads) out_roi[i] = ring[i];
@@ -1204,21 +1222,22 @@ size_t osr_roi_align_fwd_workspace(int M) {
   return osr::align256(m * 4) * 2 + osr::align256(m * kRecFloats * 4);   // order, keys, per-RoI table records
 }
 
-int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
-                      int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
-                      int min_level, float* out, int32_t* out_level, void* workspace, size_t workspace_bytes,
-                      void* stream) {
-  osr::DeviceGuard device_guard(out);
+static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                              int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
+                              int min_level, float* out, unsigned short* out_bf16, int32_t* out_level, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(out_level);
   FwdParams p;
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);
   if (rc) return rc;
   if (M < 0) return osr::fail_arg(OSR_E_ARG, "roi_align_fwd: M < 0");
   if (M == 0) return 0;
-  if (!rois || !out || !out_level) return osr::fail_arg(OSR_E_ARG, "roi_align_fwd: null pointer argument");
+  if (!rois || (!out && !out_bf16) || !out_level) return osr::fail_arg(OSR_E_ARG, "roi_align_fwd: null pointer argument");
   p.rois = rois;
   p.M = M;
   p.out = out;
+  p.out_bf16 = out_bf16;
   p.out_level = out_level;
   p.order = nullptr;
   p.rec = nullptr;
@@ -1243,6 +1262,8 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
     const LevelDesc& lv = p.L.lv[l];
     nhwc = lv.sC == 1 && lv.sW == C && lv.sH == (int64_t)lv.W * C && (lv.sN % 4 == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
   }
+  if (out_bf16 && !(nhwc && C % 8 == 0))
+    return osr::fail_arg(OSR_E_SHAPE, "roi_align_fwd_bf16: needs dense channels_last feature maps with C %% 8 == 0 and C <= 256");
   if (nhwc) {
     if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && osr::tuning(osr::kTuneFwdVariant) != 2) {
       p.rec = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 2 * osr::align256((size_t)M * 4));
@@ -1280,6 +1301,26 @@ int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_
   }
   OSR_LAUNCH_CHECK();
   return 0;
+}
+
+
+int osr_roi_align_fwd(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                      int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
+                      int min_level, float* out, int32_t* out_level, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  return roi_align_fwd_impl(h_levels, num_levels, num_images, C, rois, M, P, sampling_ratio, aligned, canonical_box_size,
+                            canonical_level, min_level, out, nullptr, out_level, workspace, workspace_bytes, stream);
+}
+
+int osr_roi_align_fwd_bf16(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                           int M, int P, int sampling_ratio, int aligned, int canonical_box_size, int canonical_level,
+                           int min_level, void* out_bf16, int32_t* out_level, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (M > 0 && (!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 15)))
+    return osr::fail_arg(OSR_E_ARG, "roi_align_fwd_bf16: null or misaligned output");
+  return roi_align_fwd_impl(h_levels, num_levels, num_images, C, rois, M, P, sampling_ratio, aligned, canonical_box_size,
+                            canonical_level, min_level, nullptr, static_cast<unsigned short*>(out_bf16), out_level, workspace,
+                            workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -50,6 +50,7 @@ class PathConfig:
     unk_thr: float = 0.23
     gt_per_image: int = 8
     name: str = "cfg2"
+    box_head: bool = False        # S4 on the path: ROIAlign writes bf16, fc1 / fc2 on tcgen05 feed the PLN
 
 
 def make_config(name: str = "cfg2", world: int = 1, **over) -> PathConfig:
@@ -80,6 +81,9 @@ class RoiPathStep:
 
     def __init__(self, cfg: PathConfig, device="cuda:0", host_inputs: bool = False):
         self.cfg = cfg
+        if cfg.box_head:
+            self.STAGES = ("s1_proposals", "s2_sample_glue", "s3_roialign_fwd", "s4_box_head_fc_fwd", "s5_pln_fwd_bwd",
+                           "s3_roialign_bwd")
         self.device = torch.device(device)
         dev = self.device
         N = cfg.num_images
@@ -140,6 +144,16 @@ class RoiPathStep:
                                                                    seed=cfg.seed + 5, device=dev)
         self.prop_off = torch.arange(0, (N + 1) * sel.kmax, sel.kmax, dtype=torch.int32, device=dev)
         self.count_col = sel.num_levels
+        if cfg.box_head:
+            # detectron2 FastRCNNConvFCHead weights (c2_xavier_fill), kept in bf16 for the tensor-core GEMMs
+            gw = torch.Generator(device=dev).manual_seed(cfg.seed + 6)
+            kin = cfg.channels * 49
+            b1 = (3.0 / kin) ** 0.5
+            b2 = (3.0 / cfg.feat_dim) ** 0.5
+            self.fc1_w = ((torch.rand(cfg.feat_dim, kin, device=dev, generator=gw) * 2 - 1) * b1).to(torch.bfloat16)
+            self.fc2_w = ((torch.rand(cfg.feat_dim, cfg.feat_dim, device=dev, generator=gw) * 2 - 1) * b2).to(torch.bfloat16)
+            self.fc1_b = torch.zeros(cfg.feat_dim, device=dev)
+            self.fc2_b = torch.zeros(cfg.feat_dim, device=dev)
         self.last: Dict[str, torch.Tensor] = {}
         self._fused_enc = None
         self.fused_gather_error = None
@@ -155,7 +169,7 @@ class RoiPathStep:
         deltas = self.deltas if deltas is None else deltas
         ctr = self.ctr if ctr is None else ctr
         feats = self.feats if feats is None else feats
-        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if stage_events else None
+        self.events = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.STAGES) + 1)] if stage_events else None
         self._mark(0)
         # S1
         sel = rpn_select_decode(self.anchors, deltas, ctr, self.image_hw_dev, cfg.pre_nms_topk)
@@ -171,11 +185,21 @@ class RoiPathStep:
         self._mark(2)
         # S3 forward (kernels are called directly, without autograd: no engine thread hop, capturable in a CUDA graph;
         # tests/test_gpu_pipeline.py checks this path against the autograd one)
-        with torch.no_grad():
-            pooled, lvl = self.pooler.pool_rois([f.detach() for f in feats], rois, self.roi_offsets)
-        self._mark(3)
-        # S5: encoder + prototype loss forward + backward to (emb, representatives)
+        k = 3
         pi = self.pln
+        roi_features = pi.roi_features
+        with torch.no_grad():
+            if cfg.box_head:
+                # S3 writes the pooled tile in bf16; S4 = fc1 + ReLU + fc2 + ReLU on tcgen05 produces the PLN's input
+                from .box_head import linear_bf16
+                pooled, lvl = self.pooler.pool_rois_bf16(feats, rois, self.roi_offsets)
+                self._mark(k); k += 1
+                h = linear_bf16(pooled.view(pooled.shape[0], -1), self.fc1_w, self.fc1_b, True, torch.bfloat16)
+                roi_features = linear_bf16(h, self.fc2_w, self.fc2_b, True, torch.float32)
+            else:
+                pooled, lvl = self.pooler.pool_rois([f.detach() for f in feats], rois, self.roi_offsets)
+        self._mark(k); k += 1
+        # S5: encoder + prototype loss forward + backward to (emb, representatives)
         reps = pi.reps
         kw = dict(num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,
                   iou_threshold=cfg.iou_threshold)
@@ -184,20 +208,20 @@ class RoiPathStep:
             # over NVLink (fused all-gather), then the global-batch loss (dist.py)
             if self._fused_enc is None:
                 try:
-                    self._fused_enc = FusedEncoderGather(pi.roi_features.shape[0], cfg.emb_dim, self.device)
+                    self._fused_enc = FusedEncoderGather(roi_features.shape[0], cfg.emb_dim, self.device)
                 except Exception as e:  # noqa: BLE001 - no symmetric memory / P2P on this box: NCCL all-gather instead
                     self._fused_enc = False
                     self.fused_gather_error = repr(e)
         if gather_pln:
             reps = reps.requires_grad_(True)
             if cfg.encoder_impl == "tcgen05" and self._fused_enc:
-                loss, emb = fused_gathered_pln_loss(self._fused_enc, pi.roi_features, pi.enc_w, pi.enc_b, reps,
+                loss, emb = fused_gathered_pln_loss(self._fused_enc, roi_features, pi.enc_w, pi.enc_b, reps,
                                                     pi.gt_classes, pi.ious, **kw)
             else:
                 if cfg.encoder_impl == "tcgen05":
-                    emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+                    emb = pln_encode_tc(roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
                 else:
-                    emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+                    emb = F.linear(roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
                 import torch.distributed as tdist
                 w = tdist.get_world_size() if tdist.is_initialized() else 1
                 loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, rows_per_rank=[emb.shape[0]] * w, **kw)
@@ -205,14 +229,14 @@ class RoiPathStep:
         else:            # the reference's semantics: per-rank loss
             with torch.no_grad():
                 if cfg.encoder_impl == "tcgen05":
-                    emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b)
+                    emb = pln_encode_tc(roi_features, pi.enc_w, pi.enc_b)
                 else:
-                    emb = F.linear(pi.roi_features, pi.enc_w, pi.enc_b)
+                    emb = F.linear(roi_features, pi.enc_w, pi.enc_b)
             loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
-        self._mark(4)
+        self._mark(k); k += 1
         # S3 backward
         g_feats = self.pooler.backward_rois(self.grad_pooled, feats, rois, self.roi_offsets)
-        self._mark(5)
+        self._mark(k)
         self.last = dict(sel=sel, match=match, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
                          g_feats=g_feats)
         return loss, sel.counts
@@ -264,6 +288,12 @@ class RoiPathStep:
             "s5_pln_fwd_bwd": roofline.s5_fwd_bytes(M, cfg.feat_dim, cfg.emb_dim, cfg.num_known) +
                               roofline.s5_bwd_bytes(M, cfg.emb_dim, cfg.num_known),
         }
+
+    def box_head_flops(self) -> int:
+        """fc1 + fc2 forward FLOPs of one step (2 R K N each)."""
+        cfg = self.cfg
+        R = cfg.num_images * cfg.rois_per_image
+        return 2 * R * (cfg.channels * 49) * cfg.feat_dim + 2 * R * cfg.feat_dim * cfg.feat_dim
 
 
 # =====================================================================================================================

@@ -151,6 +151,27 @@ class ROIPooler(torch.nn.Module):
         rois, offsets = convert_boxes_to_pooler_format(box_lists)
         return self.pool_rois(x, rois, offsets)
 
+    def pool_rois_bf16(self, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor):
+        """Forward only, pooled tile written as bf16 (``osr_roi_align_fwd_bf16``): the A operand of the tensor-core box
+        head (``box_head.FastRCNNConvFCHead``).  Dense channels_last maps, C % 8 == 0.  Returns (pooled bf16, level).
+        The gradient w.r.t. the maps is ``backward_rois`` (ROIAlign's backward never reads the pooled values)."""
+        lib = _lib.lib()
+        scales, P, sampling_ratio, canon_size, canon_level, min_level = self._cfg()
+        feats = [f.detach() for f in x]
+        arr, N, C = _feat_levels(feats, scales)
+        rois = rois.contiguous().float()
+        M = rois.shape[0]
+        dev = feats[0].device
+        out = torch.empty((M, C, P, P), dtype=torch.bfloat16, device=dev)
+        lvl = torch.empty((M,), dtype=torch.int32, device=dev)
+        if M == 0:
+            return out, lvl
+        ws = torch.empty(max(int(lib.osr_roi_align_fwd_workspace(M)), 256), dtype=torch.uint8, device=dev)
+        rc = lib.osr_roi_align_fwd_bf16(arr, len(feats), N, C, rois.data_ptr(), M, P, sampling_ratio, 1, canon_size, canon_level,
+                                        min_level, out.data_ptr(), lvl.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "osr_roi_align_fwd_bf16")
+        return out, lvl
+
     def pool_rois(self, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor):
         """Already-packed entry: rois (M,5) image-major, offsets (N+1) int32 (no python list handling)."""
         if rois.shape[0] == 0:

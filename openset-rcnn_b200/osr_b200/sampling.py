@@ -72,11 +72,17 @@ def subsample_labels(labels: torch.Tensor, num_samples: int, positive_fraction: 
 def label_and_sample_proposals(proposals: List[Instances], targets: List[Instances], *, num_classes: int,
                                batch_size_per_image: int = 512, positive_fraction: float = 0.25,
                                iou_threshold: float = 0.5, proposal_append_gt: bool = True,
-                               randperm: Optional[Callable[[int], torch.Tensor]] = None) -> List[Instances]:
+                               randperm: Optional[Callable[[int], torch.Tensor]] = None,
+                               generator: Optional[torch.Generator] = None) -> List[Instances]:
     """``OpensetROIHeads.label_and_sample_proposals(proposals, targets)`` (``osrcnn_roi_heads.py:136-230``); the
     keyword arguments are the module attributes it reads (``num_classes``, ``batch_size_per_image``,
     ``positive_fraction``, ``proposal_matcher`` threshold, ``proposal_append_gt``).  Like the reference it raises
-    ``IndexError`` for an image without ground truth (the matched-IoU gather at ``:193`` indexes an empty matrix)."""
+    ``IndexError`` for an image without ground truth (the matched-IoU gather at ``:193`` indexes an empty matrix).
+
+    Sampling: with ``randperm`` given (a callable standing for ``torch.randperm``) the reference's per-image
+    ``subsample_labels`` is replayed draw for draw (parity tests inject the reference's own permutations).  Without it the
+    whole batch is sampled at once on the device (``sample_labels_batched``: same distribution and order, its own random
+    stream, no per-image host syncs - the stage then has ONE host read, the per-image sample counts)."""
     N = len(proposals)
     assert len(targets) == N
     if N == 0:
@@ -104,6 +110,9 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
     goff = torch.tensor([0] + list(torch.tensor(gcounts).cumsum(0).tolist()), dtype=torch.int32, device=dev)
     midx, miou, mlab, mcls = match_proposals(boxes, off, gt_boxes, gt_classes, goff, max(counts),
                                              iou_threshold=iou_threshold, background_label=num_classes)
+    if randperm is None:
+        return _finish_batched(proposals, targets, box_list, logit_list, counts, off, midx, miou, mcls,
+                               num_classes, batch_size_per_image, positive_fraction, proposal_append_gt, generator)
     out = []
     b0 = 0
     for n, (p, t) in enumerate(zip(proposals, targets)):
@@ -125,4 +134,70 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
                 q.set(name, value.to(dev)[st] if hasattr(value, "to") else value[st])
         out.append(q)
         b0 = b1
+    return out
+
+
+def sample_labels_batched(labels: torch.Tensor, valid: torch.Tensor, num_samples: int, positive_fraction: float,
+                          bg_label: int, generator: Optional[torch.Generator] = None):
+    """detectron2 ``subsample_labels`` for ALL images at once, without a host sync.  ``labels`` (N, Pmax) int64 padded,
+    ``valid`` (N, Pmax) bool.  Per image: a uniformly random subset of at most ``int(num_samples * positive_fraction)``
+    foreground rows followed by a uniformly random subset of background rows filling up to ``num_samples`` - the same
+    distribution and the same (positives first) order as two ``torch.randperm`` draws, but from one ``torch.rand`` key per
+    row and two per-image top-k selections.  Returns ``(index (N, num_samples) int64, count (N,) int64)``; entries at
+    positions >= count[n] are undefined."""
+    dev = labels.device
+    N, Pmax = labels.shape
+    pos = valid & (labels != -1) & (labels != bg_label)
+    neg = valid & (labels == bg_label)
+    keys = torch.rand((N, Pmax), device=dev, generator=generator)
+    k = min(num_samples, Pmax)
+    two = torch.full((), 2.0, device=dev)
+    ip = torch.where(pos, keys, two).topk(k, dim=1, largest=False).indices
+    ineg = torch.where(neg, keys, two).topk(k, dim=1, largest=False).indices
+    npos = pos.sum(dim=1).clamp(max=int(num_samples * positive_fraction))
+    nneg = torch.minimum(neg.sum(dim=1), num_samples - npos)
+    slot = torch.arange(num_samples, device=dev)[None, :]
+    from_pos = slot < npos[:, None]
+    gp = ip.gather(1, slot.clamp(max=k - 1).expand(N, -1))
+    gn = ineg.gather(1, (slot - npos[:, None]).clamp(min=0, max=k - 1))
+    return torch.where(from_pos, gp, gn), npos + nneg
+
+
+def _finish_batched(proposals, targets, box_list, logit_list, counts, off, midx, miou, mcls, num_classes,
+                    batch_size_per_image, positive_fraction, proposal_append_gt, generator):
+    """Sampling + field gathering of ``label_and_sample_proposals`` for the whole batch: padded (N, Pmax) label matrix,
+    ``sample_labels_batched``, ONE host read of the per-image sample counts, then views."""
+    N = len(proposals)
+    dev = mcls.device
+    Pmax = max(counts)
+    cnt_t = torch.tensor(counts, device=dev)
+    img = torch.repeat_interleave(torch.arange(N, device=dev), cnt_t, output_size=int(sum(counts)))
+    local = torch.arange(int(sum(counts)), device=dev) - off.long()[img]
+    labels = torch.full((N, Pmax), -2, dtype=torch.int64, device=dev)
+    labels[img, local] = mcls
+    valid = torch.arange(Pmax, device=dev)[None, :] < cnt_t[:, None]
+    idx, cnt = sample_labels_batched(labels, valid, batch_size_per_image, positive_fraction, num_classes, generator)
+    flat = idx + off.long()[:N, None]                         # positions in the concatenated proposal list
+    boxes = torch.cat(box_list, dim=0)
+    logits = torch.cat(logit_list, dim=0)
+    flat_c = flat.clamp(max=boxes.shape[0] - 1)
+    sb, sl, sc, si, sm = boxes[flat_c], logits[flat_c], mcls[flat_c], miou[flat_c], midx[flat_c].long()
+    n_s = cnt.tolist()                                        # the one host sync of the stage
+    out = []
+    for n, (p, t) in enumerate(zip(proposals, targets)):
+        k = n_s[n]
+        q = Instances(p.image_size)
+        q.set("proposal_boxes", Boxes(sb[n, :k]))
+        q.set("objectness_logits", sl[n, :k])
+        if not proposal_append_gt:
+            for name, value in p.get_fields().items():
+                if name not in ("proposal_boxes", "objectness_logits"):
+                    q.set(name, value[idx[n, :k]])
+        q.set("gt_classes", sc[n, :k])
+        q.set("ious", si[n, :k])
+        st = sm[n, :k]
+        for name, value in t.get_fields().items():
+            if name.startswith("gt_") and not q.has(name):
+                q.set(name, value.to(dev)[st] if hasattr(value, "to") else value[st])
+        out.append(q)
     return out

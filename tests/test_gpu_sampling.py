@@ -126,3 +126,30 @@ def test_padded_layout_with_counts_column():
         assert torch.equal(midx[sl].cpu().long(), idx)
         assert torch.equal(miou[sl].cpu(), m[idx, torch.arange(p.shape[0])])
         assert torch.equal(mlab[sl].cpu().to(torch.int8), lab)
+
+
+def test_label_and_sample_batched_path_is_consistent_with_the_matcher():
+    """Default (no injected randperm): the whole batch is sampled on the device with one host read.  Every sampled row
+    must carry exactly the label / IoU / GT box the reference's matcher assigns to that box, foreground rows first."""
+    from osr_b200 import sampling as S, structures as st
+    props, tgts = _make(3, [900, 2500, 40], [4, 8, 2], seed=12)
+    P, T = [], []
+    for pb, (gb, gc) in zip(props, tgts):
+        p = st.Instances((800, 1333)); p.set("proposal_boxes", st.Boxes(pb.cuda())); p.set("objectness_logits", torch.rand(len(pb)).cuda())
+        t = st.Instances((800, 1333)); t.set("gt_boxes", st.Boxes(gb.cuda())); t.set("gt_classes", gc.cuda())
+        P.append(p); T.append(t)
+    out = S.label_and_sample_proposals(P, T, num_classes=80, batch_size_per_image=128, positive_fraction=0.25)
+    for q, pb, (gb, gc) in zip(out, props, tgts):
+        allb = torch.cat((pb, gb))                       # proposals + appended GT
+        m = pairwise_iou(OBoxes(gb), OBoxes(allb))
+        idx, lab = osamp.matcher(m, 0.5)
+        iou = m[idx, torch.arange(m.shape[1])]
+        cls = gc[idx].clone(); cls[lab == 0] = 80
+        sb = q.get("proposal_boxes").tensor.cpu()
+        # locate every sampled box in the candidate list (boxes are distinct except planted duplicates: compare values)
+        pos = [(allb == b).all(dim=1).nonzero()[0, 0].item() for b in sb]
+        assert torch.equal(q.get("gt_classes").cpu(), cls[pos]) and torch.equal(q.get("ious").cpu(), iou[pos])
+        assert torch.equal(q.get("gt_boxes").tensor.cpu(), gb[idx[pos]])
+        n_fg = int((q.get("gt_classes") != 80).sum())
+        assert n_fg <= 32 and bool((q.get("gt_classes")[:n_fg] != 80).all()) and bool((q.get("gt_classes")[n_fg:] == 80).all())
+        assert len(q) == min(128, n_fg + int((cls == 80).sum()))

@@ -51,3 +51,32 @@ def test_matching_and_inference_ops_refuse_cpu_tensors():
     p = Instances((10, 10)); p.set("proposal_boxes", Boxes(torch.rand(2, 4))); p.set("objectness_logits", torch.rand(2))
     with pytest.raises(_lib.OsrError):
         inference((torch.rand(2, 4), torch.rand(2, 1)), [p], torch.rand(2, 8))
+
+
+def test_sample_labels_batched_contract():
+    """The sync-free batched sampler: per image at most int(B * frac) foreground rows FIRST, then background rows up to B,
+    no padding / ignored rows, no duplicates, and the counts detectron2's subsample_labels would give."""
+    from osr_b200.sampling import sample_labels_batched
+    g = torch.Generator().manual_seed(11)
+    N, P, B = 5, 400, 64
+    labels = torch.where(torch.rand(N, P, generator=g) < 0.2, torch.randint(0, 20, (N, P), generator=g), torch.full((N, P), 81))
+    labels[:, ::37] = -1
+    valid = torch.ones(N, P, dtype=torch.bool)
+    valid[1, 100:] = False
+    labels[2] = 81            # no foreground at all
+    labels[3, 40:] = -1       # few candidates: fewer than B samples
+    labels[4, :] = 7          # only foreground: int(B * frac) samples
+    idx, cnt = sample_labels_batched(labels, valid, B, 0.25, 81, generator=g)
+    for n in range(N):
+        lab = labels[n][valid[n]]
+        n_pos = min(int(((lab != -1) & (lab != 81)).sum()), int(B * 0.25))
+        n_neg = min(int((lab == 81).sum()), B - n_pos)
+        k = int(cnt[n])
+        assert k == n_pos + n_neg
+        ii = idx[n, :k]
+        assert bool(valid[n, ii].all()) and len(set(ii.tolist())) == k
+        got = labels[n, ii]
+        assert bool(((got[:n_pos] != 81) & (got[:n_pos] != -1)).all()) and bool((got[n_pos:] == 81).all())
+    # a different generator state draws a different subset (it is a random sample, not a prefix)
+    idx2, _ = sample_labels_batched(labels, valid, B, 0.25, 81, generator=g)
+    assert not torch.equal(idx, idx2)
