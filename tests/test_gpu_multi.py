@@ -22,3 +22,35 @@ def test_fused_encoder_gather_two_gpus(multicast):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "bit-identical to encoder + NCCL all-gather (incl. loss, grads): True" in out.stdout, out.stdout[-2000:]
+
+
+@pytest.mark.parametrize("world,rank", [(2, 0), (2, 1), (4, 2)])
+def test_encode_gather_epilogue_on_one_gpu(world, rank):
+    """The fused encoder -> all-gather kernel with every "peer" buffer on THIS GPU (plain device allocations instead of
+    NVLink-mapped ones): verifies on a 1-GPU box that the multi-destination epilogue writes this rank's (R, E) block,
+    bit-identical to the single-destination encoder, at rows [rank*R, (rank+1)*R) of every destination and nothing else."""
+    import ctypes
+    from osr_b200 import _lib, synth
+    from osr_b200.pln import pln_encode_tc
+    lib = _lib.lib()
+    dev = torch.device("cuda:0")
+    R, Fd, E = 300, 1024, 256          # R not a multiple of the 128-row tile: the last tile is partial
+    pi = synth.make_pln_inputs(R, seed=5, device=dev)
+    ref = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b + 0.25)
+    bufs = [torch.full((world * R, E), -7.0, device=dev) for _ in range(world)]
+    ptrs = (ctypes.c_uint64 * world)(*[b.data_ptr() for b in bufs])
+    ws = torch.empty(max(int(lib.osr_pln_encode_workspace(R, Fd, E)), 256), dtype=torch.uint8, device=dev)
+    bias = (pi.enc_b + 0.25).contiguous()
+    rc = lib.osr_pln_encode_gather_fwd(pi.roi_features.data_ptr(), pi.enc_w.data_ptr(), bias.data_ptr(), R, Fd, E,
+                                       ctypes.cast(ptrs, ctypes.c_void_p), world, rank, 0, ws.data_ptr(), ws.numel(),
+                                       _lib.stream_ptr(dev))
+    _lib.check(rc, "osr_pln_encode_gather_fwd")
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[rank * R:(rank + 1) * R], ref)
+        rest = torch.cat((b[:rank * R], b[(rank + 1) * R:]))
+        assert bool((rest == -7.0).all()), "rows of other ranks must not be touched"
+    # argument checks of the entry point
+    assert lib.osr_pln_encode_gather_fwd(pi.roi_features.data_ptr(), pi.enc_w.data_ptr(), None, R, Fd, E,
+                                         ctypes.cast(ptrs, ctypes.c_void_p), world, world, 0, ws.data_ptr(), ws.numel(),
+                                         _lib.stream_ptr(dev)) < 0
