@@ -339,29 +339,35 @@ def run_ours(args, rank, local_rank, world):
     # ---- one CUDA graph replay per step: the fixed-shape device-resident step is captured once; the
     # headline is the graph-launched step when the capture succeeds, the eager one otherwise ------------------------------
     graph, graph_err = None, None
-    if not args.no_graph and not infer and not gather_headline:
+    if not args.no_graph and not infer:
+        # (the fused encoder + all-gather alternates between two symmetric buffer sets: capture two steps per graph there)
+        spg = 2 if gather_headline else 1
+        reps_n = max(1, args.steps // spg)
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                path.step()
+                for _ in range(spg):
+                    path.step(**step_kw)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
+            barrier(world)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                path.step()
+                for _ in range(spg):
+                    path.step(**step_kw)
             for _ in range(3):
                 graph.replay()
             torch.cuda.synchronize(dev)
             barrier(world)
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            for _ in range(args.steps):
+            for _ in range(reps_n):
                 graph.replay()
             g1.record()
             torch.cuda.synchronize(dev)
             barrier(world)
-            ms_step = max_over_ranks(g0.elapsed_time(g1), world, dev) / args.steps
+            ms_step = max_over_ranks(g0.elapsed_time(g1), world, dev) / (reps_n * spg)
         except Exception as e:  # noqa: BLE001 - keep the eager number, say so in the line
             graph, graph_err = None, repr(e)[:300]
             try:
@@ -455,6 +461,43 @@ def run_ours(args, rank, local_rank, world):
                                  "of the embeddings (symmetric memory unavailable: %s), " % path.fused_gather_error) +
                                 "labels/ious by NCCL all_gather, every rank then runs the loss kernels on W*R rows "
                                 "(osr_b200/dist.py); the headline value keeps the reference's per-rank loss"}
+            # the same gathered step as ONE CUDA graph per rank (peer stores, the symmetric-memory barrier and the NCCL
+            # all-gather of the labels are all stream-ordered and capturable)
+            try:
+                if args.no_gather_graph:
+                    raise RuntimeError("skipped (--no-gather-graph)")
+                gg = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    path.step(gather_pln=True)
+                    path.step(gather_pln=True)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                barrier(world)
+                with torch.cuda.graph(gg):
+                    path.step(gather_pln=True)
+                    path.step(gather_pln=True)   # two steps: the fused kernel alternates between two symmetric buffer sets
+                for _ in range(2):
+                    gg.replay()
+                torch.cuda.synchronize(dev)
+                barrier(world)
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                for _ in range(5):
+                    gg.replay()
+                h1.record()
+                torch.cuda.synchronize(dev)
+                gg_ms = max_over_ranks(h0.elapsed_time(h1), world, dev) / 10
+                gathered["graph_ms_per_step"] = gg_ms
+                gathered["graph_value"] = world * N * 1e3 / gg_ms
+                del gg
+            except Exception as e:  # noqa: BLE001
+                gathered["graph_error"] = repr(e)[:200]
+                try:
+                    torch.cuda.synchronize(dev)
+                except Exception:  # noqa: BLE001
+                    pass
         except Exception as e:  # noqa: BLE001 - the side measurement must never take the headline line down
             gathered = {"error": repr(e)}
         barrier(world)
@@ -536,7 +579,7 @@ def run_ours(args, rank, local_rank, world):
 
     if infer or args.quick:
         if rank == 0:
-            line = _line(args, world, cfg, N, value, ms_step, clocks, None, launches, roof, stages, None, None, None, None,
+            line = _line(args, world, cfg, N, value, ms_step, clocks, None, launches, roof, stages, alt, gbase, gathered, None,
                          eager, graph_err, api, bh)
             print(json.dumps(line), flush=True)
         return
@@ -589,7 +632,7 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
                                      "switched on)" % (cfg.rpn_nms_thresh, cfg.post_nms_topk)) if infer else
                                     "as_shipped (find_top_proposals.py:112-120 commented out)",
                    "l2": "inputs larger than L2 (FPN maps %.2f GB per step vs 126 MB L2)" % (N * 0.0914),
-                   "launch": "one CUDA graph replay per step" if (eager is not None) else "eager launches",
+                   "launch": ("one CUDA graph replay per step" if not (args.config == "cfg3" and world > 1) else "one CUDA graph replay per two steps") if (eager is not None) else "eager launches",
                    "timed_stages": ("S1 proposals + NMS, S3 ROIAlign fwd, S6 ROI-head post-processing (decode + NMS + PLN.inference + "
                                     "classifier NMS); box head / predictor outputs are fixed tensors") if infer else
                                    ("S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, "
@@ -629,6 +672,7 @@ def main():
                     help="BASELINE.json configs[1..4]; cfg2 is the headline (the driver's default)")
     ap.add_argument("--images", type=int, default=None, help="images per GPU (default: the config's)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph replay per step")
+    ap.add_argument("--no-gather-graph", action="store_true", help="do not time the gathered-PLN step as a CUDA graph")
     ap.add_argument("--quick", action="store_true", help="device-resident measurement only (skip alt layout, API step, e2e, baselines)")
     args = ap.parse_args()
 

@@ -213,19 +213,27 @@ class RoiPathStep:
                     self._fused_enc = False
                     self.fused_gather_error = repr(e)
         if gather_pln:
-            reps = reps.requires_grad_(True)
-            if cfg.encoder_impl == "tcgen05" and self._fused_enc:
-                loss, emb = fused_gathered_pln_loss(self._fused_enc, roi_features, pi.enc_w, pi.enc_b, reps,
-                                                    pi.gt_classes, pi.ious, **kw)
-            else:
-                if cfg.encoder_impl == "tcgen05":
-                    emb = pln_encode_tc(roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
+            # global-batch loss, autograd-free (capturable): gathered rows -> loss + closed-form gradients of ALL rows, the
+            # local block of d loss / d emb is this rank's (scaled by W: dist.py parity rule)
+            import torch.distributed as tdist
+            from .dist import _gather_meta, all_gather_rows
+            W = tdist.get_world_size() if tdist.is_initialized() else 1
+            rank = tdist.get_rank() if tdist.is_initialized() else 0
+            R_loc = roi_features.shape[0]
+            with torch.no_grad():
+                if cfg.encoder_impl == "tcgen05" and self._fused_enc:
+                    emb, emb_all = self._fused_enc(roi_features, pi.enc_w, pi.enc_b)
                 else:
-                    emb = F.linear(roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
-                import torch.distributed as tdist
-                w = tdist.get_world_size() if tdist.is_initialized() else 1
-                loss = gathered_pln_loss(emb, reps, pi.gt_classes, pi.ious, rows_per_rank=[emb.shape[0]] * w, **kw)
-            g_emb, g_reps = torch.autograd.grad(loss, [emb, reps])
+                    emb = (pln_encode_tc(roi_features, pi.enc_w, pi.enc_b) if cfg.encoder_impl == "tcgen05"
+                           else F.linear(roi_features, pi.enc_w, pi.enc_b))
+                    emb_all = all_gather_rows(emb) if W > 1 else emb
+                if W > 1:
+                    labels_all, ious_all = _gather_meta(pi.gt_classes, pi.ious, None)
+                else:
+                    labels_all, ious_all = pi.gt_classes, pi.ious
+            loss, g_all, g_reps = pln_loss_fwd_bwd(emb_all, reps, labels_all, ious_all, r_norm=float(W * R_loc),
+                                                   center_weight=float(W), emb_grad_scale=float(W), **kw)
+            g_emb = g_all[rank * R_loc:(rank + 1) * R_loc]
         else:            # the reference's semantics: per-rank loss
             with torch.no_grad():
                 if cfg.encoder_impl == "tcgen05":
