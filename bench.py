@@ -309,7 +309,7 @@ def run_ours(args, rank, local_rank, world):
     infer = args.config == "cfg4"
     gather_headline = (args.config == "cfg3") and world > 1   # cfg 3 IS the gathered-PLN configuration
     path = InferencePathStep(cfg, dev) if infer else RoiPathStep(cfg, dev)
-    step_kw = {"gather_pln": True} if gather_headline else {}
+    step_kw = {"gather_pln": "reduce"} if gather_headline else {}
 
     for _ in range(max(args.warmup, 3)):
         path.step(**step_kw)
@@ -461,6 +461,22 @@ def run_ours(args, rank, local_rank, world):
                                  "of the embeddings (symmetric memory unavailable: %s), " % path.fused_gather_error) +
                                 "labels/ious by NCCL all_gather, every rank then runs the loss kernels on W*R rows "
                                 "(osr_b200/dist.py); the headline value keeps the reference's per-rank loss"}
+            # fused gather + per-rank loss terms + one all-reduce of (loss, representatives.grad): same numbers, W-independent cost
+            for _ in range(3):
+                path.step(gather_pln="reduce")
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(10):
+                path.step(gather_pln="reduce")
+            r1.record()
+            torch.cuda.synchronize(dev)
+            r_ms = max_over_ranks(r0.elapsed_time(r1), world, dev) / 10
+            gathered["reduced"] = {"ms_per_step": r_ms, "value": world * N * 1e3 / r_ms,
+                                   "note": "fused encoder + all-gather as above; the loss kernels run on the LOCAL rows and (loss, "
+                                           "representatives.grad) are all-reduced (1 + K*256 floats): identical value / gradients "
+                                           "(tests/test_dist_gloo.py), cost independent of the world size"}
             # the same gathered step as ONE CUDA graph per rank (peer stores, the symmetric-memory barrier and the NCCL
             # all-gather of the labels are all stream-ordered and capturable)
             try:
@@ -470,14 +486,14 @@ def run_ours(args, rank, local_rank, world):
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
-                    path.step(gather_pln=True)
-                    path.step(gather_pln=True)
+                    path.step(gather_pln="reduce")
+                    path.step(gather_pln="reduce")
                 torch.cuda.current_stream(dev).wait_stream(side)
                 torch.cuda.synchronize(dev)
                 barrier(world)
                 with torch.cuda.graph(gg):
-                    path.step(gather_pln=True)
-                    path.step(gather_pln=True)   # two steps: the fused kernel alternates between two symmetric buffer sets
+                    path.step(gather_pln="reduce")
+                    path.step(gather_pln="reduce")   # two steps: the fused kernel alternates between two symmetric buffer sets
                 for _ in range(2):
                     gg.replay()
                 torch.cuda.synchronize(dev)
@@ -489,8 +505,8 @@ def run_ours(args, rank, local_rank, world):
                 h1.record()
                 torch.cuda.synchronize(dev)
                 gg_ms = max_over_ranks(h0.elapsed_time(h1), world, dev) / 10
-                gathered["graph_ms_per_step"] = gg_ms
-                gathered["graph_value"] = world * N * 1e3 / gg_ms
+                gathered["reduced"]["graph_ms_per_step"] = gg_ms
+                gathered["reduced"]["graph_value"] = world * N * 1e3 / gg_ms
                 del gg
             except Exception as e:  # noqa: BLE001
                 gathered["graph_error"] = repr(e)[:200]
@@ -636,7 +652,7 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
                    "timed_stages": ("S1 proposals + NMS, S3 ROIAlign fwd, S6 ROI-head post-processing (decode + NMS + PLN.inference + "
                                     "classifier NMS); box head / predictor outputs are fixed tensors") if infer else
                                    ("S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, "
-                                    "S5 encoder+PLN loss fwd/bwd" + (" over the GLOBAL batch (fused encoder + all-gather)" if (args.config == "cfg3" and world > 1) else "") +
+                                    "S5 encoder+PLN loss fwd/bwd" + (" over the GLOBAL batch (encoder fused with the all-gather of the embeddings over NVLink; loss terms on local rows + one all-reduce of loss and prototype gradient)" if (args.config == "cfg3" and world > 1) else "") +
                                     ", S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))"),
                    "parallelism": f"dp{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,

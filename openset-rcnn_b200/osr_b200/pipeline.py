@@ -227,13 +227,24 @@ class RoiPathStep:
                     emb = (pln_encode_tc(roi_features, pi.enc_w, pi.enc_b) if cfg.encoder_impl == "tcgen05"
                            else F.linear(roi_features, pi.enc_w, pi.enc_b))
                     emb_all = all_gather_rows(emb) if W > 1 else emb
-                if W > 1:
+                if W > 1 and gather_pln != "reduce":
                     labels_all, ious_all = _gather_meta(pi.gt_classes, pi.ious, None)
                 else:
                     labels_all, ious_all = pi.gt_classes, pi.ious
-            loss, g_all, g_reps = pln_loss_fwd_bwd(emb_all, reps, labels_all, ious_all, r_norm=float(W * R_loc),
-                                                   center_weight=float(W), emb_grad_scale=float(W), **kw)
-            g_emb = g_all[rank * R_loc:(rank + 1) * R_loc]
+            if gather_pln == "reduce":
+                # embeddings are gathered (fused into the encoder epilogue above) but every row term depends only on (its
+                # embedding, the prototypes): per-rank loss + ONE all-reduce of (loss, representatives.grad) gives the same
+                # value and gradients as evaluating the loss kernels on all W*R rows (dist.reduced_pln_loss; tested)
+                loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
+                if W > 1:
+                    packed = torch.cat((loss.reshape(1), g_reps.reshape(-1)))
+                    tdist.all_reduce(packed)
+                    packed = packed / W
+                    loss, g_reps = packed[0], packed[1:].view_as(g_reps)
+            else:
+                loss, g_all, g_reps = pln_loss_fwd_bwd(emb_all, reps, labels_all, ious_all, r_norm=float(W * R_loc),
+                                                       center_weight=float(W), emb_grad_scale=float(W), **kw)
+                g_emb = g_all[rank * R_loc:(rank + 1) * R_loc]
         else:            # the reference's semantics: per-rank loss
             with torch.no_grad():
                 if cfg.encoder_impl == "tcgen05":
