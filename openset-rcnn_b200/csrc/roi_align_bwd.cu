@@ -945,6 +945,7 @@ struct __align__(16) RegSmem {
   unsigned char pm[kCNB][kCS];
   unsigned char xne[kCNB][kCW];             // column has weight: bit b = bin b
   unsigned char xgm[kCNB][kCW / 4];         // OR of xne over the 4 columns of a group: bins the group's expansion must visit
+  unsigned long long mbar[kCWarps];         // per-warp transaction barrier of the bulk copy that fills sg[warp]
   uchar2 xr[kCNB];                          // [first, last + 1) tile column with weight
   BatchEntry e[kCNB];
   int2 org[kCNB];
@@ -1013,6 +1014,31 @@ __device__ __forceinline__ void clr_fold_subtile(const float* gl, const RegSmem&
   }
 }
 
+// One bulk copy (cp.async.bulk, TMA 1-D: SASS UBLKCP) brings the warp's whole 32 x 49 block of grad_out (6272 contiguous,
+// 16-byte aligned bytes) into its staging buffer: one instruction from one lane instead of 13 LDGSTS from every lane, and
+// completion is an mbarrier phase instead of a cp.async group.
+__device__ __forceinline__ void clr_stage_bulk(const BwdParams& p, float* sg, unsigned long long* bar, int m, int c0w, int C, int lane) {
+  if (lane == 0) {
+    const float* src = p.grad_out + ((int64_t)m * C + c0w) * (kP * kP);
+    const unsigned ba = (unsigned)__cvta_generic_to_shared(bar), da = (unsigned)__cvta_generic_to_shared(sg);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((unsigned)(kGBlk * 4)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(da), "l"(src), "r"((unsigned)(kGBlk * 4)), "r"(ba) : "memory");
+  }
+}
+__device__ __forceinline__ void clr_wait_bulk(unsigned long long* bar, unsigned parity) {
+  const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(ba), "r"(parity) : "memory");
+}
+
 template <int kSW, int kMinB>   // kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time.  kMinB: CTAs / SM the register allocation targets
 __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1031,6 +1057,14 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   const int nslab = ceil_div(C, kCWarps * 32);
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   float* sg = S.sg[warp];
+  unsigned long long* bar = &S.mbar[warp];
+  unsigned bar_phase = 0;
+  if (lane == 0) {
+    const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   const int64_t sW = kSW > 0 ? (int64_t)kSW : lv.sW;
   const int64_t sH = lv.sH;
   const bool vec = ((sW & 3) == 0) && ((sH & 3) == 0) && ((lv.sN & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.data) & 15) == 0);
@@ -1043,7 +1077,8 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
     cl_collect(p, S, level, tx0, ty0, pos, r1);
     const int nb = S.nb, next = S.next_pos;
     if (nb > 0) {
-      cl_build_tables(p, S, lv, tx0, ty0);
+      cl_build_tables(p, S, lv, tx0, ty0);   // (uses the staging buffers as scratch: generic-proxy accesses ...)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... ordered before the bulk copies that refill them
     } else {
       if (tid < kCS) S.stmask[tid] = 0;
       __syncthreads();
@@ -1053,7 +1088,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
       if (c0w >= C) break;
       float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
       int nj = cl_next_pair(S, -1, 0);
-      if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
+      if (nj >= 0) clr_stage_bulk(p, sg, bar, S.e[nj].m, c0w, C, lane);
       for (int st = 0; st < kCS; ++st) {
         unsigned m = S.stmask[st];
         const int ys = ty0 + st * kCT;
@@ -1083,15 +1118,15 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
         while (m != 0) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
-          cp_async_wait<0>();
-          __syncwarp();
+          clr_wait_bulk(bar, bar_phase);
+          bar_phase ^= 1u;
           float2 rg2[kCT / 2][kP];
           const int2 org = S.org[j];
           const float* wtab = p.wfull + (int64_t)S.e[j].m * kWRoi;   // dense y rows: only read when bins are narrower than a pixel
           clr_fold_subtile(sg + lane * (kP * kP), S, j, st, wtab + (ty0 + st * kCT - org.x) * kP, rg2);
           __syncwarp();   // every lane is done with the staged block: refill it while the columns are expanded
           nj = cl_next_pair(S, st, m);
-          if (nj >= 0) cl_stage(p, sg, S.e[nj].m, c0w, C, lane);
+          if (nj >= 0) clr_stage_bulk(p, sg, bar, S.e[nj].m, c0w, C, lane);
           const unsigned gm = *reinterpret_cast<const unsigned*>(S.xgm[j]);   // 4 x 7-bit bin masks, one per 4-column group
           const float4* xd0 = S.xd0[j];
           const float4* xd1 = S.xd1[j];
