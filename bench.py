@@ -640,7 +640,7 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config],
-                   "pln_encoder": "bf16 tcgen05, fp32 accumulate (all other arithmetic fp32)",
+                   "pln_encoder": "tcgen05 kind::tf32 on the fp32 operands, fp32 accumulate (all other arithmetic fp32)",
                    "images_per_gpu": N, "global_batch": world * N, "image_hw": list(cfg.image_hw),
                    "pre_nms_topk_per_level": cfg.pre_nms_topk, "rois_per_image": cfg.rois_per_image,
                    "feature_layout": "channels_last" if cfg.channels_last else "NCHW",

@@ -48,7 +48,7 @@ void osr_reset_launch_count(void);
  *   OSR_TUNE_BWD_VARIANT   0 register accumulators + packed fp32x2 FMAs (shipped) | 2 shared-memory accumulators
  *                          (round-1 kernel) | 3 pixel-per-thread kernel
  *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records
- *   OSR_TUNE_PLN_VARIANT   0 default | see csrc/pln_fused.cu
+ *   OSR_TUNE_PLN_VARIANT   0 encoder GEMM on fp32 operands (tcgen05 kind::tf32, no cast pass; shipped) | 1 bf16 copies (kind::f16)
  *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu */
 #define OSR_TUNE_BWD_VARIANT 0
 #define OSR_TUNE_FWD_VARIANT 1
@@ -211,6 +211,15 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
                      const int32_t* center_rep, const float* grad_loss, int R, int D, int K, int reps_per_class,
                      float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Forward and closed-form backward of the loss in one call (grad_loss: device scalar, usually 1): same outputs as
+ * osr_pln_loss_fwd followed by osr_pln_loss_bwd, bit for bit, in four launches (d loss / d emb is written by the row
+ * kernel itself).  Used by the training step when the caller does not route the loss through autograd. */
+int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
+                         int R, int D, int K, int reps_per_class, float alpha, float beta, float loss_weight,
+                         float iou_threshold, float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
+                         float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep, float* grad_emb,
+                         float* grad_reps, void* workspace, size_t workspace_bytes, void* stream);
+
 
 /*
  * PLN encoder on tensor cores: emb[R,E] = x[R,F] . W[E,F]^T + bias   (prototype_learning_network.py:133, nn.Linear)

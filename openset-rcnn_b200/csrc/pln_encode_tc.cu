@@ -62,6 +62,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::tf32: D=F32, A=B=TF32 (format 2): the fp32 operands are read from shared memory as they are (the tensor core uses
+// the top 19 bits), so x and W need no cast pass at all.  K per instruction = 8 (32 bytes), K block = 32 floats = 128 bytes.
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr int BK_TF32 = 32;
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -69,6 +73,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -89,6 +102,7 @@ struct EncParams {
   float* mc;               // NVLS multicast mapping of the same buffer (NULL: one P2P store per destination)
 };
 
+template <bool kTf32>   // true: fp32 operands straight from HBM (kind::tf32); false: bf16 copies made by cast_bf16_kernel
 __global__ void __launch_bounds__(kThreads, 1)
     pln_encode_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const __grid_constant__ EncParams p) {
@@ -104,7 +118,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int num_kb = p.F / BK;
+  constexpr int BKe = kTf32 ? BK_TF32 : BK;   // elements per 128-byte K block
+  const int num_kb = p.F / BKe;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -131,8 +146,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t ph = (uint32_t)((kb / STAGES) & 1);
         mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
-        tma_load_2d(sA + s * kStageBytesA, &map_a, &full_bar[s], kb * BK, m0);
-        tma_load_2d(sB + s * kStageBytesB, &map_b, &full_bar[s], kb * BK, n0);
+        tma_load_2d(sA + s * kStageBytesA, &map_a, &full_bar[s], kb * BKe, m0);
+        tma_load_2d(sB + s * kStageBytesB, &map_b, &full_bar[s], kb * BKe, n0);
       }
     }
     __syncwarp();
@@ -148,8 +163,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint64_t bdesc = make_smem_desc(smem_u32(sB + s * kStageBytesB));
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
+          // advance 16 bf16 (or 8 tf32) = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          if (kTf32) umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdescTf32, (kb | k) ? 1u : 0u);
+          else umma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kIdesc, (kb | k) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);                   // stage reusable once these MMAs have read it
         if (kb == num_kb - 1) umma_commit(tmem_full);  // accumulator complete
@@ -242,6 +258,17 @@ EncodeTiledFn encode_fn() {
   }();
   return fn;
 }
+// (rows, K) fp32 row-major -> 2-D map, box {32, 128} (= 128 bytes x 128 rows), 128-byte swizzle
+int encode_f32_map(CUtensorMap* map, const void* ptr, int rows, int K) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return 0;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {BK_TF32, BM};
+  cuuint32_t es[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // (rows, K) bf16 row-major -> 2-D map, box {64, 128}, 128-byte swizzle
 int encode_bf16_map(CUtensorMap* map, void* ptr, int rows, int K) {
   EncodeTiledFn fn = encode_fn();
@@ -300,26 +327,37 @@ static int encode_launch(const float* x, const float* W, const float* bias, int 
     return osr::fail_arg(OSR_E_ARG, "pln_encode: x / W / emb must be 16-byte and workspace 256-byte aligned");
   if (workspace_bytes < osr_pln_encode_workspace(R, F, E)) return osr::fail_arg(OSR_E_WORKSPACE, "pln_encode: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(workspace);
-  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(static_cast<unsigned char*>(workspace) + osr::align256((size_t)R * F * 2));
-  const int64_t nx4 = (int64_t)R * F / 4, nw4 = (int64_t)E * F / 4;
-  cast_bf16_kernel<<<(int)((nx4 + 255) / 256 < 1184 ? (nx4 + 255) / 256 : 1184), 256, 0, s>>>(x, xb, nx4);
-  OSR_LAUNCH_CHECK();
-  cast_bf16_kernel<<<(int)((nw4 + 255) / 256 < 1184 ? (nw4 + 255) / 256 : 1184), 256, 0, s>>>(W, wb, nw4);
-  OSR_LAUNCH_CHECK();
+  const bool tf32 = osr::tuning(osr::kTunePlnVariant) != 1;   // default: fp32 operands through kind::tf32, no cast passes
   CUtensorMap ma, mb;
   memset(&ma, 0, sizeof(ma));
   memset(&mb, 0, sizeof(mb));
-  if (!encode_bf16_map(&ma, xb, R, F) || !encode_bf16_map(&mb, wb, E, F))
-    return osr::fail_arg(OSR_E_ARG, "pln_encode: cuTensorMapEncodeTiled failed");
+  if (tf32) {
+    if (!encode_f32_map(&ma, x, R, F) || !encode_f32_map(&mb, W, E, F))
+      return osr::fail_arg(OSR_E_ARG, "pln_encode: cuTensorMapEncodeTiled failed");
+  } else {
+    __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(workspace);
+    __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(static_cast<unsigned char*>(workspace) + osr::align256((size_t)R * F * 2));
+    const int64_t nx4 = (int64_t)R * F / 4, nw4 = (int64_t)E * F / 4;
+    cast_bf16_kernel<<<(int)((nx4 + 255) / 256 < 1184 ? (nx4 + 255) / 256 : 1184), 256, 0, s>>>(x, xb, nx4);
+    OSR_LAUNCH_CHECK();
+    cast_bf16_kernel<<<(int)((nw4 + 255) / 256 < 1184 ? (nw4 + 255) / 256 : 1184), 256, 0, s>>>(W, wb, nw4);
+    OSR_LAUNCH_CHECK();
+    if (!encode_bf16_map(&ma, xb, R, F) || !encode_bf16_map(&mb, wb, E, F))
+      return osr::fail_arg(OSR_E_ARG, "pln_encode: cuTensorMapEncodeTiled failed");
+  }
   EncParams p;
   p.bias = bias; p.emb = emb; p.R = R; p.F = F; p.E = E;
   p.num_outs = num_outs; p.row_off = row_off; p.mc = mc;
   for (int d = 0; d < kMaxPeers; ++d) p.outs[d] = d < num_outs ? outs[d] : nullptr;
   for (int d = 0; d < num_outs; ++d)
     if (reinterpret_cast<uintptr_t>(outs[d]) & 15) return osr::fail_arg(OSR_E_ARG, "pln_encode: output buffers must be 16-byte aligned");
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_encode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  pln_encode_tc_kernel<<<dim3(osr::ceil_div(R, BM), E / BN), kThreads, kSmemBytes, s>>>(ma, mb, p);
+  if (tf32) {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_encode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    pln_encode_tc_kernel<true><<<dim3(osr::ceil_div(R, BM), E / BN), kThreads, kSmemBytes, s>>>(ma, mb, p);
+  } else {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_encode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    pln_encode_tc_kernel<false><<<dim3(osr::ceil_div(R, BM), E / BN), kThreads, kSmemBytes, s>>>(ma, mb, p);
+  }
   OSR_LAUNCH_CHECK();
   return 0;
 }

@@ -68,6 +68,9 @@ __device__ __forceinline__ void load_unit_reps(const PlnParams& p, float* rh, fl
   }
 }
 
+// kGrad: also write d loss / d emb of every row (the closed form of pln_grad_emb_kernel, same arithmetic, fused here so the
+// forward + backward of the loss is one pass over the embeddings: osr_pln_loss_fwd_bwd)
+template <bool kGrad>
 __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constant__ PlnParams p) {
   extern __shared__ __align__(16) float rh[];  // (Kr, D)
   __shared__ float s_part[kWarps][2];
@@ -88,15 +91,20 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
         p.intra_rep[i] = -1;
         p.inter_rep[i] = -1;
       }
+      if (kGrad) {
+        float* go = p.grad_emb + (int64_t)i * p.D;
+        for (int d = lane; d < p.D; d += 32) go[d] = 0.f;
+      }
       continue;
     }
     // unit embedding, 8 dims per lane (D == 256) or strided in general
-    float e[kMaxD / 32];
+    float e[kMaxD / 32], eraw[kMaxD / 32];
     float ss = 0.f;
 #pragma unroll
     for (int q = 0; q < kMaxD / 32; ++q) {
       const int d = q * 32 + lane;
       e[q] = (d < p.D) ? __ldg(p.emb + (int64_t)i * p.D + d) : 0.f;
+      eraw[q] = e[q];
       ss = fmaf(e[q], e[q], ss);
     }
     ss = warp_sum(ss);
@@ -140,6 +148,38 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
       p.emb_inv_norm[i] = 1.0f / denom;
       p.intra_rep[i] = intra_on ? intra_j : -1;
       p.inter_rep[i] = inter_on ? inter_j : -1;
+    }
+    if (kGrad) {   // pln_grad_emb_kernel's row, with the values already in registers
+      const int ja = intra_on ? intra_j : -1, jb = inter_on ? inter_j : -1;
+      float* go = p.grad_emb + (int64_t)i * p.D;
+      if (ja < 0 && jb < 0) {
+        for (int d = lane; d < p.D; d += 32) go[d] = 0.f;
+      } else {
+        const float inv = 1.0f / denom;
+        const float sc = __ldg(p.grad_loss) * p.loss_weight / fmaxf(p.r_norm, 1.0f);
+        float eh[kMaxD / 32], g[kMaxD / 32];
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < kMaxD / 32; ++q) {
+          const int d = q * 32 + lane;
+          eh[q] = 0.f; g[q] = 0.f;
+          if (d < p.D) {
+            eh[q] = eraw[q] * inv;
+            float t = 0.f;
+            if (ja >= 0) t -= rh[ja * p.D + d];
+            if (jb >= 0) t += rh[jb * p.D + d];
+            g[q] = t;
+            dot = fmaf(eh[q], t, dot);
+          }
+        }
+        dot = warp_sum(dot);
+        const float f = sc * inv;
+#pragma unroll
+        for (int q = 0; q < kMaxD / 32; ++q) {
+          const int d = q * 32 + lane;
+          if (d < p.D) go[d] = f * (g[q] - eh[q] * dot);
+        }
+      }
     }
   }
   if (lane == 0) {
@@ -443,12 +483,51 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
   p.partial = static_cast<float*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.num_ctas = fwd_ctas(R > 0 ? R : 1);   // also launched for R == 0: the separation term does not depend on the rows
-  pln_rows_kernel<<<p.num_ctas, kThreads, smem, s>>>(p);
+  pln_rows_kernel<false><<<p.num_ctas, kThreads, smem, s>>>(p);
   OSR_LAUNCH_CHECK();
   pln_final_kernel<<<1, kThreads, 0, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  return 0;
+}
+
+// Loss forward AND closed-form backward in four launches (rows + d loss / d emb fused, loss reduction, prototype-gradient
+// partials, prototype-gradient final) instead of five plus the autograd plumbing: the training step's S5.
+int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
+                         int R, int D, int K, int reps_per_class, float alpha, float beta, float loss_weight,
+                         float iou_threshold, float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
+                         float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep, float* grad_emb,
+                         float* grad_reps, void* workspace, size_t workspace_bytes, void* stream) {
+  osr::DeviceGuard device_guard(grad_reps);
+  int rc = check_shape(R, D, K, reps_per_class);
+  if (rc) return rc;
+  if (!reps || !loss_terms || !rep_inv_norm || !center_rep || !workspace || !grad_loss || !grad_reps ||
+      (R > 0 && (!emb || !labels || !ious || !emb_inv_norm || !intra_rep || !inter_rep || !grad_emb)))
+    return osr::fail_arg(OSR_E_ARG, "pln_loss_fwd_bwd: null pointer argument");
+  if (workspace_bytes < osr_pln_workspace(R, D, K, reps_per_class))
+    return osr::fail_arg(OSR_E_WORKSPACE, "pln_loss_fwd_bwd: workspace too small");
+  PlnParams p{};
+  p.emb = emb; p.reps = reps; p.labels = labels; p.ious = ious;
+  p.R = R; p.D = D; p.K = K; p.rpc = reps_per_class; p.Kr = K * reps_per_class;
+  p.alpha = alpha; p.beta = beta; p.loss_weight = loss_weight; p.iou_thr = iou_threshold;
+  p.r_norm = r_norm; p.center_weight = center_weight;
+  p.loss_terms = loss_terms; p.emb_inv_norm = emb_inv_norm; p.rep_inv_norm = rep_inv_norm;
+  p.intra_rep = intra_rep; p.inter_rep = inter_rep; p.center_rep = center_rep;
+  p.grad_loss = grad_loss; p.grad_emb = grad_emb; p.grad_reps = grad_reps;
+  p.partial = static_cast<float*>(workspace);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)p.Kr * D * sizeof(float);
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.num_ctas = fwd_ctas(R > 0 ? R : 1);
+  pln_rows_kernel<true><<<p.num_ctas, kThreads, smem, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  pln_final_kernel<<<1, kThreads, 0, s>>>(p);   // reads the forward partials before the backward partials reuse the workspace
+  OSR_LAUNCH_CHECK();
+  pln_grad_reps_partial<<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
+  OSR_LAUNCH_CHECK();
+  pln_grad_reps_final<<<p.Kr, kThreads, smem, s>>>(p);
   OSR_LAUNCH_CHECK();
   return 0;
 }

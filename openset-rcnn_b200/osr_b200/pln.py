@@ -96,13 +96,48 @@ def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_pe
     """Loss and its closed-form gradients in one call, WITHOUT autograd: ``(loss, d loss / d emb, d loss / d reps)``.
     Same kernels as ``pln_loss_from_emb`` + ``backward()``; used by the device-resident training step (no autograd engine
     hop, capturable in a CUDA graph)."""
-    cfg = (int(num_known_classes), int(reps_per_class), float(alpha), float(beta), float(loss_weight),
-           float(iou_threshold), r_norm, float(center_weight), float(emb_grad_scale))
+    lib = _lib.lib()
+    _lib.require_cuda(emb, reps, labels, ious)
     with torch.no_grad():
-        loss, saved, bcfg = _pln_fwd(emb, reps, labels, ious, cfg)
-        gl = torch.ones(1, dtype=torch.float32, device=loss.device) if grad_loss is None else grad_loss
-        g_emb, g_reps = _pln_bwd(saved, bcfg, gl)
-    return loss, g_emb, g_reps
+        emb_c = emb.detach().contiguous().float()
+        reps_c = reps.detach().contiguous().float()
+        labels_c = labels.contiguous().to(torch.int64)
+        ious_c = ious.contiguous().float()
+        R, D = emb_c.shape
+        K, rpc = int(num_known_classes), int(reps_per_class)
+        Kr = K * rpc
+        dev = emb_c.device
+        assert reps_c.shape == (Kr, D)
+        gl = _ones_scalar(dev) if grad_loss is None else grad_loss.reshape(1).contiguous().float()
+        # one allocation for the small per-row / per-prototype outputs
+        small = torch.empty(4 + R + Kr, dtype=torch.float32, device=dev)
+        terms, emb_inv, rep_inv = small[:4], small[4:4 + R], small[4 + R:]
+        idx = torch.empty(2 * R + Kr, dtype=torch.int32, device=dev)
+        intra, inter, center = idx[:R], idx[R:2 * R], idx[2 * R:]
+        grad_emb = torch.empty_like(emb_c)
+        grad_reps = torch.empty_like(reps_c)
+        ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
+        rn = float(R) if r_norm is None else float(r_norm)
+        rc = lib.osr_pln_loss_fwd_bwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(), gl.data_ptr(),
+                                      R, D, K, rpc, float(alpha), float(beta), float(loss_weight), float(iou_threshold), rn,
+                                      float(center_weight), terms.data_ptr(), emb_inv.data_ptr(), rep_inv.data_ptr(),
+                                      intra.data_ptr(), inter.data_ptr(), center.data_ptr(), grad_emb.data_ptr(),
+                                      grad_reps.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "osr_pln_loss_fwd_bwd")
+        if emb_grad_scale != 1.0:
+            grad_emb = grad_emb * float(emb_grad_scale)
+    return terms[0], grad_emb, grad_reps
+
+
+_ONES = {}
+
+
+def _ones_scalar(dev) -> torch.Tensor:
+    """A cached device scalar 1.0 (the upstream gradient of a loss that is backpropagated directly)."""
+    key = (dev.type, dev.index)
+    if key not in _ONES:
+        _ONES[key] = torch.ones(1, dtype=torch.float32, device=dev)
+    return _ONES[key]
 
 
 class _EncodeTcFn(torch.autograd.Function):
