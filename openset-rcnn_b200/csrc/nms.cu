@@ -19,7 +19,7 @@ namespace {
 constexpr int kSortThreads = 1024;
 constexpr int kMaxSortLen = 16384;
 constexpr int kMaxLen = 65536;
-constexpr int kSweepThreads = 256;
+constexpr int kSweepThreads = 512;
 
 struct NmsParams {
   const float* boxes;
@@ -113,6 +113,12 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const __grid_constant__ Nm
   }
 }
 
+// Suppression sweep of one segment (boxes already in score order).  64 rows are resolved per step from the DIAGONAL mask
+// words (greedy NMS inside the block is a 64-bit recurrence: thread 0 walks only the KEPT rows with ffs), then the kept
+// rows' mask words are OR-ed into the `removed` bit-vector of the later column blocks with a WARP-BALLOT style reduction:
+// a warp owns one column word at a time, lane l loads the words of rows l and l + 32 (if kept) - 64 independent loads in
+// flight per warp instead of a dependent load-OR chain per thread - and __reduce_or_sync folds them.  Same keep set and
+// order as the serial sweep, bit for bit.
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const __grid_constant__ NmsParams p) {
   extern __shared__ __align__(16) unsigned long long removed[];  // [wpr]
   __shared__ unsigned long long diag[64];
@@ -120,7 +126,8 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const __grid_c
   __shared__ int s_count;
   const int s = blockIdx.x;
   const int begin = p.seg_begin[s], len = min(p.seg_len[s], p.max_len);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kSweepWarps = kSweepThreads / 32;
   const int nblk = (len + 63) >> 6;
   for (int w = tid; w < nblk; w += kSweepThreads) removed[w] = 0ull;
   if (tid == 0) s_count = 0;
@@ -133,12 +140,15 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const __grid_c
     if (tid < rows) diag[tid] = mrow[(int64_t)(rb * 64 + tid) * p.wpr + rb];
     __syncthreads();
     if (tid == 0) {
+      const unsigned long long valid = rows == 64 ? ~0ull : ((1ull << rows) - 1ull);
       unsigned long long cur = removed[rb], kept = 0ull;
-      for (int i = 0; i < rows; ++i) {
-        if (!((cur >> i) & 1ull)) {
-          kept |= 1ull << i;
-          cur |= diag[i];
-        }
+      unsigned long long avail = ~cur & valid;
+      while (avail) {                       // visits kept rows only
+        const int i = __ffsll((long long)avail) - 1;
+        kept |= 1ull << i;
+        cur |= diag[i];
+        const unsigned long long above = (i == 63) ? 0ull : (~0ull << (i + 1));
+        avail = ~cur & valid & above;
       }
       s_kept = kept;
     }
@@ -153,16 +163,19 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const __grid_c
       p.keep_idx[begin + pos] = (int64_t)orig;
       if (p.keep_mask) p.keep_mask[begin + orig] = 1;
     }
-    // OR the kept rows' masks into `removed` for the column blocks after rb
-    for (int w = rb + 1 + tid; w < nblk; w += kSweepThreads) {
-      unsigned long long acc = removed[w];
-      unsigned long long k = kept;
-      while (k) {
-        const int i = __ffsll((long long)k) - 1;
-        k &= k - 1;
-        acc |= mrow[(int64_t)(rb * 64 + i) * p.wpr + w];
+    // OR the kept rows' masks into `removed` for the column blocks after rb: one warp per column word
+    if (kept != 0ull) {
+      const bool k0 = (kept >> lane) & 1ull, k1 = (kept >> (lane + 32)) & 1ull;
+      const unsigned long long* r0 = mrow + (int64_t)(rb * 64 + lane) * p.wpr;
+      const unsigned long long* r1 = r0 + (int64_t)32 * p.wpr;
+      for (int w = rb + 1 + warp; w < nblk; w += kSweepWarps) {
+        unsigned long long v = 0ull;
+        if (k0) v = r0[w];
+        if (k1) v |= r1[w];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
       }
-      removed[w] = acc;
     }
     __syncthreads();
     if (tid == 0) s_count = base + __popcll(kept);

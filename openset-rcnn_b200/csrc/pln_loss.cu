@@ -343,7 +343,22 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_c
       if (code[k] != 0) s_rows[pos++] = code[k];
     __syncthreads();
     const int n = s_wcnt[kWarps];
-    for (int q = 0; q < n; ++q) {
+    // four rows per iteration: their loads are independent and issued together (the loop is latency-bound otherwise);
+    // the FMAs keep the row order, so the sum is bit-identical to the one-row-at-a-time loop
+    int q = 0;
+    for (; q + 4 <= n; q += 4) {
+      float x[4], w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = s_rows[q + u];
+        const int i = (c < 0 ? -c : c) - 1;
+        w[u] = p.emb_inv_norm[i] * (c < 0 ? -1.f : 1.f);
+        x[u] = (tid < p.D) ? __ldg(p.emb + (int64_t)i * p.D + tid) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[0] = fmaf(x[u], w[u], acc[0]);
+    }
+    for (; q < n; ++q) {
       const int c = s_rows[q];
       const int i = (c < 0 ? -c : c) - 1;
       const float sg = c < 0 ? -1.f : 1.f;
