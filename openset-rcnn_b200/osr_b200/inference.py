@@ -115,54 +115,98 @@ def _clip(boxes: torch.Tensor, image_size) -> torch.Tensor:
                         boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1)
 
 
+def _nonzero_known_size(mask: torch.Tensor, size: int) -> torch.Tensor:
+    """``mask.nonzero()`` when the number of hits is already known on the host: no device->host sync."""
+    try:
+        return torch.nonzero_static(mask, size=int(size))
+    except (AttributeError, RuntimeError, NotImplementedError):
+        return mask.nonzero()
+
+
 def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, unknown_id: int = 80,
                                  known_score_thresh: float = 0.05, known_nms_thresh: float = 0.5, known_topk: int = 100,
                                  unknown_score_thresh: float = 0.05, unknown_nms_thresh: float = 0.5,
                                  unknown_topk: int = 50, class_id=None) -> List[Instances]:
     """``SoftMaxClassifier.inference(fg_instances)`` (``softmax_classifier.py:287-346``): known detections through the
     linear classifier + softmax + per-class NMS, unknown detections through class-agnostic NMS, unknown first.
-    The classifier GEMM and the softmax stay torch (not on the RoI path); the two per-image NMS loops
-    (``fast_rcnn_inference_single_image_known/unknown``, ``:47-168``) run as ONE segmented NMS call each for the whole
-    batch (``batched_nms_images``: segments = images, torchvision's per-image coordinate trick preserved)."""
+
+    The whole batch is processed at once: the per-image Python loop of the reference (masks, finite filters, clip,
+    threshold, ``nonzero``: ~25 launches and 3 host syncs per image) becomes one pass over the concatenated detections
+    with per-row image ids, and its two per-image NMS loops (``fast_rcnn_inference_single_image_known/unknown``,
+    ``:47-168``) one segmented NMS call each (``batched_nms_images``: segments = images, torchvision's per-image
+    coordinate trick preserved).  Four host reads per batch (known counts, candidate counts, two NMS keep counts).  Only
+    the classifier GEMM + softmax stay per image, on exactly the rows the reference feeds it (a batched GEMM may pick
+    another algorithm and round differently, and the score threshold / NMS order would see it)."""
     from .nms import batched_nms_images
     if not fg_instances:
         return []
+    N = len(fg_instances)
     dev = fg_instances[0].get("scores").device
-    kb, ks, kc, ub, us, uc, has_unknown = [], [], [], [], [], [], []
-    known_masks = [inst.get("pred_classes") != unknown_id for inst in fg_instances]
-    n_known = torch.stack([k.sum() for k in known_masks]).cpu().tolist()   # host sync 1
-    for inst, k, nk in zip(fg_instances, known_masks, n_known):
-        boxes = inst.get("pred_boxes").tensor
-        # the classifier runs per image like the reference (a batched GEMM could round differently)
-        probs = torch.softmax(cls_score(inst.get("features")[k]), dim=-1)
-        b = boxes[k]
-        valid = torch.isfinite(b).all(dim=1) & torch.isfinite(probs).all(dim=1)
-        b, probs = b[valid], probs[valid][:, :-1]
-        b = _clip(b, inst.image_size)
-        inds = (probs > known_score_thresh).nonzero()
-        kb.append(b[inds[:, 0]]); ks.append(probs[inds[:, 0], inds[:, 1]]); kc.append(inds[:, 1])
-        has_unknown.append(nk < len(inst))
-        bu, su = boxes[~k], inst.get("scores")[~k]
-        vu = torch.isfinite(bu).all(dim=1) & torch.isfinite(su)
-        bu, su = _clip(bu[vu], inst.image_size), su[vu]
-        fu = su > unknown_score_thresh
-        ub.append(bu[fu]); us.append(su[fu]); uc.append(torch.zeros(bu[fu].shape[0], dtype=torch.int64, device=dev))
-    keep_k = batched_nms_images(kb, ks, kc, known_nms_thresh, topk_per_image=known_topk)
-    keep_u = batched_nms_images(ub, us, uc, unknown_nms_thresh, topk_per_image=unknown_topk)
+    sizes = [len(x) for x in fg_instances]
+    T = int(sum(sizes))
+    boxes = torch.cat([x.get("pred_boxes").tensor for x in fg_instances], dim=0)
+    scores = torch.cat([x.get("scores") for x in fg_instances], dim=0)
+    pcls = torch.cat([x.get("pred_classes") for x in fg_instances], dim=0)
+    feats = torch.cat([x.get("features") for x in fg_instances], dim=0)
+    img = torch.repeat_interleave(torch.arange(N, device=dev), torch.tensor(sizes, device=dev), output_size=T)
+    hw = torch.tensor([[float(x.image_size[0]), float(x.image_size[1])] for x in fg_instances], device=dev)
+    known = pcls != unknown_id
+    n_known = torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, img, known.long()).cpu().tolist()   # host read 1
+    n_unknown = [s - k for s, k in zip(sizes, n_known)]
+    kidx = _nonzero_known_size(known, sum(n_known))[:, 0]          # image-major, ascending
+    uidx = _nonzero_known_size(~known, sum(n_unknown))[:, 0]
+
+    def clip(b, rows):   # Boxes.clip(image_size) with per-row image sizes
+        h, w = hw[rows, 0], hw[rows, 1]
+        zero = torch.zeros((), device=dev)
+        return torch.stack((torch.minimum(torch.maximum(b[:, 0], zero), w), torch.minimum(torch.maximum(b[:, 1], zero), h),
+                            torch.minimum(torch.maximum(b[:, 2], zero), w), torch.minimum(torch.maximum(b[:, 3], zero), h)), dim=-1)
+
+    # ---- known detections: classifier (per image), finite filter, clip, score threshold -> (row, class) candidates
+    probs_l, o = [], 0
+    for n in range(N):
+        probs_l.append(torch.softmax(cls_score(feats.index_select(0, kidx[o:o + n_known[n]])), dim=-1))
+        o += n_known[n]
+    probs = torch.cat(probs_l, dim=0)
+    kb = boxes.index_select(0, kidx)
+    kimg = img.index_select(0, kidx)
+    valid_k = torch.isfinite(kb).all(dim=1) & torch.isfinite(probs).all(dim=1)
+    cand = valid_k[:, None] & (probs[:, :-1] > known_score_thresh)
+    # ---- unknown detections: finite filter, clip, score threshold
+    ub = boxes.index_select(0, uidx)
+    us = scores.index_select(0, uidx)
+    uimg = img.index_select(0, uidx)
+    keep_u_mask = torch.isfinite(ub).all(dim=1) & torch.isfinite(us) & (us > unknown_score_thresh)
+    cnt = torch.stack((torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, kimg, cand.sum(dim=1)),
+                       torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, uimg, keep_u_mask.long()))).cpu().tolist()   # host read 2
+    cnt_k, cnt_u = cnt
+    inds = _nonzero_known_size(cand, sum(cnt_k))                   # (row, class), row-major = the reference's per-image order
+    kb_c = clip(kb, kimg)
+    c_boxes = kb_c.index_select(0, inds[:, 0])
+    c_scores = probs[inds[:, 0], inds[:, 1]]
+    c_cls = inds[:, 1]
+    usel = _nonzero_known_size(keep_u_mask, sum(cnt_u))[:, 0]
+    u_boxes = clip(ub, uimg).index_select(0, usel)
+    u_scores = us.index_select(0, usel)
+    kb_l, ks_l, kc_l = list(c_boxes.split(cnt_k)), list(c_scores.split(cnt_k)), list(c_cls.split(cnt_k))
+    ub_l, us_l = list(u_boxes.split(cnt_u)), list(u_scores.split(cnt_u))
+    uc_l = [torch.zeros(c, dtype=torch.int64, device=dev) for c in cnt_u]
+    keep_k = batched_nms_images(kb_l, ks_l, kc_l, known_nms_thresh, topk_per_image=known_topk)      # host read 3
+    keep_u = batched_nms_images(ub_l, us_l, uc_l, unknown_nms_thresh, topk_per_image=unknown_topk)  # host read 4
     out = []
     for n, inst in enumerate(fg_instances):
         res = Instances(inst.image_size)
-        kcls = kc[n][keep_k[n]]
+        kcls = kc_l[n][keep_k[n]]
         if class_id is not None:
             kcls = class_id[kcls]
-        if has_unknown[n]:
+        if n_unknown[n] > 0:   # `not known.all()` in the reference
             ucls = (torch.zeros(len(keep_u[n]), device=dev) + unknown_id).long()
-            res.set("pred_boxes", Boxes(torch.cat([ub[n][keep_u[n]], kb[n][keep_k[n]]])))
-            res.set("scores", torch.cat([us[n][keep_u[n]], ks[n][keep_k[n]]]))
+            res.set("pred_boxes", Boxes(torch.cat([ub_l[n][keep_u[n]], kb_l[n][keep_k[n]]])))
+            res.set("scores", torch.cat([us_l[n][keep_u[n]], ks_l[n][keep_k[n]]]))
             res.set("pred_classes", torch.cat([ucls, kcls]))
         else:
-            res.set("pred_boxes", Boxes(kb[n][keep_k[n]]))
-            res.set("scores", ks[n][keep_k[n]])
+            res.set("pred_boxes", Boxes(kb_l[n][keep_k[n]]))
+            res.set("scores", ks_l[n][keep_k[n]])
             res.set("pred_classes", kcls)
         out.append(res)
     return out
