@@ -161,6 +161,12 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
                       int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Layout staging for NCHW callers (the reference's backbone emits NCHW maps): tiled transposes between
+ * (N, C, H*W) and (N, H*W, C) contiguous fp32 buffers.  osr_b200.poolers.ROIPooler uses them to run the channels_last
+ * kernels on NCHW maps (forward: maps in; backward: gradient maps out). */
+int osr_nchw_to_nhwc(const float* src, float* dst, int N, int C, int64_t HW, void* stream);
+int osr_nhwc_to_nchw(const float* src, float* dst, int N, int C, int64_t HW, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3b) Box-head fully connected layers on tensor cores
  * Replaces detectron2 FastRCNNConvFCHead.forward (flatten -> fc1 -> ReLU -> fc2 -> ReLU), called at

@@ -62,6 +62,8 @@ SIGNATURES = {
     "osr_linear_bf16_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_int, C.c_void_p]),
     "osr_cast_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "osr_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    "osr_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     "osr_roi_align_bwd_workspace": (C.c_size_t, [C.POINTER(FeatLevel), C.c_int, C.c_int, C.c_int, C.c_int]),
     "osr_roi_align_bwd": (C.c_int, [
         C.POINTER(FeatLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -52,6 +52,31 @@ def convert_boxes_to_pooler_format(box_lists: List[Boxes]) -> Tuple[torch.Tensor
     return torch.cat([idx[:, None], boxes], dim=1), offsets
 
 
+# NCHW callers (the reference's layout): stage the maps through a tiled transpose and run the channels_last kernels
+# (forward: NCHW -> NHWC copy of each level; backward: the NHWC gradient is transposed back).  2.3 vs 3.0 ms per cfg-2
+# step.  Set to False to run the NCHW-native kernels instead (tests cover both).
+NCHW_STAGING = True
+
+
+def _stage_ok(f: torch.Tensor) -> bool:
+    return f.is_contiguous() and f.shape[1] % 32 == 0 and f.shape[1] <= 256 and not (f.shape[2] == 1 and f.shape[3] == 1)
+
+
+def nchw_to_channels_last(f: torch.Tensor) -> torch.Tensor:
+    """Same logical (N, C, H, W) tensor in channels_last memory, copied by ``osr_nchw_to_nhwc``."""
+    N, C, H, W = f.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=f.device, memory_format=torch.channels_last)
+    _lib.check(_lib.lib().osr_nchw_to_nhwc(f.data_ptr(), out.data_ptr(), N, C, H * W, _lib.stream_ptr(f.device)), "osr_nchw_to_nhwc")
+    return out
+
+
+def channels_last_to_nchw(g: torch.Tensor) -> torch.Tensor:
+    N, C, H, W = g.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.lib().osr_nhwc_to_nchw(g.data_ptr(), out.data_ptr(), N, C, H * W, _lib.stream_ptr(g.device)), "osr_nhwc_to_nchw")
+    return out
+
+
 class _ROIAlignFPN(torch.autograd.Function):
     """(x_0..x_{L-1}) -> (M, C, P, P); backward writes one dense gradient per level."""
 
@@ -59,7 +84,9 @@ class _ROIAlignFPN(torch.autograd.Function):
     def forward(ctx, rois, offsets, cfg, *feats):
         lib = _lib.lib()
         scales, P, sampling_ratio, canon_size, canon_level, min_level = cfg
-        arr, N, C = _feat_levels(feats, scales)
+        ctx.staged = bool(NCHW_STAGING and all(f.dtype == torch.float32 and _stage_ok(f) for f in feats))
+        src = [nchw_to_channels_last(f) for f in feats] if ctx.staged else feats
+        arr, N, C = _feat_levels(src, scales)
         M = rois.shape[0]
         dev = feats[0].device
         out = torch.empty((M, C, P, P), dtype=torch.float32, device=dev)
@@ -79,7 +106,11 @@ class _ROIAlignFPN(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_lvl):
         rois, offsets = ctx.saved_tensors
-        grads = roi_align_backward(grad_out, rois, offsets, ctx.shapes, ctx.channels_last, ctx.cfg)
+        if ctx.staged:   # gradients through the channels_last kernel, handed back in the caller's NCHW layout
+            grads = roi_align_backward(grad_out, rois, offsets, ctx.shapes, [True] * len(ctx.shapes), ctx.cfg)
+            grads = [channels_last_to_nchw(g) for g in grads]
+        else:
+            grads = roi_align_backward(grad_out, rois, offsets, ctx.shapes, ctx.channels_last, ctx.cfg)
         return (None, None, None) + tuple(grads)
 
 
@@ -186,4 +217,8 @@ class ROIPooler(torch.nn.Module):
     def backward_rois(self, grad_pooled: torch.Tensor, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor):
         """Gradient of ``pool_rois`` w.r.t. the maps ``x`` (only their shapes / layouts are read), without autograd."""
         cl = [f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous() for f in x]
+        if NCHW_STAGING and all(_stage_ok(f) for f in x):
+            grads = roi_align_backward(grad_pooled, rois.contiguous().float(), offsets, [tuple(f.shape) for f in x],
+                                       [True] * len(x), self._cfg())
+            return [channels_last_to_nchw(g) for g in grads]
         return roi_align_backward(grad_pooled, rois.contiguous().float(), offsets, [tuple(f.shape) for f in x], cl, self._cfg())

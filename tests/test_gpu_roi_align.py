@@ -24,6 +24,17 @@ def bwd_variant(request):
     _lib.set_tuning("bwd", prev)
 
 
+@pytest.fixture(params=[True, False], ids=["nchw_staged", "nchw_native"])
+def nchw_staging(request):
+    """NCHW maps either go through the tiled NCHW->NHWC staging copy + the channels_last kernels (default) or through the
+    NCHW-native kernels (``poolers.NCHW_STAGING = False``); the staging path only engages for C % 32 == 0."""
+    from osr_b200 import poolers
+    prev = poolers.NCHW_STAGING
+    poolers.NCHW_STAGING = request.param
+    yield request.param
+    poolers.NCHW_STAGING = prev
+
+
 def _pooler_pair():
     from osr_b200.poolers import ROIPooler
     from osr_b200 import synth
@@ -45,7 +56,7 @@ def _special_rois(h, w):
 
 
 @pytest.mark.parametrize("hw,n,per_img,C", [((800, 1333), 2, 300, 256), ((320, 480), 3, 200, 64), ((224, 224), 1, 64, 40)])
-def test_forward_matches_torchvision(hw, n, per_img, C):
+def test_forward_matches_torchvision(hw, n, per_img, C, nchw_staging):
     from osr_b200 import synth
     ours, ref = _pooler_pair()
     feats = synth.make_features(n, hw, C, seed=3, device="cuda:0")
@@ -127,7 +138,7 @@ def _grads(pooler, feats, box_lists, gout):
 
 
 @pytest.mark.parametrize("hw,n,per_img,C", [((800, 1333), 2, 256, 64), ((320, 480), 3, 200, 48), ((224, 224), 1, 64, 20)])
-def test_backward_matches_torchvision_autograd(hw, n, per_img, C):
+def test_backward_matches_torchvision_autograd(hw, n, per_img, C, nchw_staging):
     from osr_b200 import synth
     ours, ref = _pooler_pair()
     feats = synth.make_features(n, hw, C, seed=4, device="cuda:0")
@@ -302,3 +313,26 @@ def test_channels_last_width_sweep_stage_geometry(bwd_variant):
     for a, b in zip(_grads(ours, feats, boxes, gout), _grads(ref, [f.contiguous() for f in feats], boxes, gout)):
         scale = max(1.0, float(b.abs().max()))
         torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
+
+
+def test_nchw_staging_equals_channels_last_path_exactly():
+    """NCHW maps staged through osr_nchw_to_nhwc / osr_nhwc_to_nchw run the SAME kernels on the same values as
+    channels_last maps: outputs and gradients are bit-identical, gradients come back NCHW-contiguous."""
+    from osr_b200 import poolers, synth
+    ours, _ = _pooler_pair()
+    assert poolers.NCHW_STAGING
+    feats = synth.make_features(2, (320, 480), 64, seed=21, device="cuda:0")            # NCHW
+    feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    for f in feats:
+        assert torch.equal(poolers.nchw_to_channels_last(f), f) and poolers.nchw_to_channels_last(f).is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(poolers.channels_last_to_nchw(f.contiguous(memory_format=torch.channels_last)), f)
+    rois = synth.make_rois(2, 120, (320, 480), seed=23)
+    boxes = [OBoxes(r.cuda()) for r in rois]
+    gout = torch.randn(240, 64, 7, 7, device="cuda:0")
+    a = ours.forward([f.clone().requires_grad_(True) for f in feats], boxes)
+    b = ours.forward([f.clone().requires_grad_(True) for f in feats_cl], boxes)
+    assert torch.equal(a, b)
+    ga = _grads(ours, feats, boxes, gout)
+    gb = _grads(ours, feats_cl, boxes, gout)
+    for x, y in zip(ga, gb):
+        assert x.is_contiguous() and torch.equal(x, y)
