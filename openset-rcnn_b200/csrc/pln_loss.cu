@@ -19,7 +19,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxD = 256;   // embedding dim handled: D == 256 fast layout (8 floats per lane), checked on host
-constexpr int kMaxReps = 64; // K * reps_per_class
+constexpr int kMaxReps = 160; // K * reps_per_class (28 classes x 5 representatives = 140: 140 KB of unit prototypes in shared memory)
 constexpr int kSeg = 8;      // row segments of the grad_reps partial reduction
 constexpr float kEps = 1e-12f;
 

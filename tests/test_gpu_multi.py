@@ -54,3 +54,39 @@ def test_encode_gather_epilogue_on_one_gpu(world, rank):
     assert lib.osr_pln_encode_gather_fwd(pi.roi_features.data_ptr(), pi.enc_w.data_ptr(), None, R, Fd, E,
                                          ctypes.cast(ptrs, ctypes.c_void_p), world, world, 0, ws.data_ptr(), ws.numel(),
                                          _lib.stream_ptr(dev)) < 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_ops_on_a_non_current_device():
+    """Tensors on cuda:1 while the current device is cuda:0: every entry point launches on the device that owns its
+    output pointer (osr::DeviceGuard) and the caller's current device is restored."""
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb
+    from osr_b200.poolers import ROIPooler
+    from osr_b200.proposals import rpn_select_decode
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:1")
+    ho = synth.make_head_outputs(2, (320, 480), seed=3, device=dev)
+    sel = rpn_select_decode(ho.anchors, ho.deltas, ho.centerness, ho.image_sizes, 300)
+    ref = rpn_select_decode([a.to("cuda:0") for a in ho.anchors], [d.to("cuda:0") for d in ho.deltas],
+                            [c.to("cuda:0") for c in ho.centerness], ho.image_sizes, 300)
+    assert sel.boxes.device == dev and torch.equal(sel.counts.cpu(), ref.counts.cpu())
+    L = sel.num_levels
+    for n in range(2):
+        k = int(sel.counts[n, L])
+        assert torch.equal(sel.boxes[n, :k].cpu(), ref.boxes[n, :k].cpu())
+    feats = synth.make_features(2, (320, 480), 64, seed=4, device=dev, channels_last=True)
+    rois = [r.to(dev) for r in synth.make_rois(2, 50, (320, 480), seed=5)]
+    pooler = ROIPooler(7, synth.POOL_SCALES, 0, "ROIAlignV2")
+    from oracle.structures import Boxes as OBoxes
+    fg = [f.requires_grad_(True) for f in feats]
+    out = pooler(fg, [OBoxes(r) for r in rois])
+    out0 = pooler([f.detach().to("cuda:0") for f in feats], [OBoxes(r.to("cuda:0")) for r in rois])
+    assert torch.equal(out.detach().cpu(), out0.cpu())
+    g = torch.autograd.grad(out, fg, torch.ones_like(out))
+    assert all(x.device == dev and torch.isfinite(x).all() for x in g)
+    pi = synth.make_pln_inputs(256, seed=6, device=dev)
+    emb = (pi.roi_features @ pi.enc_w.t()).requires_grad_(True)
+    loss = pln_loss_from_emb(emb, pi.reps.clone().requires_grad_(True), pi.gt_classes, pi.ious, num_known_classes=20)
+    loss.backward()
+    assert loss.device == dev and torch.cuda.current_device() == 0

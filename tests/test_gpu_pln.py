@@ -14,15 +14,23 @@ def _kw(K=20, alpha=0.1, beta=0.9, w=0.5):
     return dict(num_known_classes=K, alpha=alpha, beta=beta, loss_weight=w, iou_threshold=0.5)
 
 
-def _margin_mask(emb, reps, labels, ious, K, alpha, beta):
+def _margin_mask(emb, reps, labels, ious, K, alpha, beta, rpc=1):
     eh = torch.nn.functional.normalize(emb); rh = torch.nn.functional.normalize(reps)
     d = 1 - eh @ rh.t()
+    if rpc > 1:   # class distance = min over the class's representatives; also require a clear arg-min inside each class
+        d3 = d.reshape(-1, K, rpc)
+        top2 = torch.topk(d3, 2, dim=2, largest=False).values
+        clear = ((top2[:, :, 1] - top2[:, :, 0]) > 1e-5).all(dim=1)
+        d = d3.min(dim=2)[0]
+    else:
+        clear = torch.ones(d.shape[0], dtype=torch.bool, device=d.device)
     fg = (labels >= 0) & (labels < K) & (ious > 0.5)
     y = labels.clamp(0, K - 1)
     intra = d.gather(1, y[:, None])[:, 0]
     dm = d.clone(); dm.scatter_(1, y[:, None], 1000.0)
     inter = dm.min(1)[0]
-    safe = ((intra - alpha).abs() > 1e-5) & ((beta - inter).abs() > 1e-5)
+    dm2 = torch.topk(dm, 2, dim=1, largest=False).values
+    safe = ((intra - alpha).abs() > 1e-5) & ((beta - inter).abs() > 1e-5) & ((dm2[:, 1] - dm2[:, 0]) > 1e-5) & clear
     return safe | ~fg
 
 
@@ -43,11 +51,41 @@ def test_loss_and_gradients_match_oracle(R, K, alpha, beta, w):
     safe = _margin_mask(emb0, pi.reps, pi.gt_classes, pi.ious, K, alpha, beta)
     assert safe.float().mean() > 0.99
     torch.testing.assert_close(emb_a.grad[safe], emb_b.grad[safe], rtol=1e-4, atol=1e-7)
-    if bool(safe.all()):
-        torch.testing.assert_close(reps_a.grad, reps_b.grad, rtol=1e-4, atol=1e-6)
+    # prototype gradient: ALWAYS checked - rows within 1e-5 of a hinge threshold (where a flipped hinge is a discontinuity,
+    # not an error) are taken out of the foreground in BOTH implementations by zeroing their IoU
+    ious2 = torch.where(safe, pi.ious, torch.zeros_like(pi.ious))
+    ra = pi.reps.clone().requires_grad_(True); rb = pi.reps.clone().requires_grad_(True)
+    pln_loss_from_emb(emb0, ra, pi.gt_classes, ious2, **kw).backward()
+    opln.pln_loss_from_emb(emb0, rb, pi.gt_classes, ious2, **kw).backward()
+    torch.testing.assert_close(ra.grad, rb.grad, rtol=1e-4, atol=1e-6)
     # CPU oracle too
     lc = opln.pln_loss_from_emb(emb0.cpu(), pi.reps.cpu(), pi.gt_classes.cpu(), pi.ious.cpu(), **kw)
     torch.testing.assert_close(la.cpu(), lc, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("rpc,D", [(2, 256), (5, 256), (1, 64), (2, 128), (5, 64)])
+def test_reps_per_class_and_small_embedding_dims(rpc, D):
+    """REPS_PER_CLASS > 1 (min over a class's representatives, `prototype_learning_network.py:164`) and EMD_DIM < 256:
+    loss and both gradients against the autograd oracle (same neutralisation of near-threshold rows as above)."""
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb
+    K, R = 20, 1500
+    pi = synth.make_pln_inputs(R, emb_dim=D, num_known=K, seed=rpc * 100 + D, device="cuda:0")
+    g = torch.Generator("cuda:0").manual_seed(rpc + D)
+    reps0 = torch.randn(K * rpc, D, device="cuda:0", generator=g)
+    emb0 = (pi.roi_features @ pi.enc_w.t()).detach()
+    kw = dict(_kw(K), reps_per_class=rpc)
+    safe = _margin_mask(emb0, reps0, pi.gt_classes, pi.ious, K, 0.1, 0.9, rpc)
+    assert safe.float().mean() > 0.98
+    ious2 = torch.where(safe, pi.ious, torch.zeros_like(pi.ious))
+    ea = emb0.clone().requires_grad_(True); ra = reps0.clone().requires_grad_(True)
+    eb = emb0.clone().requires_grad_(True); rb = reps0.clone().requires_grad_(True)
+    la = pln_loss_from_emb(ea, ra, pi.gt_classes, ious2, **kw)
+    lb = opln.pln_loss_from_emb(eb, rb, pi.gt_classes, ious2, **kw)
+    la.backward(); lb.backward()
+    torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(ea.grad, eb.grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(ra.grad, rb.grad, rtol=1e-4, atol=1e-6)
 
 
 def test_no_foreground_rows_only_center_term():
