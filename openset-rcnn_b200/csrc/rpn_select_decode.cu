@@ -32,6 +32,10 @@ struct RpnParams {
   int ktop[OSR_MAX_LEVELS];
   int num_levels, num_images, kmax;
   int slice_cap;  // keys per CTA the shared-memory carve-up can hold
+  // cluster packing: a level whose slice fits in fewer CTAs shares its 8-CTA cluster between 8 / split images, so small
+  // levels do not burn whole clusters (800x1333: 26 clusters = 208 CTAs = ONE wave on 148 SMs, instead of 80 = 640 = three)
+  int split[OSR_MAX_LEVELS];          // CTAs that share one (image, level) segment: 8, 4, 2 or 1
+  int cl_base[OSR_MAX_LEVELS + 1];    // first cluster id of each level
   int kpad;       // candidate-buffer capacity (power of two >= max k)
   float min_box_size;
   const int32_t* image_hw;
@@ -86,10 +90,17 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
     rpn_select_decode_kernel(const __grid_constant__ RpnParams p) {
   cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
+  const int crank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kCluster;
-  const int level = cid / p.num_images;  // big (fine) levels first
-  const int n = cid - level * p.num_images;
+  int level = 0;   // big (fine) levels first
+  while (level + 1 < p.num_levels && cid >= p.cl_base[level + 1]) ++level;
+  const int split = p.split[level];             // CTAs sharing this segment
+  const int seg = crank / split;                // segment of this cluster the CTA works on
+  const int rank = crank - seg * split;         // rank inside the segment's CTA group
+  const int base_rank = seg * split;            // cluster rank of the group's first CTA (owner of the candidate buffer)
+  const int n_raw = (cid - p.cl_base[level]) * (kCluster / split) + seg;
+  const bool active = n_raw < p.num_images;     // the last cluster of a level may have idle groups: they join every
+  const int n = active ? n_raw : 0;             //   cluster.sync with an empty slice and leave before the decode
   const osr_rpn_level_t& L = p.lv[level];
   const int S = (int)L.num_anchors;
   const int k = p.ktop[level];
@@ -103,9 +114,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
   uint32_t* misc = total + kBins;       // [64]
 
   // ---- slice of this CTA -------------------------------------------------------------------------
-  const int per = osr::round_up(osr::ceil_div(S, kCluster), 4);
+  const int per = osr::round_up(osr::ceil_div(S, split), 4);
   const int begin = min(S, rank * per);
-  const int len = min(S, begin + per) - begin;
+  const int len = active ? min(S, begin + per) - begin : 0;
 
   {
     const float* sp = L.scores + (int64_t)n * L.score_stride_n;
@@ -150,8 +161,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
       cluster.sync();
       if (tid < kBins) {
         uint32_t s = 0;
-#pragma unroll
-        for (int r = 0; r < kCluster; ++r) s += cluster.map_shared_rank(h, r)[tid];
+        for (int r = 0; r < split; ++r) s += cluster.map_shared_rank(h, base_rank + r)[tid];
         total[tid] = s;
       }
       __syncthreads();
@@ -208,9 +218,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
   }
   cluster.sync();
   uint32_t base_gt = 0, base_eq = 0, total_gt = 0;
-#pragma unroll
-  for (int r = 0; r < kCluster; ++r) {
-    const uint32_t* rm = cluster.map_shared_rank(misc, r);
+  for (int r = 0; r < split; ++r) {
+    const uint32_t* rm = cluster.map_shared_rank(misc, base_rank + r);
     uint32_t g = rm[2], e = rm[3];
     if (r < rank) {
       base_gt += g;
@@ -219,7 +228,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
     total_gt += g;
   }
   {
-    unsigned long long* cand0 = cluster.map_shared_rank(cand, 0);
+    unsigned long long* cand0 = cluster.map_shared_rank(cand, base_rank);
     uint32_t pg = base_gt + (pre & 0xffffu), pe = base_eq + (pre >> 16);
     for (int i = i0; i < i1; ++i) {
       uint32_t key = keys[i];
@@ -233,9 +242,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
     }
   }
   cluster.sync();
-  if (rank != 0) return;
+  if (rank != 0 || !active) return;
 
-  // ---- rank 0: sort the k survivors -----------------------------------------------------------------
+  // ---- rank 0 of the group: sort the k survivors -----------------------------------------------------------------
   int kp = 32;
   while (kp < k) kp <<= 1;
   for (int i = k + tid; i < kp; i += kThreads) cand[i] = 0ull;
@@ -381,6 +390,17 @@ int fill_params(RpnParams& p, const osr_rpn_level_t* h_levels, int num_levels, i
   p.kmax = off;
   p.kpad = osr::next_pow2(kmaxlvl < 32 ? 32 : kmaxlvl);
   p.slice_cap = cap;
+  // cluster packing: the fewest CTAs per segment whose slice still fits the carve-up sized for the largest level
+  int base = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int S = (int)h_levels[l].num_anchors;
+    int split = kCluster;
+    while (split > 1 && osr::round_up(osr::ceil_div(S, split / 2), 4) <= cap) split /= 2;
+    p.split[l] = split;
+    p.cl_base[l] = base;
+    base += osr::ceil_div(num_images, kCluster / split);
+  }
+  p.cl_base[num_levels] = base;
   return 0;
 }
 
@@ -444,7 +464,7 @@ int osr_rpn_select_decode(const osr_rpn_level_t* h_levels, int num_levels, int n
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   OSR_CUDA_CHECK(cudaFuncSetAttribute(rpn_select_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rpn_select_decode_kernel<<<num_images * num_levels * kCluster, kThreads, smem, s>>>(p);
+  rpn_select_decode_kernel<<<p.cl_base[num_levels] * kCluster, kThreads, smem, s>>>(p);
   OSR_LAUNCH_CHECK();
   rpn_concat_kernel<<<dim3(num_images, kConcatY), 256, 0, s>>>(p, out_boxes, out_scores, out_level, out_index);
   OSR_LAUNCH_CHECK();
