@@ -502,49 +502,59 @@ struct __align__(16) ClSmem {
 static_assert((kCNB * kCH + kCThreads) * 8 <= kCWarps * kGBlk, "table scratch must fit in the staging buffers");
 
 
+// Scan the image's RoI indices from `pos` in order and keep the first kCNB that hit the tile (level + footprint box):
+// S.nb = how many, S.next_pos = where the next batch resumes (r1 when the image is exhausted).  The scan advances in
+// windows of 4 x kCThreads indices and keeps going until the batch is full - an image with more RoIs than one window
+// (1024 per image at cfg 5) must not split the few RoIs of a tile over several batches.
 template <class SM>
 __device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level, int tx0, int ty0, int pos, int r1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int hit[4], cnt = 0;
+  if (tid == 0) S.next_pos = r1;
+  int filled = 0;
+  for (int cur = pos; cur < r1 && filled < kCNB; cur += 4 * kCThreads) {
+    int hit[4], cnt = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int m = pos + tid * 4 + k;
-    hit[k] = 0;
-    if (m < r1) {
-      const RoiInfo r = load_info(p.info + m);
-      hit[k] = (r.level == level) && (r.x0 <= tx0 + kCW - 1) && (r.x1 >= tx0) && (r.y0 <= ty0 + kCH - 1) && (r.y1 >= ty0);
+    for (int k = 0; k < 4; ++k) {
+      const int m = cur + tid * 4 + k;
+      hit[k] = 0;
+      if (m < r1) {
+        const RoiInfo r = load_info(p.info + m);
+        hit[k] = (r.level == level) && (r.x0 <= tx0 + kCW - 1) && (r.x1 >= tx0) && (r.y0 <= ty0 + kCH - 1) && (r.y1 >= ty0);
+      }
+      cnt += hit[k];
     }
-    cnt += hit[k];
-  }
-  int inc = cnt;
+    int inc = cnt;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) S.warp_cnt[warp] = inc;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int w = 0; w < kCWarps; ++w) {
-      int c = S.warp_cnt[w];
-      S.warp_cnt[w] = run;
-      run += c;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    S.nb = min(run, kCNB);
-    S.next_pos = min(pos + 4 * kCThreads, r1);
-  }
-  __syncthreads();
-  int rank = S.warp_cnt[warp] + inc - cnt;
+    if (lane == 31) S.warp_cnt[warp] = inc;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int w = 0; w < kCWarps; ++w) {
+        int c = S.warp_cnt[w];
+        S.warp_cnt[w] = run;
+        run += c;
+      }
+      S.warp_cnt[kCWarps] = run;
+    }
+    __syncthreads();
+    int rank = filled + S.warp_cnt[warp] + inc - cnt;
+    filled += S.warp_cnt[kCWarps];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (hit[k]) {
-      const int m = pos + tid * 4 + k;
-      if (rank < kCNB) S.e[rank].m = m;
-      else if (rank == kCNB) S.next_pos = m;
-      ++rank;
+    for (int k = 0; k < 4; ++k) {
+      if (hit[k]) {
+        const int m = cur + tid * 4 + k;
+        if (rank < kCNB) S.e[rank].m = m;
+        else if (rank == kCNB) S.next_pos = m;   // the first hit that did not fit: the next batch resumes here
+        ++rank;
+      }
     }
+    __syncthreads();   // warp_cnt is rewritten by the next window
   }
+  if (tid == 0) S.nb = min(filled, kCNB);
   __syncthreads();
 }
 
@@ -1112,10 +1122,28 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
           continue;
         }
         float2 acc[kCT / 2][kCW];   // acc[q][x] = rows (2q, 2q+1) of column x
+        float* gp = gimg + (int64_t)ys * sH + (int64_t)tx0 * sW + lane;
+        const bool interior = (ncol == kCW) && (ny == kCT);
+        if (first) {
 #pragma unroll
-        for (int q = 0; q < kCT / 2; ++q)
+          for (int q = 0; q < kCT / 2; ++q)
 #pragma unroll
-          for (int x = 0; x < kCW; ++x) acc[q][x] = make_float2(0.f, 0.f);
+            for (int x = 0; x < kCW; ++x) acc[q][x] = make_float2(0.f, 0.f);
+        } else {
+          // a later batch of a dense tile CONTINUES the sums of the earlier batches: the 64 partial sums are loaded up
+          // front (independent loads, one latency) instead of a load-add-store chain per pixel at write-out - and the
+          // result is what one batch holding all the RoIs would have produced
+#pragma unroll
+          for (int q = 0; q < kCT / 2; ++q) {
+#pragma unroll
+            for (int x = 0; x < kCW; ++x) {
+              const bool okx = interior || (x < ncol);
+              const float* g0 = gp + (int64_t)(2 * q) * sH + (int64_t)x * sW;
+              acc[q][x].x = (okx && (interior || 2 * q < ny)) ? __ldcg(g0) : 0.f;
+              acc[q][x].y = (okx && (interior || 2 * q + 1 < ny)) ? __ldcg(g0 + sH) : 0.f;
+            }
+          }
+        }
         while (m != 0) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
@@ -1163,8 +1191,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
           }
         }
         // write-out straight from registers: one 128-byte row segment (32 channels of one pixel) per store instruction
-        float* gp = gimg + (int64_t)ys * sH + (int64_t)tx0 * sW + lane;
-        if (first && ncol == kCW && ny == kCT) {   // interior tile, first batch: 64 unconditional stores
+        if (interior) {   // interior tile: 64 unconditional stores
 #pragma unroll
           for (int q = 0; q < kCT / 2; ++q) {
             float* g0 = gp + (int64_t)(2 * q) * sH;
@@ -1184,11 +1211,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
               if (r < ny) {
 #pragma unroll
                 for (int x = 0; x < kCW; ++x) {
-                  if (x < ncol) {
-                    float* dst = gp + (int64_t)r * sH + (int64_t)x * sW;
-                    const float v = h ? acc[q][x].y : acc[q][x].x;
-                    *dst = first ? v : (*dst + v);
-                  }
+                  if (x < ncol) gp[(int64_t)r * sH + (int64_t)x * sW] = h ? acc[q][x].y : acc[q][x].x;
                 }
               }
             }

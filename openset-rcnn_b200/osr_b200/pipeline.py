@@ -63,8 +63,9 @@ def make_config(name: str = "cfg2", world: int = 1, **over) -> PathConfig:
     elif name == "cfg4":  # inference-only: 32 images, k = 1000 / level, NMS -> 1000 proposals / image
         cfg = PathConfig(name=name, num_images=32, pre_nms_topk=1000, post_nms_topk=1000)
     elif name == "cfg5":  # stress: 1333x1333, k = 4000 / level, 1024 RoIs / image, 128 images over the GPUs
-        cfg = PathConfig(name=name, num_images=max(1, 128 // max(world, 1)), image_hw=(1333, 1333), pre_nms_topk=4000,
-                         rois_per_image=1024)
+        # (the configuration is defined for 2 / 4 / 8 GPUs: 64 / 32 / 16 images per GPU; one GPU runs the 8-GPU share)
+        cfg = PathConfig(name=name, num_images=max(1, 128 // max(world, 1)) if world > 1 else 16, image_hw=(1333, 1333),
+                         pre_nms_topk=4000, rois_per_image=1024)
     else:
         raise ValueError(f"unknown config {name!r} (cfg2 | cfg3 | cfg4 | cfg5)")
     for k, v in over.items():

@@ -201,6 +201,24 @@ def test_backward_dense_tile_more_than_64_rois():
         torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
 
 
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_backward_more_rois_per_image_than_one_scan_window(channels_last):
+    """1300 RoIs per image (cfg 5 has 1024): the tile kernels collect a batch over several 512-index scan windows, and
+    dense tiles continue the partial sums of their earlier batches."""
+    from osr_b200 import synth
+    ours, ref = _pooler_pair()
+    feats = synth.make_features(2, (320, 480), 32, seed=19, device="cuda:0", channels_last=channels_last)
+    rois = synth.make_rois(2, 1300, (320, 480), seed=23)
+    boxes = [OBoxes(r.cuda()) for r in rois]
+    gout = torch.randn(2600, 32, 7, 7, device="cuda:0")
+    a1 = _grads(ours, feats, boxes, gout)
+    a2 = _grads(ours, feats, boxes, gout)
+    for a, a_again, b in zip(a1, a2, _grads(ref, feats, boxes, gout)):
+        assert torch.equal(a, a_again)   # deterministic
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
+
+
 def test_backward_empty_rois_gives_zero_grads():
     from osr_b200 import synth
     ours, _ = _pooler_pair()

@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--images", type=int, default=16)
 ap.add_argument("--nchw", action="store_true")
+ap.add_argument("--config", default=None, help="cfg2 | cfg3 | cfg5 (training path shapes of that configuration)")
 ap.add_argument("--infer", action="store_true", help="inference path (cfg 4): nominal proposals + NMS, ROIAlign fwd, post-processing")
 ap.add_argument("--tune", action="append", default=[], help="key=value of an OSR_TUNE_* switch (bwd, fwd, pln, rpn, nms)")
 a = ap.parse_args()
@@ -24,6 +25,9 @@ for kv in a.tune:
 if a.infer:
     from osr_b200.pipeline import InferencePathStep, make_config
     path = InferencePathStep(make_config("cfg4", num_images=a.images, seed=3234), "cuda:0")
+elif a.config:
+    from osr_b200.pipeline import make_config
+    path = RoiPathStep(make_config(a.config, num_images=a.images, channels_last=not a.nchw, seed=3234), "cuda:0")
 else:
     path = RoiPathStep(PathConfig(num_images=a.images, channels_last=not a.nchw, seed=3234), "cuda:0")
 for _ in range(a.steps):
