@@ -509,9 +509,8 @@ static_assert((kCNB * kCH + kCThreads) * 8 <= kCWarps * kGBlk, "table scratch mu
 template <class SM>
 __device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level, int tx0, int ty0, int pos, int r1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) S.next_pos = r1;
-  int filled = 0;
-  for (int cur = pos; cur < r1 && filled < kCNB; cur += 4 * kCThreads) {
+  int filled = 0, cur = pos;
+  for (; cur < r1 && filled < kCNB; cur += 4 * kCThreads) {
     int hit[4], cnt = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -554,7 +553,10 @@ __device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level,
     }
     __syncthreads();   // warp_cnt is rewritten by the next window
   }
-  if (tid == 0) S.nb = min(filled, kCNB);
+  if (tid == 0) {
+    S.nb = min(filled, kCNB);
+    if (filled <= kCNB) S.next_pos = min(cur, r1);   // no hit was left over: resume at the first index not scanned yet
+  }
   __syncthreads();
 }
 

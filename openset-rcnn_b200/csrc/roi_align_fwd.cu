@@ -43,6 +43,8 @@ struct FwdParams {
   float* rec;            // (M, kRecFloats) per-RoI table records written by roi_fwd_prep_kernel, or nullptr
   int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules AND the TMA path is enabled for this call
   int ring_floats;             // floats of the staging ring at the start of dynamic shared memory
+  int* counter;                // persistent NHWC kernel: next unclaimed record (set to the grid size by roi_fwd_prep_kernel)
+  int pers_grid;               // grid size of the persistent NHWC kernel (0: not used)
 };
 
 // TMA staging geometry: a stage holds the WHOLE footprint (<= kTRmax rows x 32 columns) of kTC channels of one image;
@@ -627,12 +629,16 @@ __device__ __forceinline__ float2 f2_fma_s(float2 a, float s, float2 c) { return
 // marked FAST for the common case the fully unrolled row loop handles (footprint <= 48 x 64 pixels, bins <= 8 pixels
 // wide, every row in <= 3 bins); every other RoI keeps the in-CTA prologue.  Layout (floats):
 //   [0..3]   int4   flags(bit 0 = FAST) | level << 8,  xmin,  ymin,  wf | hf << 16
-//   [4..7]   float4 1/count, tmax (int bits), image (int bits), -
+//   [4..7]   float4 1/count, tmax (int bits), image (int bits), RoI index m (int bits)
 //   [8..15]  int    first column of each bin relative to xmin (0 for empty bins)
 //   [16..71] float  x-tap weights of each bin padded to 8
-//   [72.. ]  float4 per footprint row: (w(ph0), w(ph0+1), w(ph0+2), ph0)
+//   [72..327] float4 per footprint row: (w(ph0), w(ph0+1), w(ph0+2), ph0)
+//   [328..391] float the x-tap weights again, pair-interleaved for the packed row loop (Tables::wt2)
+// Record j describes RoI order[j] (the j-th RoI in processing order), so consumers walk the records sequentially.
 constexpr int kRecRows = 64;
-constexpr int kRecFloats = 72 + 4 * kRecRows;
+constexpr int kRecW2 = 72 + 4 * kRecRows;
+constexpr int kRecFloats = kRecW2 + 64;
+static_assert((kRecFloats * 4) % 16 == 0, "records are fetched with one 16-byte-granular bulk copy");
 constexpr int kPrepWarpsF = 4;
 
 struct PrepScratch {
@@ -644,17 +650,22 @@ struct PrepScratch {
 __global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __grid_constant__ FwdParams p) {
   __shared__ PrepScratch S4[kPrepWarpsF];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int m = blockIdx.x * kPrepWarpsF + warp;
-  if (m >= p.M) return;   // warp-uniform, no block barrier below
+  const int j = blockIdx.x * kPrepWarpsF + warp;
+  if (j == 0 && lane == 0 && p.counter != nullptr) *p.counter = p.pers_grid;   // work counter of the persistent kernel
+  if (j >= p.M) return;   // warp-uniform, no block barrier below
+  const int m = p.order ? p.order[j] : j;
   PrepScratch& T = S4[warp];
-  float* rec = p.rec + (int64_t)m * kRecFloats;
+  float* rec = p.rec + (int64_t)j * kRecFloats;
   const float* roi = p.rois + (int64_t)m * 5;
   const float fimg = __ldg(roi), x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
   const int img = (int)fimg;
   const int level = assign_level(x1, y1, x2, y2, p.L);
   const bool zero = (level < 0) || (level >= p.L.num_levels) || (img < 0) || (img >= p.L.num_images);
   if (zero) {
-    if (lane == 0) reinterpret_cast<int4*>(rec)[0] = make_int4(0, 0, 0, 0);
+    if (lane == 0) {
+      reinterpret_cast<int4*>(rec)[0] = make_int4(0, 0, 0, 0);
+      reinterpret_cast<float4*>(rec)[1] = make_float4(0.f, 0.f, 0.f, __int_as_float(m));
+    }
     return;
   }
   const LevelDesc& lv = p.L.lv[level];
@@ -714,30 +725,32 @@ __global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __
       const int first = nx > 0 ? T.xb[pw] - xmin : 0;
       const int start = max(0, min(first, wf - TT));
       const int qq = q - (first - start);
-      rec[16 + i] = (qq >= 0 && qq < nx) ? T.wx[pw * kRB + qq] : 0.f;
+      const float wv = (qq >= 0 && qq < nx) ? T.wx[pw * kRB + qq] : 0.f;
+      rec[16 + i] = wv;
+      rec[kRecW2 + (pw >> 1) * 16 + (q >> 1) * 4 + (q & 1) * 2 + (pw & 1)] = wv;   // element (pp, t2, k): k = (tap & 1) * 2 + (bin & 1)
     }
+    if (lane < 8) rec[kRecW2 + 3 * 16 + (lane >> 1) * 4 + (lane & 1) * 2 + 1] = 0.f;   // the missing 8th bin
     if (lane < 8) {
       const int nx = lane < kP ? T.nx[lane] : 0;
       const int first = nx > 0 ? T.xb[lane] - xmin : 0;
       reinterpret_cast<int*>(rec)[8 + lane] = max(0, min(first, wf - TT));
     }
-    if (lane == 0) reinterpret_cast<float4*>(rec)[1] = make_float4(1.0f / g.count, __int_as_float(tmax), __int_as_float(img), 0.f);
   }
-  if (lane == 0) reinterpret_cast<int4*>(rec)[0] = make_int4((fast ? 1 : 0) | (level << 8), xmin, ymin, wf | (hf << 16));
+  if (lane == 0) {
+    reinterpret_cast<float4*>(rec)[1] = make_float4(1.0f / g.count, __int_as_float(tmax), __int_as_float(img), __int_as_float(m));
+    reinterpret_cast<int4*>(rec)[0] = make_int4((fast ? 1 : 0) | (level << 8), xmin, ymin, wf | (hf << 16));
+  }
 }
 
-template <int kC>   // kC > 0: compile-time channel count (immediate LDS offsets); 0: run-time C
-__global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const __grid_constant__ FwdParams p) {
-  // dynamic smem: [ ring: 96 cols x C floats, cut into row stages sized to this RoI (re-used as the 49 x C output tile) | barriers | T ]
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* ring = reinterpret_cast<float*>(smem_raw);
+// One RoI (record j) by one 256-thread CTA.  kUseRec = false ignores the prep record (the persistent kernel calls this form
+// for the records that are not FAST; the barriers must then be fresh, i.e. invalidated by the caller).
+template <int kC, bool kUseRec>   // kC > 0: compile-time channel count (immediate LDS offsets); 0: run-time C
+__device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring, uint64_t* s_bar, Tables& T) {
   const int C = kC > 0 ? kC : p.L.C;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(ring + p.ring_floats);
-  Tables& T = *reinterpret_cast<Tables*>(s_bar + 2 * kNhwcMaxStages);
   uint64_t* full_bar = s_bar;
   uint64_t* empty_bar = s_bar + kNhwcMaxStages;
 
-  const int m = p.order ? p.order[blockIdx.x] : blockIdx.x;
+  const int m = p.order ? p.order[j] : j;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* out_roi = p.out + (int64_t)m * C * (kP * kP);
   unsigned short* out_bf = p.out_bf16 ? p.out_bf16 + (int64_t)m * C * (kP * kP) : nullptr;
@@ -752,8 +765,8 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   bool pre = false, early = false;
   int4 h0 = make_int4(0, 0, 0, 0);
   const float* rec = nullptr;
-  if (p.rec != nullptr) {
-    rec = p.rec + (int64_t)m * kRecFloats;
+  if (kUseRec && p.rec != nullptr) {
+    rec = p.rec + (int64_t)j * kRecFloats;
     h0 = __ldg(reinterpret_cast<const int4*>(rec));
     pre = (h0.x & 1) != 0;
   }
@@ -792,11 +805,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
     toff[0] = o0.x * C; toff[1] = o0.y * C; toff[2] = o0.z * C; toff[3] = o0.w * C;
     toff[4] = o1.x * C; toff[5] = o1.y * C; toff[6] = o1.z * C;
     if (tid < 2 * kP) reinterpret_cast<float4*>(&T.wt[0][0])[tid] = __ldg(reinterpret_cast<const float4*>(rec + 16) + tid);
-    if (tid >= 64 && tid < 128) {   // pair-interleaved copy for the packed row loop: element (pp, t2, k) with k = (tap & 1) * 2 + (bin & 1)
-      const int e = tid - 64, pp = e >> 4, t2 = (e >> 2) & 3, k = e & 3;
-      const int pw = 2 * pp + (k & 1), tap = 2 * t2 + (k >> 1);
-      reinterpret_cast<float*>(&T.wt2[0][0])[e] = pw < kP ? __ldg(rec + 16 + pw * 8 + tap) : 0.f;
-    }
+    if (tid >= 64 && tid < 80) reinterpret_cast<float4*>(&T.wt2[0][0])[tid - 64] = __ldg(reinterpret_cast<const float4*>(rec + kRecW2) + (tid - 64));
     for (int r = tid; r < hf; r += kThreads) T.rw[r] = __ldg(reinterpret_cast<const float4*>(rec + 72) + r);
   } else {
   const float* roi = p.rois + (int64_t)m * 5;
@@ -915,6 +924,10 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   const float* img_base = lv.data + (int64_t)img * lv.sN;
   if (tid == 0 && !early) {
     for (int i = 0; i < kNhwcMaxStages; ++i) {
+      if (!kUseRec) {   // called per RoI by the persistent kernel: the barriers hold valid (idle) objects from the last call
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[i])) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&empty_bar[i])) : "memory");
+      }
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], kWarps);
     }
@@ -1096,6 +1109,274 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const _
   }
 }
 
+// One CTA per RoI (the shipped form): dynamic smem = [ ring | barriers | Tables ]
+template <int kC>
+__global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(ring + p.ring_floats);
+  nhwc_roi<kC, true>(p, blockIdx.x, ring, s_bar, *reinterpret_cast<Tables*>(s_bar + 2 * kNhwcMaxStages));
+}
+
+template <int kC>
+__device__ __noinline__ void nhwc_roi_slow(const FwdParams& p, int j, float* ring, uint64_t* s_bar, Tables& T) {
+  nhwc_roi<kC, false>(p, j, ring, s_bar, T);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent form of the channels_last forward (opt-in, OSR_TUNE_FWD_VARIANT = 4): 2 CTAs per SM walk the records in
+// processing order (a global counter hands out the next record), so the per-RoI fixed costs of the one-CTA-per-RoI kernel
+// leave the critical path.  MEASURED RESULT (B200, cfg 2): 0.506 ms against 0.499 ms for one CTA per RoI with identical
+// output - hiding the prologue buys nothing, because the kernel is not bound by per-RoI latency but by the shared-memory
+// data pipe (row-loop LDS + bulk-copy fills + epilogue transposition = ~70 % of its cycles; ablations in DESIGN.md 4).
+// Kept as the documented experiment and as a second implementation the tests cross-check.  What it overlaps:
+//   * the record of the NEXT RoI (1.5 KB: header, tap offsets / weights, row weights) is fetched into shared memory by one
+//     bulk copy while the current RoI is processed - the row loop reads its tables straight from that copy, no dependent
+//     global loads, no table-building prologue;
+//   * the first rows of the next RoI are requested BEFORE the current RoI's epilogue (the 49 x C output tile is staged in
+//     the upper 49 columns of the ring, the early rows go to the stages below it), so the row loop of the next RoI starts
+//     on data that is already in flight for the whole epilogue;
+//   * the ring's mbarriers live for the whole kernel: a slot's phase parity is one bit of `cpar` (flipped per consumed
+//     tile; fills and consumptions of a slot alternate, so the same bit serves the full and the empty barrier).
+// Records that are not FAST (footprint > 48 x 64, bins > 8 pixels, rows in > 3 bins, off-pyramid) are rare and go through
+// the general per-RoI body (nhwc_roi_slow) on a private barrier set.
+// dynamic smem: [ ring 96 x C | full[6] empty[6] | slow-body barriers[12] | Tables (slow body) | 2 records | rec barriers[2] | ctl[2] ]
+constexpr int kTileCols = kP * kP;   // the output tile of a RoI takes 49 columns (x C floats) of the ring
+
+template <int kC>
+__global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  const int C = kC > 0 ? kC : p.L.C;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + p.ring_floats);
+  uint64_t* empty_bar = full_bar + kNhwcMaxStages;
+  uint64_t* slow_bar = empty_bar + kNhwcMaxStages;
+  Tables& T = *reinterpret_cast<Tables*>(slow_bar + 2 * kNhwcMaxStages);
+  float* recbuf = reinterpret_cast<float*>(&T + 1);
+  uint64_t* rec_bar = reinterpret_cast<uint64_t*>(recbuf + 2 * kRecFloats);
+  volatile int* s_ctl = reinterpret_cast<volatile int*>(rec_bar + 2);   // record index held by each record buffer (-1: none)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = tid;
+  const bool cin = c < C;
+  const int tile_off = p.ring_floats - kTileCols * C;   // floats; the ring is 96 columns, the tile its upper 49
+  const int fit_cols = tile_off / C;                    // early stages of the next RoI must end below the tile
+  const uint32_t rec_bytes = kRecFloats * 4;
+  int jn = 0;   // (thread 0) the record this CTA fetches next
+  if (tid == 0) {
+    for (int i = 0; i < kNhwcMaxStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kWarps);
+      mbar_init(&slow_bar[i], 1);
+      mbar_init(&slow_bar[kNhwcMaxStages + i], kWarps);
+    }
+    mbar_init(&rec_bar[0], 1);
+    mbar_init(&rec_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_ctl[0] = blockIdx.x;   // the host launches at most M CTAs
+    s_ctl[1] = -1;
+    mbar_expect_tx(&rec_bar[0], rec_bytes);
+    bulk_load_1d(recbuf, p.rec + (int64_t)blockIdx.x * kRecFloats, rec_bytes, &rec_bar[0]);
+    jn = atomicAdd(p.counter, 1);
+  }
+  // Zero-weight padded taps read whatever the ring holds: zero it once, afterwards it only ever holds feature values and
+  // output tiles (finite whenever the inputs are).
+  for (int i = tid; i < (p.ring_floats >> 2); i += kThreads) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  int buf = 0;
+  uint32_t rpar = 0;       // bit b: phase parity of rec_bar[b]
+  uint32_t cpar = 0;       // bit s: phase parity of ring slot s
+  bool after_fast = false; // the previous RoI went through the fast path (and may have requested my first rows)
+  while (true) {
+    const int j = s_ctl[buf];
+    if (j < 0) break;
+    mbar_wait(&rec_bar[buf], (rpar >> buf) & 1u);
+    const float* rs = recbuf + buf * kRecFloats;
+    const int4 h0 = *reinterpret_cast<const int4*>(rs);
+    const float4 h1 = *reinterpret_cast<const float4*>(rs + 4);
+    if (tid == 0) {   // fetch the record after this one into the other buffer (its last readers passed the previous RoI's barriers)
+      const int nb = buf ^ 1;
+      if (jn < p.M) {
+        s_ctl[nb] = jn;
+        mbar_expect_tx(&rec_bar[nb], rec_bytes);
+        bulk_load_1d(recbuf + nb * kRecFloats, p.rec + (int64_t)jn * kRecFloats, rec_bytes, &rec_bar[nb]);
+        jn = atomicAdd(p.counter, 1);
+      } else {
+        s_ctl[nb] = -1;
+      }
+    }
+    if ((h0.x & 1) == 0) {   // not FAST: general body on its own barriers
+      __syncthreads();       // the previous RoI's tile has been copied out
+      nhwc_roi_slow<kC>(p, j, ring, slow_bar, T);
+      __syncthreads();
+      rpar ^= 1u << buf;
+      buf ^= 1;
+      after_fast = false;
+      continue;
+    }
+    const int level = h0.x >> 8, xmin = h0.y, ymin = h0.z, wf = h0.w & 0xffff, hf = h0.w >> 16;
+    const float inv_count = h1.x;
+    const int tmax = __float_as_int(h1.y), img = __float_as_int(h1.z), m = __float_as_int(h1.w);
+    if (tid == 0) p.out_level[m] = level;
+    int toff[kP];
+    {
+      const int4 o0 = *reinterpret_cast<const int4*>(rs + 8), o1 = *reinterpret_cast<const int4*>(rs + 12);
+      toff[0] = o0.x * C; toff[1] = o0.y * C; toff[2] = o0.z * C; toff[3] = o0.w * C;
+      toff[4] = o1.x * C; toff[5] = o1.y * C; toff[6] = o1.z * C;
+    }
+    const float4* wt2 = reinterpret_cast<const float4*>(rs + kRecW2);   // [pp * 4 + t2]
+    const float4* rw = reinterpret_cast<const float4*>(rs + 72);
+    const LevelDesc& lv = p.L.lv[level];
+    const float* img_base = lv.data + (int64_t)img * lv.sN + ((int64_t)ymin * lv.sH + (int64_t)xmin * lv.sW);
+    const int scols = max(8, (wf + 3) & ~3);   // FAST records are at most 48 columns wide: a stage is one whole footprint row
+    const int nstages = min(kNhwcMaxStages, kNhwcRingCols / scols);
+    const int stage_floats = scols * C;
+    const uint32_t row_bytes = (uint32_t)(wf * C * 4);
+    const int total = hf;
+    const int n_first = min(nstages, total);
+    const int n_early = after_fast ? min(n_first, fit_cols / scols) : 0;   // already requested by the previous RoI's epilogue
+
+    float2 acc2[kP][4];
+#pragma unroll
+    for (int a = 0; a < kP; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc2[a][b] = make_float2(0.f, 0.f);
+
+    __syncthreads();   // (C) the previous RoI's tile has been copied out: the whole ring is free
+    if (warp == 0 && n_early < n_first) {
+      if (elect_one()) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy tile traffic before async-proxy refills
+        for (int t = n_early; t < n_first; ++t) {
+          mbar_expect_tx(&full_bar[t], row_bytes);
+          bulk_load_1d(ring + t * stage_floats, img_base + (int64_t)t * lv.sH, row_bytes, &full_bar[t]);
+        }
+      }
+      __syncwarp();
+    }
+    int slot = 0;
+    const float* rowc0 = ring + min(c, C - 1);
+    for (int t = 0; t < total; ++t) {
+      const uint32_t parity = (cpar >> slot) & 1u;
+      mbar_wait(&full_bar[slot], parity);
+      const float* rowc = rowc0 + slot * stage_floats;
+      float2 U2[4];
+#define OSR_NHWC_TAPS(NT2)                                                                                         \
+  _Pragma("unroll") for (int pp = 0; pp < 3; ++pp) {                                                                \
+    const float* ra = rowc + toff[2 * pp];                                                                          \
+    const float* rb = rowc + toff[2 * pp + 1];                                                                      \
+    float2 u = make_float2(0.f, 0.f);                                                                               \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+      const float4 w = wt2[pp * 4 + t2];                                                                            \
+      const float2 d0 = make_float2(ra[(2 * t2) * C], rb[(2 * t2) * C]);                                            \
+      const float2 d1 = make_float2(ra[(2 * t2 + 1) * C], rb[(2 * t2 + 1) * C]);                                    \
+      u = (t2 == 0) ? f2_mul(d0, make_float2(w.x, w.y)) : f2_fma(d0, make_float2(w.x, w.y), u);                     \
+      u = f2_fma(d1, make_float2(w.z, w.w), u);                                                                     \
+    }                                                                                                               \
+    U2[pp] = u;                                                                                                     \
+  }                                                                                                                 \
+  {                                                                                                                 \
+    const float* ra = rowc + toff[kP - 1];                                                                          \
+    float u = 0.f;                                                                                                  \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+      const float4 w = wt2[12 + t2];                                                                                \
+      u = fmaf(w.x, ra[(2 * t2) * C], u);                                                                           \
+      u = fmaf(w.z, ra[(2 * t2 + 1) * C], u);                                                                       \
+    }                                                                                                               \
+    U2[3] = make_float2(u, 0.f);                                                                                    \
+  }
+      if (tmax <= 4) {          // CTA-uniform: widest bin of this RoI spans <= 4 pixels
+        OSR_NHWC_TAPS(2)
+      } else if (tmax <= 6) {
+        OSR_NHWC_TAPS(3)
+      } else {
+        OSR_NHWC_TAPS(4)
+      }
+#undef OSR_NHWC_TAPS
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[slot]);
+      // refill the slot with row t + stages once every warp has released it
+      if (warp == 0 && t + nstages < total) {
+        if (elect_one()) {
+          mbar_wait(&empty_bar[slot], parity);
+          mbar_expect_tx(&full_bar[slot], row_bytes);
+          bulk_load_1d(ring + slot * stage_floats, img_base + (int64_t)(t + nstages) * lv.sH, row_bytes, &full_bar[slot]);
+        }
+        __syncwarp();
+      }
+      cpar ^= 1u << slot;
+      // y fold: the row feeds the <= 3 consecutive bins that contain it (bin index is CTA-uniform)
+      const float4 w = rw[t];
+      switch (__float_as_int(w.w)) {
+#define OSR_NHWC_CASE(PH)                                                                                   \
+  case PH:                                                                                                  \
+    _Pragma("unroll") for (int pp = 0; pp < 4; ++pp) {                                                      \
+      acc2[PH][pp] = f2_fma_s(U2[pp], w.x, acc2[PH][pp]);                                                   \
+      if (PH + 1 < kP) acc2[PH + 1 < kP ? PH + 1 : 0][pp] = f2_fma_s(U2[pp], w.y, acc2[PH + 1 < kP ? PH + 1 : 0][pp]); \
+      if (PH + 2 < kP) acc2[PH + 2 < kP ? PH + 2 : 0][pp] = f2_fma_s(U2[pp], w.z, acc2[PH + 2 < kP ? PH + 2 : 0][pp]); \
+    }                                                                                                       \
+    break;
+        OSR_NHWC_CASE(0) OSR_NHWC_CASE(1) OSR_NHWC_CASE(2) OSR_NHWC_CASE(3) OSR_NHWC_CASE(4) OSR_NHWC_CASE(5) OSR_NHWC_CASE(6)
+#undef OSR_NHWC_CASE
+        default: break;
+      }
+      if (++slot == nstages) slot = 0;
+    }
+    __syncthreads();   // (A) every warp has consumed every row: all ring slots are free, their barriers idle
+    // Request the first rows of the NEXT RoI now (stages that end below the output tile), so they fly during the epilogue.
+    if (tid == 0) {
+      const int nb = buf ^ 1;
+      if (s_ctl[nb] >= 0) {
+        mbar_wait(&rec_bar[nb], (rpar >> nb) & 1u);   // landed long ago
+        const float* rn = recbuf + nb * kRecFloats;
+        const int4 g0 = *reinterpret_cast<const int4*>(rn);
+        if (g0.x & 1) {
+          const int wfn = g0.w & 0xffff, hfn = g0.w >> 16;
+          const int scn = max(8, (wfn + 3) & ~3);
+          const int ne = min(min(min(kNhwcMaxStages, kNhwcRingCols / scn), hfn), fit_cols / scn);
+          const LevelDesc& ln = p.L.lv[g0.x >> 8];
+          const float* nbase = ln.data + (int64_t)__float_as_int(rn[6]) * ln.sN + ((int64_t)g0.z * ln.sH + (int64_t)g0.y * ln.sW);
+          const uint32_t nbytes = (uint32_t)(wfn * C * 4);
+          for (int t = 0; t < ne; ++t) {
+            mbar_expect_tx(&full_bar[t], nbytes);
+            bulk_load_1d(ring + t * (scn * C), nbase + (int64_t)t * ln.sH, nbytes, &full_bar[t]);
+          }
+        }
+      }
+    }
+    // epilogue: 49 x C tile -> shared memory as [c][49] (stride 49 is odd: conflict-free) -> coalesced 16-byte stores
+    float* tile = ring + tile_off;
+    if (cin) {
+      float* o = tile + c * (kP * kP);
+#pragma unroll
+      for (int a = 0; a < kP; ++a)
+#pragma unroll
+        for (int b = 0; b < kP; ++b) o[a * kP + b] = ((b & 1) ? acc2[a][b >> 1].y : acc2[a][b >> 1].x) * inv_count;
+    }
+    __syncthreads();   // (B)
+    const int n4 = (C * kP * kP) >> 2;
+    if (p.out_bf16) {   // bf16 pooled output for the tensor-core box head: 8 values per 16-byte store (C % 8 == 0 host-checked)
+      unsigned short* out_bf = p.out_bf16 + (int64_t)m * C * (kP * kP);
+      for (int i = tid; i < (n4 >> 1); i += kThreads) {
+        const float4 a = reinterpret_cast<const float4*>(tile)[2 * i], b = reinterpret_cast<const float4*>(tile)[2 * i + 1];
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(a.x, a.y), b1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(b.x, b.y), b3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+        o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+        reinterpret_cast<uint4*>(out_bf)[i] = o;
+      }
+    } else {
+      float* out_roi = p.out + (int64_t)m * C * (kP * kP);   // 16-byte aligned: host-checked for this kernel
+      for (int i = tid; i < n4; i += kThreads) reinterpret_cast<float4*>(out_roi)[i] = reinterpret_cast<const float4*>(tile)[i];
+    }
+    rpar ^= 1u << buf;
+    buf ^= 1;
+    after_fast = true;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Processing order: RoIs bucketed by (image, level, y band) with a single-CTA counting sort, so that CTAs that
 // run concurrently read neighbouring feature rows (L2-resident working set instead of a whole image's pyramid).
@@ -1219,7 +1500,7 @@ extern "C" {
 
 size_t osr_roi_align_fwd_workspace(int M) {
   const size_t m = (size_t)(M > 0 ? M : 1);
-  return osr::align256(m * 4) * 2 + osr::align256(m * kRecFloats * 4);   // order, keys, per-RoI table records
+  return osr::align256(m * 4) * 2 + osr::align256(m * kRecFloats * 4) + 256;   // order, keys, per-RoI table records, work counter
 }
 
 static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
@@ -1228,6 +1509,8 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
                               size_t workspace_bytes, void* stream) {
   osr::DeviceGuard device_guard(out_level);
   FwdParams p;
+  p.counter = nullptr;
+  p.pers_grid = 0;
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);
   if (rc) return rc;
@@ -1265,22 +1548,48 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
   if (out_bf16 && !(nhwc && C % 8 == 0))
     return osr::fail_arg(OSR_E_SHAPE, "roi_align_fwd_bf16: needs dense channels_last feature maps with C %% 8 == 0 and C <= 256");
   if (nhwc) {
-    if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && osr::tuning(osr::kTuneFwdVariant) != 2) {
-      p.rec = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 2 * osr::align256((size_t)M * 4));
+    const int variant = osr::tuning(osr::kTuneFwdVariant);
+    const bool have_ws = workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && variant != 2;
+    // opt-in (OSR_TUNE_FWD_VARIANT = 4): persistent CTAs (2 per SM) over the prep records; needs the workspace and 16-byte
+    // aligned output rows.  Measured equal to one CTA per RoI (0.506 vs 0.499 ms at cfg 2): see the kernel's header.
+    const bool pers = have_ws && variant == 4 &&
+                      ((reinterpret_cast<uintptr_t>(out_bf16 ? (const void*)out_bf16 : (const void*)out) & 15) == 0);
+    for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = 0;
+    if (have_ws) {
+      unsigned char* wsb = static_cast<unsigned char*>(workspace);
+      p.rec = reinterpret_cast<float*>(wsb + 2 * osr::align256((size_t)M * 4));
+      if (pers) {
+        int dev = 0, sms = 0;
+        OSR_CUDA_CHECK(cudaGetDevice(&dev));
+        OSR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        p.pers_grid = std::min(M, 2 * sms);
+        p.counter = reinterpret_cast<int*>(wsb + 2 * osr::align256((size_t)M * 4) + osr::align256((size_t)M * kRecFloats * 4));
+      }
       roi_fwd_prep_kernel<<<osr::ceil_div(M, kPrepWarpsF), kPrepWarpsF * 32, 0, s>>>(p);
       OSR_LAUNCH_CHECK();
     }
-    int ring = (kNhwcRingCols + 8) * C;              // + 8 columns of slack for the zero-weight padded taps
-    if (ring < kP * kP * C) ring = kP * kP * C;                 // the ring doubles as the 49 x C output tile
-    p.ring_floats = (ring + 31) & ~31;
-    for (int l = 0; l < num_levels; ++l) p.tma_ok[l] = 0;
-    const size_t smem = (size_t)p.ring_floats * 4 + 2 * kNhwcMaxStages * 8 + sizeof(Tables) + 16;
-    if (C == 256) {
-      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_fwd_nhwc_kernel<256><<<M, kThreads, smem, s>>>(p);
+    if (pers) {
+      p.ring_floats = kNhwcRingCols * C;   // 96 columns; the upper 49 double as the output tile
+      const size_t smem = (size_t)p.ring_floats * 4 + 4 * kNhwcMaxStages * 8 + sizeof(Tables) + 2 * kRecFloats * 4 + 2 * 8 + 16;
+      if (C == 256) {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_pers_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_fwd_nhwc_pers_kernel<256><<<p.pers_grid, kThreads, smem, s>>>(p);
+      } else {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_pers_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_fwd_nhwc_pers_kernel<0><<<p.pers_grid, kThreads, smem, s>>>(p);
+      }
     } else {
-      OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      roi_align_fwd_nhwc_kernel<0><<<M, kThreads, smem, s>>>(p);
+      int ring = (kNhwcRingCols + 8) * C;              // + 8 columns of slack for the zero-weight padded taps
+      if (ring < kP * kP * C) ring = kP * kP * C;                 // the ring doubles as the 49 x C output tile
+      p.ring_floats = (ring + 31) & ~31;
+      const size_t smem = (size_t)p.ring_floats * 4 + 2 * kNhwcMaxStages * 8 + sizeof(Tables) + 16;
+      if (C == 256) {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_fwd_nhwc_kernel<256><<<M, kThreads, smem, s>>>(p);
+      } else {
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        roi_align_fwd_nhwc_kernel<0><<<M, kThreads, smem, s>>>(p);
+      }
     }
     OSR_LAUNCH_CHECK();
     return 0;

@@ -24,6 +24,16 @@ def bwd_variant(request):
     _lib.set_tuning("bwd", prev)
 
 
+@pytest.fixture(params=[0, 4], ids=["fwd_cta_per_roi", "fwd_persistent"])
+def fwd_variant(request):
+    """channels_last forward tests run on both implementations (include/osr.h OSR_TUNE_FWD_VARIANT): 0 = one CTA per RoI
+    (shipped), 4 = persistent CTAs that prefetch the next RoI's record and first rows."""
+    from osr_b200 import _lib
+    prev = _lib.set_tuning("fwd", request.param)
+    yield request.param
+    _lib.set_tuning("fwd", prev)
+
+
 @pytest.fixture(params=[True, False], ids=["nchw_staged", "nchw_native"])
 def nchw_staging(request):
     """NCHW maps either go through the tiled NCHW->NHWC staging copy + the channels_last kernels (default) or through the
@@ -75,7 +85,7 @@ def test_forward_matches_torchvision(hw, n, per_img, C, nchw_staging):
     assert (ref_gpu.cpu() - ref_cpu).abs().max() > 0  # (documenting that the two reference kernels are not bit-equal)
 
 
-def test_forward_channels_last_input():
+def test_forward_channels_last_input(fwd_variant):
     from osr_b200 import synth
     ours, ref = _pooler_pair()
     feats = synth.make_features(2, (320, 480), 64, seed=5, device="cuda:0", channels_last=True)
@@ -232,7 +242,7 @@ def test_backward_empty_rois_gives_zero_grads():
 
 
 @pytest.mark.parametrize("hw,n,per_img,C", [((800, 1333), 2, 300, 256), ((320, 480), 3, 200, 64), ((224, 224), 1, 64, 40)])
-def test_forward_channels_last_kernel_matches_torchvision(hw, n, per_img, C):
+def test_forward_channels_last_kernel_matches_torchvision(hw, n, per_img, C, fwd_variant):
     """channels_last maps take the dedicated NHWC kernel (bulk-copy ring, thread = channel)."""
     from osr_b200 import synth
     ours, ref = _pooler_pair()
@@ -247,6 +257,31 @@ def test_forward_channels_last_kernel_matches_torchvision(hw, n, per_img, C):
     # and it agrees with our own NCHW kernel to fp32 summation-order noise
     out_nchw = ours.forward([f.contiguous() for f in feats], boxes)
     torch.testing.assert_close(out, out_nchw, rtol=FWD_RTOL, atol=FWD_ATOL)
+
+
+def test_forward_persistent_kernel_is_bit_identical_to_cta_per_roi():
+    """Both channels_last forwards execute the same arithmetic per RoI: outputs must be bit-equal, including RoIs that
+    leave the fast path (oversized / degenerate footprints), images without RoIs and the bf16 output mode."""
+    from osr_b200 import _lib, synth
+    from osr_b200.poolers import ROIPooler
+    ours = ROIPooler(7, synth.POOL_SCALES, 0, "ROIAlignV2")
+    feats = synth.make_features(3, (800, 1333), 256, seed=31, device="cuda:0", channels_last=True)
+    rois = synth.make_rois(3, 700, (800, 1333), seed=41)
+    rois[1] = torch.empty(0, 4)
+    rois[2] = torch.cat([rois[2], _special_rois(800, 1333)])
+    boxes = [OBoxes(r.cuda()) for r in rois]
+    packed = torch.cat([torch.cat([torch.full((len(r), 1), float(i)), r], dim=1) for i, r in enumerate(rois)]).cuda()
+    offsets = torch.tensor([0, 700, 700, 700 + len(rois[2])], dtype=torch.int32, device="cuda:0")
+    outs = {}
+    for v in (0, 4):
+        prev = _lib.set_tuning("fwd", v)
+        try:
+            outs[v] = (ours.forward(feats, boxes), ours.pool_rois_bf16(feats, packed, offsets)[0])
+        finally:
+            _lib.set_tuning("fwd", prev)
+    assert torch.equal(outs[0][0], outs[4][0])
+    assert torch.equal(outs[0][1], outs[4][1])
+    torch.testing.assert_close(outs[4][1].float(), outs[4][0], rtol=8e-3, atol=1e-6)   # bf16 = fp32 result rounded once
 
 
 def test_backward_channels_last_grads(bwd_variant):
