@@ -48,6 +48,7 @@ void osr_reset_launch_count(void);
  *   OSR_TUNE_BWD_VARIANT   0 register accumulators + packed fp32x2 FMAs (shipped) | 2 shared-memory accumulators
  *                          (round-1 kernel) | 3 pixel-per-thread kernel
  *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records | 4 persistent channels_last kernel
+ *                          | 5 one footprint row per row-loop iteration (round-1 loop; the default folds two)
  *   OSR_TUNE_PLN_VARIANT   0 encoder GEMM on fp32 operands (tcgen05 kind::tf32, no cast pass; shipped) | 1 bf16 copies (kind::f16)
  *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu */
 #define OSR_TUNE_BWD_VARIANT 0

@@ -43,6 +43,7 @@ struct FwdParams {
   float* rec;            // (M, kRecFloats) per-RoI table records written by roi_fwd_prep_kernel, or nullptr
   int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules AND the TMA path is enabled for this call
   int ring_floats;             // floats of the staging ring at the start of dynamic shared memory
+  int two_rows;                // NHWC kernel: 2 footprint rows per row-loop iteration
   int* counter;                // persistent NHWC kernel: next unclaimed record (set to the grid size by roi_fwd_prep_kernel)
   int pers_grid;               // grid size of the persistent NHWC kernel (0: not used)
 };
@@ -639,6 +640,8 @@ constexpr int kRecRows = 64;
 constexpr int kRecW2 = 72 + 4 * kRecRows;
 constexpr int kRecFloats = kRecW2 + 64;
 static_assert((kRecFloats * 4) % 16 == 0, "records are fetched with one 16-byte-granular bulk copy");
+// taps the row loop executes per bin for a RoI whose widest bin spans `tmax` pixels (one unrolled loop per count)
+__host__ __device__ __forceinline__ int nhwc_tap_count(int tmax) { return tmax <= 2 ? 2 : (tmax <= 6 ? tmax : 8); }
 constexpr int kPrepWarpsF = 4;
 
 struct PrepScratch {
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __
     // pulled left so that all TT taps stay inside the row (columns [0, wf)) and the weights are shifted right by the
     // same amount: zero-weight taps then re-read real data of the SAME row, never uninitialised shared memory, and the
     // CTA does not have to zero-fill its 96 KB ring (footprints narrower than TT still do).
-    const int TT = tmax <= 4 ? 4 : (tmax <= 6 ? 6 : 8);
+    const int TT = nhwc_tap_count(tmax);
     for (int i = lane; i < kP * 8; i += 32) {
       const int pw = i >> 3, q = i & 7;
       const int nx = T.nx[pw];
@@ -894,7 +897,7 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) tmax = max(tmax, T.nx[pw]);
     // tap windows pulled inside the row, weights shifted by the same amount (see roi_fwd_prep_kernel)
-    const int TT = tmax <= 4 ? 4 : (tmax <= 6 ? 6 : 8);
+    const int TT = nhwc_tap_count(tmax);
 #pragma unroll
     for (int pw = 0; pw < kP; ++pw) {
       const int first = T.nx[pw] > 0 ? T.xb[pw] - xmin : 0;
@@ -953,7 +956,8 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
   // Common case (one x chunk): every bin's x taps are padded to 8 with zero weights (T.wt), so the row loop is fully
   // unrolled and predicate-free; padded taps read finite data (the ring is zero-initialised once and only ever holds
   // feature values; 8 columns of slack follow the last stage).
-  const bool fast_taps = (nxc == 1) && (tmax <= 8);   // tmax = widest bin in pixels: picks the 4-, 6- or 8-tap row loop
+  const bool fast_taps = (nxc == 1) && (tmax <= 8);   // tmax = widest bin in pixels: picks the unrolled row loop
+  const int ntaps = nhwc_tap_count(tmax);
   // Zero-weight padded taps must read finite data.  The tap windows stay inside the loaded row unless the footprint is
   // narrower than the tap count; only then the pad columns exist and the ring is zero-filled first.
   if (wf < 8) {
@@ -983,7 +987,129 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
     rxc = t0 / hf;
     rr = t0 - rxc * hf;
   }
-  for (int t = 0; t < total; ++t) {
+  int t = 0;
+  // Two rows per iteration (whole-row stages only): the tap weights - a quarter of the row loop's shared-memory wavefronts -
+  // are loaded once for both rows and the per-row loop overhead (barrier wait, release, refill, ~90 of the ~160 instructions
+  // of a one-row iteration) is halved.  0.506 -> 0.471 ms at cfg 2; OSR_TUNE_FWD_VARIANT = 5 keeps the one-row loop.
+  if (fast_taps && p.two_rows) {
+    const int cc = min(c, C - 1);
+    for (; t + 1 < total; t += 2) {
+      const int slot_a = slot;
+      const uint32_t par_a = parity;
+      if (++slot == nstages) { slot = 0; parity ^= 1u; }
+      const int slot_b = slot;
+      const uint32_t par_b = parity;
+      if (++slot == nstages) { slot = 0; parity ^= 1u; }
+      mbar_wait(&full_bar[slot_a], par_a);
+      mbar_wait(&full_bar[slot_b], par_b);
+      const float* rowa = ring + slot_a * stage_floats + cc;
+      const float* rowb = ring + slot_b * stage_floats + cc;
+      float2 Ua[4], Ub[4];
+#define OSR_NHWC_TAPS2(NT)                                                                                         \
+  _Pragma("unroll") for (int pp = 0; pp < 3; ++pp) {                                                                \
+    const int o0 = toff[2 * pp], o1 = toff[2 * pp + 1];                                                             \
+    float2 ua = make_float2(0.f, 0.f), ub = make_float2(0.f, 0.f);                                                  \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT) / 2; ++t2) {                                                       \
+      const float4 w = T.wt2[pp][t2];                                                                               \
+      const float2 wl = make_float2(w.x, w.y), wh = make_float2(w.z, w.w);                                          \
+      const float2 a0 = make_float2(rowa[o0 + (2 * t2) * C], rowa[o1 + (2 * t2) * C]);                              \
+      const float2 a1 = make_float2(rowa[o0 + (2 * t2 + 1) * C], rowa[o1 + (2 * t2 + 1) * C]);                      \
+      const float2 b0 = make_float2(rowb[o0 + (2 * t2) * C], rowb[o1 + (2 * t2) * C]);                              \
+      const float2 b1 = make_float2(rowb[o0 + (2 * t2 + 1) * C], rowb[o1 + (2 * t2 + 1) * C]);                      \
+      ua = (t2 == 0) ? f2_mul(a0, wl) : f2_fma(a0, wl, ua);                                                         \
+      ub = (t2 == 0) ? f2_mul(b0, wl) : f2_fma(b0, wl, ub);                                                         \
+      ua = f2_fma(a1, wh, ua);                                                                                      \
+      ub = f2_fma(b1, wh, ub);                                                                                      \
+    }                                                                                                               \
+    if ((NT) & 1) {   /* odd tap count: the last tap uses half a weight vector */                                   \
+      const float4 w = T.wt2[pp][(NT) / 2];                                                                         \
+      const float2 wl = make_float2(w.x, w.y);                                                                      \
+      ua = f2_fma(make_float2(rowa[o0 + ((NT) - 1) * C], rowa[o1 + ((NT) - 1) * C]), wl, ua);                       \
+      ub = f2_fma(make_float2(rowb[o0 + ((NT) - 1) * C], rowb[o1 + ((NT) - 1) * C]), wl, ub);                       \
+    }                                                                                                               \
+    Ua[pp] = ua;                                                                                                    \
+    Ub[pp] = ub;                                                                                                    \
+  }                                                                                                                 \
+  {                                                                                                                 \
+    const int o0 = toff[kP - 1];                                                                                    \
+    float2 u = make_float2(0.f, 0.f);   /* (row a, row b) of the unpaired bin */                                     \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT) / 2; ++t2) {                                                       \
+      const float4 w = T.wt2[3][t2];                                                                                \
+      u = f2_fma_s(make_float2(rowa[o0 + (2 * t2) * C], rowb[o0 + (2 * t2) * C]), w.x, u);                          \
+      u = f2_fma_s(make_float2(rowa[o0 + (2 * t2 + 1) * C], rowb[o0 + (2 * t2 + 1) * C]), w.z, u);                  \
+    }                                                                                                               \
+    if ((NT) & 1) u = f2_fma_s(make_float2(rowa[o0 + ((NT) - 1) * C], rowb[o0 + ((NT) - 1) * C]), T.wt2[3][(NT) / 2].x, u); \
+    Ua[3] = make_float2(u.x, 0.f);                                                                                  \
+    Ub[3] = make_float2(u.y, 0.f);                                                                                  \
+  }
+      switch (ntaps) {   // CTA-uniform
+        case 2: OSR_NHWC_TAPS2(2) break;
+        case 3: OSR_NHWC_TAPS2(3) break;
+        case 4: OSR_NHWC_TAPS2(4) break;
+        case 5: OSR_NHWC_TAPS2(5) break;
+        case 6: OSR_NHWC_TAPS2(6) break;
+        default: OSR_NHWC_TAPS2(8) break;
+      }
+#undef OSR_NHWC_TAPS2
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty_bar[slot_a]);
+        mbar_arrive(&empty_bar[slot_b]);
+      }
+      if (warp == 0 && t + nstages < total) {
+        if (elect_one()) {
+          const uint32_t bytes = (uint32_t)(wf * C * 4);
+          mbar_wait(&empty_bar[slot_a], par_a);
+          mbar_expect_tx(&full_bar[slot_a], bytes);
+          bulk_load_1d(ring + slot_a * stage_floats, img_base + ((int64_t)(ymin + t + nstages) * lv.sH + (int64_t)xmin * lv.sW), bytes, &full_bar[slot_a]);
+          if (t + 1 + nstages < total) {
+            mbar_wait(&empty_bar[slot_b], par_b);
+            mbar_expect_tx(&full_bar[slot_b], bytes);
+            bulk_load_1d(ring + slot_b * stage_floats, img_base + ((int64_t)(ymin + t + 1 + nstages) * lv.sH + (int64_t)xmin * lv.sW), bytes, &full_bar[slot_b]);
+          }
+        }
+        __syncwarp();
+      }
+#define OSR_NHWC_CASE(PH, UU, W)                                                                            \
+  case PH:                                                                                                  \
+    _Pragma("unroll") for (int pp = 0; pp < 4; ++pp) {                                                      \
+      acc2[PH][pp] = f2_fma_s(UU[pp], (W).x, acc2[PH][pp]);                                                 \
+      if (PH + 1 < kP) acc2[PH + 1 < kP ? PH + 1 : 0][pp] = f2_fma_s(UU[pp], (W).y, acc2[PH + 1 < kP ? PH + 1 : 0][pp]); \
+      if (PH + 2 < kP) acc2[PH + 2 < kP ? PH + 2 : 0][pp] = f2_fma_s(UU[pp], (W).z, acc2[PH + 2 < kP ? PH + 2 : 0][pp]); \
+    }                                                                                                       \
+    break;
+#define OSR_NHWC_FOLD(UU, ROWIDX)                                                                           \
+  {                                                                                                         \
+    const float4 w = T.rw[ROWIDX];                                                                          \
+    switch (__float_as_int(w.w)) {                                                                          \
+      OSR_NHWC_CASE(0, UU, w) OSR_NHWC_CASE(1, UU, w) OSR_NHWC_CASE(2, UU, w) OSR_NHWC_CASE(3, UU, w)       \
+      OSR_NHWC_CASE(4, UU, w) OSR_NHWC_CASE(5, UU, w) OSR_NHWC_CASE(6, UU, w)                               \
+      case -1: {                                                                                            \
+        const int y = ymin + (ROWIDX);                                                                      \
+        _Pragma("unroll") for (int ph = 0; ph < kP; ++ph) {                                                 \
+          const int rr2 = y - T.yb[ph];                                                                     \
+          const float wy = (rr2 >= 0 && rr2 < T.ny[ph]) ? T.wy[ph * kRB + rr2] : 0.f;                       \
+          _Pragma("unroll") for (int pp = 0; pp < 4; ++pp) acc2[ph][pp] = f2_fma_s(UU[pp], wy, acc2[ph][pp]); \
+        }                                                                                                   \
+        break;                                                                                              \
+      }                                                                                                     \
+      default: break;                                                                                       \
+    }                                                                                                       \
+  }
+      OSR_NHWC_FOLD(Ua, t)
+      OSR_NHWC_FOLD(Ub, t + 1)
+#undef OSR_NHWC_FOLD
+#undef OSR_NHWC_CASE
+    }
+    // (whole-row stages: chunk 0, row t) bookkeeping of the one-row loop that finishes an odd row count
+    r = t;
+    {
+      const int tn = min(t + nstages, total);
+      rxc = tn / hf;
+      rr = tn - rxc * hf;
+    }
+  }
+  for (; t < total; ++t) {
     mbar_wait(&full_bar[slot], parity);
     const float* row = ring + slot * stage_floats + c;
     const int x_lo = xmin + xc * scols, x_hi = min(xmin + wf, x_lo + scols);
@@ -991,36 +1117,42 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
     float2 U2[4];
     if (fast_taps) {
       const float* rowc = ring + slot * stage_floats + min(c, C - 1);
-#define OSR_NHWC_TAPS(NT2)                                                                                         \
+#define OSR_NHWC_TAPS(NT)                                                                                          \
   _Pragma("unroll") for (int pp = 0; pp < 3; ++pp) {                                                                \
     const float* ra = rowc + toff[2 * pp];                                                                          \
     const float* rb = rowc + toff[2 * pp + 1];                                                                      \
     float2 u = make_float2(0.f, 0.f);                                                                               \
-    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT) / 2; ++t2) {                                                       \
       const float4 w = T.wt2[pp][t2];                                                                               \
       const float2 d0 = make_float2(ra[(2 * t2) * C], rb[(2 * t2) * C]);                                            \
       const float2 d1 = make_float2(ra[(2 * t2 + 1) * C], rb[(2 * t2 + 1) * C]);                                    \
       u = (t2 == 0) ? f2_mul(d0, make_float2(w.x, w.y)) : f2_fma(d0, make_float2(w.x, w.y), u);                     \
       u = f2_fma(d1, make_float2(w.z, w.w), u);                                                                     \
     }                                                                                                               \
+    if ((NT) & 1) {                                                                                                 \
+      const float4 w = T.wt2[pp][(NT) / 2];                                                                         \
+      u = f2_fma(make_float2(ra[((NT) - 1) * C], rb[((NT) - 1) * C]), make_float2(w.x, w.y), u);                    \
+    }                                                                                                               \
     U2[pp] = u;                                                                                                     \
   }                                                                                                                 \
   {                                                                                                                 \
     const float* ra = rowc + toff[kP - 1];                                                                          \
     float u = 0.f;                                                                                                  \
-    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT) / 2; ++t2) {                                                       \
       const float4 w = T.wt2[3][t2];                                                                                \
       u = fmaf(w.x, ra[(2 * t2) * C], u);                                                                           \
       u = fmaf(w.z, ra[(2 * t2 + 1) * C], u);                                                                       \
     }                                                                                                               \
+    if ((NT) & 1) u = fmaf(T.wt2[3][(NT) / 2].x, ra[((NT) - 1) * C], u);                                            \
     U2[3] = make_float2(u, 0.f);                                                                                    \
   }
-      if (tmax <= 4) {          // CTA-uniform: widest bin of this RoI spans <= 4 pixels
-        OSR_NHWC_TAPS(2)
-      } else if (tmax <= 6) {
-        OSR_NHWC_TAPS(3)
-      } else {
-        OSR_NHWC_TAPS(4)
+      switch (ntaps) {   // CTA-uniform: taps per bin of this RoI
+        case 2: OSR_NHWC_TAPS(2) break;
+        case 3: OSR_NHWC_TAPS(3) break;
+        case 4: OSR_NHWC_TAPS(4) break;
+        case 5: OSR_NHWC_TAPS(5) break;
+        case 6: OSR_NHWC_TAPS(6) break;
+        default: OSR_NHWC_TAPS(8) break;
       }
 #undef OSR_NHWC_TAPS
     } else {
@@ -1236,6 +1368,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
     const uint32_t row_bytes = (uint32_t)(wf * C * 4);
     const int total = hf;
     const int n_first = min(nstages, total);
+    const int ntaps = nhwc_tap_count(tmax);
     const int n_early = after_fast ? min(n_first, fit_cols / scols) : 0;   // already requested by the previous RoI's epilogue
 
     float2 acc2[kP][4];
@@ -1262,36 +1395,42 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
       mbar_wait(&full_bar[slot], parity);
       const float* rowc = rowc0 + slot * stage_floats;
       float2 U2[4];
-#define OSR_NHWC_TAPS(NT2)                                                                                         \
+#define OSR_NHWC_TAPS(NT)                                                                                          \
   _Pragma("unroll") for (int pp = 0; pp < 3; ++pp) {                                                                \
     const float* ra = rowc + toff[2 * pp];                                                                          \
     const float* rb = rowc + toff[2 * pp + 1];                                                                      \
     float2 u = make_float2(0.f, 0.f);                                                                               \
-    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT) / 2; ++t2) {                                                       \
       const float4 w = wt2[pp * 4 + t2];                                                                            \
       const float2 d0 = make_float2(ra[(2 * t2) * C], rb[(2 * t2) * C]);                                            \
       const float2 d1 = make_float2(ra[(2 * t2 + 1) * C], rb[(2 * t2 + 1) * C]);                                    \
       u = (t2 == 0) ? f2_mul(d0, make_float2(w.x, w.y)) : f2_fma(d0, make_float2(w.x, w.y), u);                     \
       u = f2_fma(d1, make_float2(w.z, w.w), u);                                                                     \
     }                                                                                                               \
+    if ((NT) & 1) {                                                                                                 \
+      const float4 w = wt2[pp * 4 + (NT) / 2];                                                                      \
+      u = f2_fma(make_float2(ra[((NT) - 1) * C], rb[((NT) - 1) * C]), make_float2(w.x, w.y), u);                    \
+    }                                                                                                               \
     U2[pp] = u;                                                                                                     \
   }                                                                                                                 \
   {                                                                                                                 \
     const float* ra = rowc + toff[kP - 1];                                                                          \
     float u = 0.f;                                                                                                  \
-    _Pragma("unroll") for (int t2 = 0; t2 < (NT2); ++t2) {                                                          \
+    _Pragma("unroll") for (int t2 = 0; t2 < (NT) / 2; ++t2) {                                                       \
       const float4 w = wt2[12 + t2];                                                                                \
       u = fmaf(w.x, ra[(2 * t2) * C], u);                                                                           \
       u = fmaf(w.z, ra[(2 * t2 + 1) * C], u);                                                                       \
     }                                                                                                               \
+    if ((NT) & 1) u = fmaf(wt2[12 + (NT) / 2].x, ra[((NT) - 1) * C], u);                                            \
     U2[3] = make_float2(u, 0.f);                                                                                    \
   }
-      if (tmax <= 4) {          // CTA-uniform: widest bin of this RoI spans <= 4 pixels
-        OSR_NHWC_TAPS(2)
-      } else if (tmax <= 6) {
-        OSR_NHWC_TAPS(3)
-      } else {
-        OSR_NHWC_TAPS(4)
+      switch (ntaps) {   // CTA-uniform: taps per bin of this RoI
+        case 2: OSR_NHWC_TAPS(2) break;
+        case 3: OSR_NHWC_TAPS(3) break;
+        case 4: OSR_NHWC_TAPS(4) break;
+        case 5: OSR_NHWC_TAPS(5) break;
+        case 6: OSR_NHWC_TAPS(6) break;
+        default: OSR_NHWC_TAPS(8) break;
       }
 #undef OSR_NHWC_TAPS
       __syncwarp();
@@ -1511,6 +1650,7 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
   FwdParams p;
   p.counter = nullptr;
   p.pers_grid = 0;
+  p.two_rows = osr::tuning(osr::kTuneFwdVariant) == 5 ? 0 : 1;   // 5: one row per iteration (A/B: 0.506 vs 0.471 ms at cfg 2)
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);
   if (rc) return rc;

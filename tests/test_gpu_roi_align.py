@@ -24,10 +24,11 @@ def bwd_variant(request):
     _lib.set_tuning("bwd", prev)
 
 
-@pytest.fixture(params=[0, 4], ids=["fwd_cta_per_roi", "fwd_persistent"])
+@pytest.fixture(params=[0, 4, 5], ids=["fwd_cta_per_roi", "fwd_persistent", "fwd_one_row_loop"])
 def fwd_variant(request):
-    """channels_last forward tests run on both implementations (include/osr.h OSR_TUNE_FWD_VARIANT): 0 = one CTA per RoI
-    (shipped), 4 = persistent CTAs that prefetch the next RoI's record and first rows."""
+    """channels_last forward tests run on every implementation (include/osr.h OSR_TUNE_FWD_VARIANT): 0 = one CTA per RoI,
+    two footprint rows per iteration (shipped), 4 = persistent CTAs that prefetch the next RoI's record and first rows,
+    5 = one CTA per RoI with the one-row loop."""
     from osr_b200 import _lib
     prev = _lib.set_tuning("fwd", request.param)
     yield request.param
@@ -273,14 +274,15 @@ def test_forward_persistent_kernel_is_bit_identical_to_cta_per_roi():
     packed = torch.cat([torch.cat([torch.full((len(r), 1), float(i)), r], dim=1) for i, r in enumerate(rois)]).cuda()
     offsets = torch.tensor([0, 700, 700, 700 + len(rois[2])], dtype=torch.int32, device="cuda:0")
     outs = {}
-    for v in (0, 4):
+    for v in (0, 4, 5):
         prev = _lib.set_tuning("fwd", v)
         try:
             outs[v] = (ours.forward(feats, boxes), ours.pool_rois_bf16(feats, packed, offsets)[0])
         finally:
             _lib.set_tuning("fwd", prev)
-    assert torch.equal(outs[0][0], outs[4][0])
-    assert torch.equal(outs[0][1], outs[4][1])
+    assert torch.equal(outs[5][0], outs[4][0]) and torch.equal(outs[5][1], outs[4][1])   # same one-row arithmetic
+    # the two-row loop adds the rows of a pair in the same order, with the same roundings: bit-equal as well
+    assert torch.equal(outs[0][0], outs[5][0]) and torch.equal(outs[0][1], outs[5][1])
     torch.testing.assert_close(outs[4][1].float(), outs[4][0], rtol=8e-3, atol=1e-6)   # bf16 = fp32 result rounded once
 
 
