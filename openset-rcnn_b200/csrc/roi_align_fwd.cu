@@ -991,7 +991,7 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
   // Two rows per iteration (whole-row stages only): the tap weights - a quarter of the row loop's shared-memory wavefronts -
   // are loaded once for both rows and the per-row loop overhead (barrier wait, release, refill, ~90 of the ~160 instructions
   // of a one-row iteration) is halved.  0.506 -> 0.471 ms at cfg 2; OSR_TUNE_FWD_VARIANT = 5 keeps the one-row loop.
-  if (fast_taps && p.two_rows) {
+  if (fast_taps && p.two_rows && nstages >= 2) {
     const int cc = min(c, C - 1);
     for (; t + 1 < total; t += 2) {
       const int slot_a = slot;
