@@ -196,18 +196,26 @@ int osr_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
  * center_weight = 1 (reference) or world_size for the gathered multi-GPU variant.
  * ------------------------------------------------------------------------------------------ */
 size_t osr_pln_workspace(int R, int D, int K, int reps_per_class);
+/* distance_type = MODEL.PLN.DISTANCE_TYPE (prototype_learning_network.py:156-161,171-176,210-215), between the UNIT
+ * embedding and the UNIT prototypes: COS 1 - <a, b> (both shipped configurations), L1 = torch.cdist(a, b, p=1),
+ * L2 = torch.cdist(a, b) (computed as sqrt(sum (a-b)^2); torch's mm formulation differs from it by rounding only). */
+#define OSR_PLN_DIST_COS 0
+#define OSR_PLN_DIST_L1 1
+#define OSR_PLN_DIST_L2 2
 /*
  * saved-for-backward outputs:
  *   emb_inv_norm (R) fp32, rep_inv_norm (K*rpc) fp32,
  *   intra_rep (R) int32: rep index of the own-class minimum if the intra hinge is active else -1
  *   inter_rep (R) int32: rep index of the nearest other-class rep if the inter hinge is active else -1
  *   center_rep (K*rpc) int32: nearest other-class rep if the separation hinge is active else -1
+ *   saved_dist (2*R + K*rpc) fp32: [intra distance (R) | inter distance (R) | separation distance (K*rpc)] - the L2
+ *     backward divides by them; REQUIRED for L2 when a backward follows, may be NULL otherwise
  *   loss_terms (4) fp32: [loss, intra_sum, inter_sum, center_sum]
  */
 int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, int R, int D,
-                     int K, int reps_per_class, float alpha, float beta, float loss_weight, float iou_threshold,
-                     float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
-                     float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep,
+                     int K, int reps_per_class, int distance_type, float alpha, float beta, float loss_weight,
+                     float iou_threshold, float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
+                     float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep, float* saved_dist,
                      void* workspace, size_t workspace_bytes, void* stream);
 /*
  *   grad_loss (1) device fp32 (upstream gradient of the scalar loss)
@@ -215,17 +223,18 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
  */
 int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels, const float* emb_inv_norm,
                      const float* rep_inv_norm, const int32_t* intra_rep, const int32_t* inter_rep,
-                     const int32_t* center_rep, const float* grad_loss, int R, int D, int K, int reps_per_class,
-                     float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     const int32_t* center_rep, const float* saved_dist, const float* grad_loss, int R, int D, int K,
+                     int reps_per_class, int distance_type, float loss_weight, float r_norm, float center_weight,
+                     float* grad_emb, float* grad_reps, void* workspace, size_t workspace_bytes, void* stream);
 /* Forward and closed-form backward of the loss in one call (grad_loss: device scalar, usually 1): same outputs as
  * osr_pln_loss_fwd followed by osr_pln_loss_bwd, bit for bit, in four launches (d loss / d emb is written by the row
  * kernel itself).  Used by the training step when the caller does not route the loss through autograd. */
 int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
-                         int R, int D, int K, int reps_per_class, float alpha, float beta, float loss_weight,
-                         float iou_threshold, float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
-                         float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep, float* grad_emb,
-                         float* grad_reps, void* workspace, size_t workspace_bytes, void* stream);
+                         int R, int D, int K, int reps_per_class, int distance_type, float alpha, float beta,
+                         float loss_weight, float iou_threshold, float r_norm, float center_weight, float* loss_terms,
+                         float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep,
+                         int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 
 /*
@@ -253,10 +262,11 @@ int osr_pln_encode_gather_fwd(const float* x, const float* W, const float* bias,
  * PLN.inference nearest-prototype classification (prototype_learning_network.py:203-226), all images at once:
  *   pred[i] = class of the nearest prototype of normalize(emb[i]) (min over the reps of a class first),
  *   mapped through class_id_map (K int64, may be NULL = identity; the reference's self.class_id for GraspNet),
- *   or unknown_id when the minimum cosine distance is > unk_thr.  min_dist (R) fp32 is also returned.
+ *   or unknown_id when the minimum distance (distance_type as above) is > unk_thr.  min_dist (R) fp32 is also returned.
  */
-int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, float unk_thr,
-                    int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist, void* stream);
+int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, int distance_type,
+                    float unk_thr, int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist,
+                    void* stream);
 
 /*
  * Proposal <-> ground-truth matching of the ROI-head sampling glue, all images at once

@@ -1,4 +1,4 @@
-// PLN prototype loss (cosine distance) forward + closed-form backward for sm_100a.
+// PLN prototype loss (MODEL.PLN.DISTANCE_TYPE = COS | L1 | L2) forward + closed-form backward for sm_100a.
 // Replaces prototype_learning_network.py:134,137-187 (F.normalize x2, nonzero (host sync), index, mm, reshape/min,
 // two index_puts, K-iteration Python loop :179-180, three relu/sum chains) and its autograd graph.
 //
@@ -40,11 +40,40 @@ struct PlnParams {
   // workspace
   float* partial;      // fwd: (num_ctas, 2)   bwd: (kSeg, Kr, D)
   int num_ctas;
+  int dist_type;       // OSR_PLN_DIST_COS / _L1 / _L2 (prototype_learning_network.py:156-161,171-176)
+  float* saved_dist;   // (2 R + Kr): intra distance, inter distance of every foreground row, separation distance of every
+                       // prototype - read by the L2 backward (d dist / d x = (x - y) / dist); may be null for COS / L1
   // backward only
   const float* grad_loss;
   float* grad_emb;
   float* grad_reps;
 };
+
+// ---- the three distances between unit vectors and their derivatives (torch.cdist semantics: sign(0) = 0, and the L2
+// gradient is 0 where the distance is 0)
+enum { kCos = OSR_PLN_DIST_COS, kL1 = OSR_PLN_DIST_L1, kL2 = OSR_PLN_DIST_L2 };
+template <int kDist>
+__device__ __forceinline__ float dist_acc(float a, float b, float acc) {   // one dimension's contribution to the lane partial
+  if (kDist == kCos) return fmaf(a, b, acc);
+  const float d = a - b;
+  return kDist == kL1 ? acc + fabsf(d) : fmaf(d, d, acc);
+}
+template <int kDist>
+__device__ __forceinline__ float dist_finish(float s) {   // the reduced sum -> the distance
+  return kDist == kCos ? 1.0f - s : (kDist == kL1 ? s : sqrtf(s));
+}
+template <int kDist>
+__device__ __forceinline__ float dist_d_first(float a, float b, float dist) {   // d dist(a, b) / d a, one dimension
+  if (kDist == kCos) return -b;
+  const float d = a - b;
+  if (kDist == kL1) return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  return dist > 0.f ? d / dist : 0.f;
+}
+template <int kDist>
+__device__ __forceinline__ float dist_d_second(float a, float b, float dist) {  // d dist(a, b) / d b
+  if (kDist == kCos) return -a;
+  return -dist_d_first<kDist>(a, b, dist);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -70,7 +99,7 @@ __device__ __forceinline__ void load_unit_reps(const PlnParams& p, float* rh, fl
 
 // kGrad: also write d loss / d emb of every row (the closed form of pln_grad_emb_kernel, same arithmetic, fused here so the
 // forward + backward of the loss is one pass over the embeddings: osr_pln_loss_fwd_bwd)
-template <bool kGrad>
+template <bool kGrad, int kDist>
 __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constant__ PlnParams p) {
   extern __shared__ __align__(16) float rh[];  // (Kr, D)
   __shared__ float s_part[kWarps][2];
@@ -123,10 +152,10 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
 #pragma unroll
         for (int q = 0; q < kMaxD / 32; ++q) {
           const int d = q * 32 + lane;
-          if (d < p.D) dot = fmaf(e[q], rh[j * p.D + d], dot);
+          if (d < p.D) dot = dist_acc<kDist>(e[q], rh[j * p.D + d], dot);
         }
         dot = warp_sum(dot);
-        const float dist = 1.0f - dot;
+        const float dist = dist_finish<kDist>(dot);
         if (best_j < 0 || dist < best) {
           best = dist;
           best_j = j;
@@ -148,6 +177,10 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
       p.emb_inv_norm[i] = 1.0f / denom;
       p.intra_rep[i] = intra_on ? intra_j : -1;
       p.inter_rep[i] = inter_on ? inter_j : -1;
+      if (p.saved_dist) {
+        p.saved_dist[i] = intra;
+        p.saved_dist[p.R + i] = inter;
+      }
     }
     if (kGrad) {   // pln_grad_emb_kernel's row, with the values already in registers
       const int ja = intra_on ? intra_j : -1, jb = inter_on ? inter_j : -1;
@@ -165,9 +198,9 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
           eh[q] = 0.f; g[q] = 0.f;
           if (d < p.D) {
             eh[q] = eraw[q] * inv;
-            float t = 0.f;
-            if (ja >= 0) t -= rh[ja * p.D + d];
-            if (jb >= 0) t += rh[jb * p.D + d];
+            float t = 0.f;   // d (relu(d_y - alpha) + relu(beta - d_c*)) / d e_hat
+            if (ja >= 0) t += dist_d_first<kDist>(eh[q], rh[ja * p.D + d], intra);
+            if (jb >= 0) t -= dist_d_first<kDist>(eh[q], rh[jb * p.D + d], inter);
             g[q] = t;
             dot = fmaf(eh[q], t, dot);
           }
@@ -204,9 +237,9 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
     for (int j = 0; j < p.Kr; ++j) {
       if (j / p.rpc == k / p.rpc) continue;  // own-class block masked with 1000 (:179-180)
       float dot = 0.f;
-      for (int d = lane; d < p.D; d += 32) dot = fmaf(rh[k * p.D + d], rh[j * p.D + d], dot);
+      for (int d = lane; d < p.D; d += 32) dot = dist_acc<kDist>(rh[k * p.D + d], rh[j * p.D + d], dot);
       dot = warp_sum(dot);
-      const float dist = 1.0f - dot;
+      const float dist = dist_finish<kDist>(dot);
       if (dist < best) {
         best = dist;
         best_j = j;
@@ -216,6 +249,7 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
     if (lane == 0) {
       p.partial[2 * gridDim.x + k] = h > 0.f ? h : 0.f;
       p.center_rep[k] = (h > 0.f) ? best_j : -1;
+      if (p.saved_dist) p.saved_dist[2 * p.R + k] = best;
     }
   }
 }
@@ -256,6 +290,7 @@ __global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ backward
+template <int kDist>
 __global__ void __launch_bounds__(kThreads) pln_grad_emb_kernel(const __grid_constant__ PlnParams p) {
   extern __shared__ __align__(16) float rh[];
   load_unit_reps(p, rh, nullptr);
@@ -270,6 +305,7 @@ __global__ void __launch_bounds__(kThreads) pln_grad_emb_kernel(const __grid_con
       continue;
     }
     const float inv = p.emb_inv_norm[i];
+    const float da = kDist == kL2 ? p.saved_dist[i] : 0.f, db = kDist == kL2 ? p.saved_dist[p.R + i] : 0.f;
     float eh[kMaxD / 32], g[kMaxD / 32];
     float dot = 0.f;
 #pragma unroll
@@ -279,8 +315,8 @@ __global__ void __launch_bounds__(kThreads) pln_grad_emb_kernel(const __grid_con
       if (d < p.D) {
         eh[q] = __ldg(p.emb + (int64_t)i * p.D + d) * inv;
         float t = 0.f;
-        if (ja >= 0) t -= rh[ja * p.D + d];   // d/dS of relu(d_y - alpha) = -1, dS/de_hat = r_hat
-        if (jb >= 0) t += rh[jb * p.D + d];   // d/dS of relu(beta - d_c*) = +1
+        if (ja >= 0) t += dist_d_first<kDist>(eh[q], rh[ja * p.D + d], da);   // relu(d_y - alpha): +d dist / d e_hat (COS: -r_hat)
+        if (jb >= 0) t -= dist_d_first<kDist>(eh[q], rh[jb * p.D + d], db);   // relu(beta - d_c*): -d dist / d e_hat
         g[q] = t;
         dot = fmaf(eh[q], t, dot);
       }
@@ -295,7 +331,9 @@ __global__ void __launch_bounds__(kThreads) pln_grad_emb_kernel(const __grid_con
   }
 }
 
-// grid (Kr, kSeg): partial[seg][j][:] = sum over rows of segment seg (in row order) of G[i][j] * e_hat_i
+// grid (Kr, kSeg): partial[seg][j][:] = sum over rows of segment seg (in row order) of G[i][j] * d dist(e_hat_i, r_hat_j) / d r_hat_j
+// (COS: -e_hat_i)
+template <int kDist>
 __global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_constant__ PlnParams p) {
   __shared__ int s_rows[2048];       // |row+1| with sign = sign of G; segment length <= 2048 enforced by the host loop
   __shared__ int s_wcnt[kWarps + 1];
@@ -304,6 +342,7 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_c
   const int seg_len = osr::ceil_div(p.R, kSeg);
   const int r0 = seg * seg_len, r1 = min(p.R, r0 + seg_len);
   float acc[kMaxD / kThreads > 0 ? kMaxD / kThreads : 1] = {0.f};
+  const float rj = (kDist != kCos && tid < p.D) ? __ldg(p.reps + (int64_t)j * p.D + tid) * p.rep_inv_norm[j] : 0.f;   // r_hat_j[tid]
   for (int base = r0; base < r1; base += 2048) {
     // ordered compaction of matching rows of [base, base+2048): each thread owns 8 consecutive rows
     int code[8], cnt = 0;
@@ -346,6 +385,18 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_c
     // four rows per iteration: their loads are independent and issued together (the loop is latency-bound otherwise);
     // the FMAs keep the row order, so the sum is bit-identical to the one-row-at-a-time loop
     int q = 0;
+    if (kDist != kCos) {   // general form: the derivative depends on (e_hat_i - r_hat_j) and, for L2, on the saved distance
+      for (; q < n; ++q) {
+        const int c = s_rows[q];
+        const int i = (c < 0 ? -c : c) - 1;
+        const float coef = c < 0 ? 1.f : -1.f;   // intra hinge: +d dist, inter hinge: -d dist
+        const float dist = kDist == kL2 ? p.saved_dist[(c < 0 ? 0 : p.R) + i] : 0.f;
+        if (tid < p.D) {
+          const float eh = __ldg(p.emb + (int64_t)i * p.D + tid) * p.emb_inv_norm[i];
+          acc[0] = fmaf(coef, dist_d_second<kDist>(eh, rj, dist), acc[0]);
+        }
+      }
+    }
     for (; q + 4 <= n; q += 4) {
       float x[4], w[4];
 #pragma unroll
@@ -370,6 +421,7 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_c
   if (tid < p.D) p.partial[((int64_t)seg * p.Kr + j) * p.D + tid] = acc[0];
 }
 
+template <int kDist>
 __global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_constant__ PlnParams p) {
   extern __shared__ __align__(16) float rh[];
   __shared__ float s_red[kWarps];
@@ -383,10 +435,13 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_con
     if (tid < p.D) {
       for (int seg = 0; seg < kSeg; ++seg) g += p.partial[((int64_t)seg * p.Kr + j) * p.D + tid];
       // separation term: (Gamma + Gamma^T) r_hat, Gamma[k][j*_k] = center_weight * [hinge active]
+      // relu(beta + alpha - c_dist_k): -center_weight * d dist(r_hat_k, r_hat_j*k) / d (either argument)
+      const float* cd = p.saved_dist ? p.saved_dist + 2 * p.R : nullptr;
       const int js = p.center_rep[j];
-      if (js >= 0) g = fmaf(p.center_weight, rh[js * p.D + tid], g);
+      if (js >= 0) g = fmaf(-p.center_weight, dist_d_first<kDist>(rh[j * p.D + tid], rh[js * p.D + tid], kDist == kL2 ? cd[j] : 0.f), g);
       for (int k = 0; k < p.Kr; ++k)
-        if (p.center_rep[k] == j) g = fmaf(p.center_weight, rh[k * p.D + tid], g);
+        if (p.center_rep[k] == j)
+          g = fmaf(-p.center_weight, dist_d_second<kDist>(rh[k * p.D + tid], rh[j * p.D + tid], kDist == kL2 ? cd[k] : 0.f), g);
     }
     float dot = (tid < p.D) ? rh[j * p.D + tid] * g : 0.f;
     dot = warp_sum(dot);
@@ -408,6 +463,7 @@ struct NearestParams {
 };
 
 // PLN.inference: nearest prototype + unknown threshold, one warp per row
+template <int kDist>
 __global__ void __launch_bounds__(kThreads) pln_nearest_kernel(const __grid_constant__ NearestParams q) {
   extern __shared__ __align__(16) float rh[];
   const PlnParams& p = q.base;
@@ -436,10 +492,10 @@ __global__ void __launch_bounds__(kThreads) pln_nearest_kernel(const __grid_cons
 #pragma unroll
         for (int t = 0; t < kMaxD / 32; ++t) {
           const int d = t * 32 + lane;
-          if (d < p.D) dot = fmaf(e[t], rh[j * p.D + d], dot);
+          if (d < p.D) dot = dist_acc<kDist>(e[t], rh[j * p.D + d], dot);
         }
         dot = warp_sum(dot);
-        const float dist = 1.0f - dot;
+        const float dist = dist_finish<kDist>(dot);
         if (best_c < 0 || dist < best) {
           best = dist;
           best_c = c;
@@ -462,6 +518,22 @@ int check_shape(int R, int D, int K, int rpc) {
   return 0;
 }
 
+int check_dist(int distance_type, const void* saved_dist, bool need_saved) {
+  if (distance_type != kCos && distance_type != kL1 && distance_type != kL2)
+    return osr::fail_arg(OSR_E_ARG, "pln: distance_type %d is not OSR_PLN_DIST_COS / _L1 / _L2", distance_type);
+  if (need_saved && distance_type == kL2 && !saved_dist)
+    return osr::fail_arg(OSR_E_ARG, "pln: the L2 distance needs the saved_dist buffer (2 R + K * reps_per_class floats)");
+  return 0;
+}
+
+// run STMT with kD bound to the compile-time distance type
+#define OSR_PLN_DISPATCH(DT, ...)                                  \
+  do {                                                             \
+    if ((DT) == kL1) { constexpr int kD = kL1; __VA_ARGS__; }      \
+    else if ((DT) == kL2) { constexpr int kD = kL2; __VA_ARGS__; } \
+    else { constexpr int kD = kCos; __VA_ARGS__; }                 \
+  } while (0)
+
 // two rows per warp: enough CTAs to fill the GPU in one wave at R = 8192 (the stage is latency-bound)
 int fwd_ctas(int R) { return R < 2 * kWarps ? 1 : (R / (2 * kWarps) > 592 ? 592 : R / (2 * kWarps)); }
 
@@ -476,13 +548,14 @@ size_t osr_pln_workspace(int R, int D, int K, int reps_per_class) {
 }
 
 int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, int R, int D,
-                     int K, int reps_per_class, float alpha, float beta, float loss_weight, float iou_threshold,
-                     float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
-                     float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep,
+                     int K, int reps_per_class, int distance_type, float alpha, float beta, float loss_weight,
+                     float iou_threshold, float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
+                     float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep, float* saved_dist,
                      void* workspace, size_t workspace_bytes, void* stream) {
   osr::DeviceGuard device_guard(emb);
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
+  if ((rc = check_dist(distance_type, saved_dist, false))) return rc;
   if (!reps || !loss_terms || !rep_inv_norm || !center_rep || !workspace ||
       (R > 0 && (!emb || !labels || !ious || !emb_inv_norm || !intra_rep || !inter_rep)))
     return osr::fail_arg(OSR_E_ARG, "pln_loss_fwd: null pointer argument");
@@ -495,12 +568,15 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
   p.r_norm = r_norm; p.center_weight = center_weight;
   p.loss_terms = loss_terms; p.emb_inv_norm = emb_inv_norm; p.rep_inv_norm = rep_inv_norm;
   p.intra_rep = intra_rep; p.inter_rep = inter_rep; p.center_rep = center_rep;
+  p.dist_type = distance_type; p.saved_dist = saved_dist;
   p.partial = static_cast<float*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.num_ctas = fwd_ctas(R > 0 ? R : 1);   // also launched for R == 0: the separation term does not depend on the rows
-  pln_rows_kernel<false><<<p.num_ctas, kThreads, smem, s>>>(p);
+  OSR_PLN_DISPATCH(distance_type, {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<false, kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pln_rows_kernel<false, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
+  });
   OSR_LAUNCH_CHECK();
   pln_final_kernel<<<1, kThreads, 0, s>>>(p);
   OSR_LAUNCH_CHECK();
@@ -510,13 +586,15 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
 // Loss forward AND closed-form backward in four launches (rows + d loss / d emb fused, loss reduction, prototype-gradient
 // partials, prototype-gradient final) instead of five plus the autograd plumbing: the training step's S5.
 int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
-                         int R, int D, int K, int reps_per_class, float alpha, float beta, float loss_weight,
-                         float iou_threshold, float r_norm, float center_weight, float* loss_terms, float* emb_inv_norm,
-                         float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep, int32_t* center_rep, float* grad_emb,
-                         float* grad_reps, void* workspace, size_t workspace_bytes, void* stream) {
+                         int R, int D, int K, int reps_per_class, int distance_type, float alpha, float beta,
+                         float loss_weight, float iou_threshold, float r_norm, float center_weight, float* loss_terms,
+                         float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep,
+                         int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   osr::DeviceGuard device_guard(grad_reps);
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
+  if ((rc = check_dist(distance_type, saved_dist, true))) return rc;
   if (!reps || !loss_terms || !rep_inv_norm || !center_rep || !workspace || !grad_loss || !grad_reps ||
       (R > 0 && (!emb || !labels || !ious || !emb_inv_norm || !intra_rep || !inter_rep || !grad_emb)))
     return osr::fail_arg(OSR_E_ARG, "pln_loss_fwd_bwd: null pointer argument");
@@ -530,32 +608,36 @@ int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* lab
   p.loss_terms = loss_terms; p.emb_inv_norm = emb_inv_norm; p.rep_inv_norm = rep_inv_norm;
   p.intra_rep = intra_rep; p.inter_rep = inter_rep; p.center_rep = center_rep;
   p.grad_loss = grad_loss; p.grad_emb = grad_emb; p.grad_reps = grad_reps;
+  p.dist_type = distance_type; p.saved_dist = saved_dist;
   p.partial = static_cast<float*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.num_ctas = fwd_ctas(R > 0 ? R : 1);
-  pln_rows_kernel<true><<<p.num_ctas, kThreads, smem, s>>>(p);
-  OSR_LAUNCH_CHECK();
-  pln_final_kernel<<<1, kThreads, 0, s>>>(p);   // reads the forward partials before the backward partials reuse the workspace
-  OSR_LAUNCH_CHECK();
-  pln_grad_reps_partial<<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
-  OSR_LAUNCH_CHECK();
-  pln_grad_reps_final<<<p.Kr, kThreads, smem, s>>>(p);
-  OSR_LAUNCH_CHECK();
+  OSR_PLN_DISPATCH(distance_type, {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<true, kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pln_rows_kernel<true, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+    pln_final_kernel<<<1, kThreads, 0, s>>>(p);   // reads the forward partials before the backward partials reuse the workspace
+    OSR_LAUNCH_CHECK();
+    pln_grad_reps_partial<kD><<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
+    OSR_LAUNCH_CHECK();
+    pln_grad_reps_final<kD><<<p.Kr, kThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+  });
   return 0;
 }
 
 int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels, const float* emb_inv_norm,
                      const float* rep_inv_norm, const int32_t* intra_rep, const int32_t* inter_rep,
-                     const int32_t* center_rep, const float* grad_loss, int R, int D, int K, int reps_per_class,
-                     float loss_weight, float r_norm, float center_weight, float* grad_emb, float* grad_reps,
-                     void* workspace, size_t workspace_bytes, void* stream) {
+                     const int32_t* center_rep, const float* saved_dist, const float* grad_loss, int R, int D, int K,
+                     int reps_per_class, int distance_type, float loss_weight, float r_norm, float center_weight,
+                     float* grad_emb, float* grad_reps, void* workspace, size_t workspace_bytes, void* stream) {
   osr::DeviceGuard device_guard(emb);
   (void)labels;
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
+  if ((rc = check_dist(distance_type, saved_dist, true))) return rc;
   if (!reps || !rep_inv_norm || !center_rep || !grad_loss || !grad_reps || !workspace ||
       (R > 0 && (!emb || !emb_inv_norm || !intra_rep || !inter_rep || !grad_emb)))
     return osr::fail_arg(OSR_E_ARG, "pln_loss_bwd: null pointer argument");
@@ -569,29 +651,34 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
   p.intra_rep = const_cast<int32_t*>(intra_rep); p.inter_rep = const_cast<int32_t*>(inter_rep);
   p.center_rep = const_cast<int32_t*>(center_rep);
   p.grad_loss = grad_loss; p.grad_emb = grad_emb; p.grad_reps = grad_reps;
+  p.dist_type = distance_type; p.saved_dist = const_cast<float*>(saved_dist);
   p.partial = static_cast<float*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_emb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (R > 0) {
-    int ctas = osr::ceil_div(R, kWarps * 4);
-    if (ctas > 592) ctas = 592;
-    pln_grad_emb_kernel<<<ctas, kThreads, smem, s>>>(p);
+  OSR_PLN_DISPATCH(distance_type, {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_emb_kernel<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (R > 0) {
+      int ctas = osr::ceil_div(R, kWarps * 4);
+      if (ctas > 592) ctas = 592;
+      pln_grad_emb_kernel<kD><<<ctas, kThreads, smem, s>>>(p);
+      OSR_LAUNCH_CHECK();
+    }
+    pln_grad_reps_partial<kD><<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
     OSR_LAUNCH_CHECK();
-  }
-  pln_grad_reps_partial<<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
-  OSR_LAUNCH_CHECK();
-  pln_grad_reps_final<<<p.Kr, kThreads, smem, s>>>(p);
-  OSR_LAUNCH_CHECK();
+    pln_grad_reps_final<kD><<<p.Kr, kThreads, smem, s>>>(p);
+    OSR_LAUNCH_CHECK();
+  });
   return 0;
 }
 
-int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, float unk_thr,
-                    int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist, void* stream) {
+int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, int reps_per_class, int distance_type,
+                    float unk_thr, int64_t unknown_id, const int64_t* class_id_map, int64_t* pred, float* min_dist,
+                    void* stream) {
   osr::DeviceGuard device_guard(emb);
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
+  if ((rc = check_dist(distance_type, nullptr, false))) return rc;
   if (R == 0) return 0;
   if (!emb || !reps || !pred || !min_dist) return osr::fail_arg(OSR_E_ARG, "pln_nearest: null pointer argument");
   NearestParams q{};
@@ -599,10 +686,12 @@ int osr_pln_nearest(const float* emb, const float* reps, int R, int D, int K, in
   q.base.R = R; q.base.D = D; q.base.K = K; q.base.rpc = reps_per_class; q.base.Kr = K * reps_per_class;
   q.unk_thr = unk_thr; q.unknown_id = unknown_id; q.class_id_map = class_id_map; q.pred = pred; q.min_dist = min_dist;
   const size_t smem = (size_t)q.base.Kr * D * sizeof(float);
-  OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas = osr::ceil_div(R, kWarps * 4);
   if (ctas > 592) ctas = 592;
-  pln_nearest_kernel<<<ctas, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  OSR_PLN_DISPATCH(distance_type, {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_nearest_kernel<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pln_nearest_kernel<kD><<<ctas, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(q);
+  });
   OSR_LAUNCH_CHECK();
   return 0;
 }

@@ -70,18 +70,18 @@ SIGNATURES = {
         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "osr_pln_loss_fwd": (C.c_int, [
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_loss_bwd": (C.c_int, [
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_loss_fwd_bwd": (C.c_int, [
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_encode_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "osr_pln_encode_fwd": (C.c_int, [
@@ -90,7 +90,7 @@ SIGNATURES = {
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
         C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_nearest": (C.c_int, [
-        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_void_p]),
     "osr_rcnn_decode_score": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -23,9 +23,21 @@ from . import _lib
 from .structures import Instances
 
 
+DISTANCE_TYPES = {"COS": 0, "L1": 1, "L2": 2}   # include/osr.h OSR_PLN_DIST_*  (MODEL.PLN.DISTANCE_TYPE)
+
+
+def _dist_code(distance_type) -> int:
+    if isinstance(distance_type, int):
+        return distance_type
+    try:
+        return DISTANCE_TYPES[distance_type]
+    except KeyError:
+        raise ValueError(f"MODEL.PLN.DISTANCE_TYPE must be one of {sorted(DISTANCE_TYPES)}, got {distance_type!r}") from None
+
+
 def _pln_fwd(emb, reps, labels, ious, cfg):
     """osr_pln_loss_fwd: returns (loss scalar tensor, saved tuple for ``_pln_bwd``)."""
-    (K, rpc, alpha, beta, loss_weight, iou_thr, r_norm, center_weight, emb_grad_scale) = cfg
+    (K, rpc, alpha, beta, loss_weight, iou_thr, r_norm, center_weight, emb_grad_scale, dist) = cfg
     lib = _lib.lib()
     _lib.require_cuda(emb, reps, labels, ious)
     emb_c = emb.contiguous().float()
@@ -42,23 +54,24 @@ def _pln_fwd(emb, reps, labels, ious, cfg):
     intra = torch.empty(R, dtype=torch.int32, device=dev)
     inter = torch.empty(R, dtype=torch.int32, device=dev)
     center = torch.empty(Kr, dtype=torch.int32, device=dev)
+    sdist = torch.empty(2 * R + Kr, dtype=torch.float32, device=dev)   # distances saved for the (L2) backward
     ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
     rn = float(R) if r_norm is None else float(r_norm)
     rc = lib.osr_pln_loss_fwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(),
-                              R, D, K, rpc, alpha, beta, loss_weight, iou_thr, rn, center_weight,
+                              R, D, K, rpc, dist, alpha, beta, loss_weight, iou_thr, rn, center_weight,
                               terms.data_ptr(), emb_inv.data_ptr(), rep_inv.data_ptr(), intra.data_ptr(),
-                              inter.data_ptr(), center.data_ptr(), ws.data_ptr(), ws.numel(),
+                              inter.data_ptr(), center.data_ptr(), sdist.data_ptr(), ws.data_ptr(), ws.numel(),
                               _lib.stream_ptr(dev))
     _lib.check(rc, "osr_pln_loss_fwd")
-    saved = (emb_c, reps_c, labels_c, emb_inv, rep_inv, intra, inter, center)
-    return terms[0], saved, (K, rpc, loss_weight, rn, center_weight, emb_grad_scale)
+    saved = (emb_c, reps_c, labels_c, emb_inv, rep_inv, intra, inter, center, sdist)
+    return terms[0], saved, (K, rpc, loss_weight, rn, center_weight, emb_grad_scale, dist)
 
 
 def _pln_bwd(saved, bcfg, grad_loss):
     """osr_pln_loss_bwd (closed form): returns (grad_emb, grad_reps)."""
     lib = _lib.lib()
-    emb, reps, labels, emb_inv, rep_inv, intra, inter, center = saved
-    K, rpc, loss_weight, rn, center_weight, emb_grad_scale = bcfg
+    emb, reps, labels, emb_inv, rep_inv, intra, inter, center, sdist = saved
+    K, rpc, loss_weight, rn, center_weight, emb_grad_scale, dist = bcfg
     R, D = emb.shape
     dev = emb.device
     gl = grad_loss.reshape(1).contiguous().float()
@@ -66,8 +79,8 @@ def _pln_bwd(saved, bcfg, grad_loss):
     grad_reps = torch.empty_like(reps)
     ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
     rc = lib.osr_pln_loss_bwd(emb.data_ptr(), reps.data_ptr(), labels.data_ptr(), emb_inv.data_ptr(),
-                              rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
-                              gl.data_ptr(), R, D, K, rpc, loss_weight, rn, center_weight,
+                              rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(), sdist.data_ptr(),
+                              gl.data_ptr(), R, D, K, rpc, dist, loss_weight, rn, center_weight,
                               grad_emb.data_ptr(), grad_reps.data_ptr(), ws.data_ptr(), ws.numel(),
                               _lib.stream_ptr(dev))
     _lib.check(rc, "osr_pln_loss_bwd")
@@ -92,7 +105,8 @@ class _PlnLossFn(torch.autograd.Function):
 
 def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_per_class: int = 1, alpha: float = 0.1,
                      beta: float = 0.9, loss_weight: float = 0.5, iou_threshold: float = 0.5, r_norm: Optional[float] = None,
-                     center_weight: float = 1.0, emb_grad_scale: float = 1.0, grad_loss: Optional[torch.Tensor] = None):
+                     center_weight: float = 1.0, emb_grad_scale: float = 1.0, grad_loss: Optional[torch.Tensor] = None,
+                     distance_type="COS"):
     """Loss and its closed-form gradients in one call, WITHOUT autograd: ``(loss, d loss / d emb, d loss / d reps)``.
     Same kernels as ``pln_loss_from_emb`` + ``backward()``; used by the device-resident training step (no autograd engine
     hop, capturable in a CUDA graph)."""
@@ -110,8 +124,8 @@ def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_pe
         assert reps_c.shape == (Kr, D)
         gl = _ones_scalar(dev) if grad_loss is None else grad_loss.reshape(1).contiguous().float()
         # one allocation for the small per-row / per-prototype outputs
-        small = torch.empty(4 + R + Kr, dtype=torch.float32, device=dev)
-        terms, emb_inv, rep_inv = small[:4], small[4:4 + R], small[4 + R:]
+        small = torch.empty(4 + R + Kr + 2 * R + Kr, dtype=torch.float32, device=dev)
+        terms, emb_inv, rep_inv, sdist = small[:4], small[4:4 + R], small[4 + R:4 + R + Kr], small[4 + R + Kr:]
         idx = torch.empty(2 * R + Kr, dtype=torch.int32, device=dev)
         intra, inter, center = idx[:R], idx[R:2 * R], idx[2 * R:]
         grad_emb = torch.empty_like(emb_c)
@@ -119,9 +133,10 @@ def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_pe
         ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
         rn = float(R) if r_norm is None else float(r_norm)
         rc = lib.osr_pln_loss_fwd_bwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(), gl.data_ptr(),
-                                      R, D, K, rpc, float(alpha), float(beta), float(loss_weight), float(iou_threshold), rn,
-                                      float(center_weight), terms.data_ptr(), emb_inv.data_ptr(), rep_inv.data_ptr(),
-                                      intra.data_ptr(), inter.data_ptr(), center.data_ptr(), grad_emb.data_ptr(),
+                                      R, D, K, rpc, _dist_code(distance_type), float(alpha), float(beta), float(loss_weight),
+                                      float(iou_threshold), rn, float(center_weight), terms.data_ptr(), emb_inv.data_ptr(),
+                                      rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
+                                      sdist.data_ptr(), grad_emb.data_ptr(),
                                       grad_reps.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "osr_pln_loss_fwd_bwd")
         if emb_grad_scale != 1.0:
@@ -179,15 +194,16 @@ def pln_encode_tc(x, weight, bias=None):
 
 def pln_loss_from_emb(emb, reps, labels, ious, *, num_known_classes: int, reps_per_class: int = 1,
                       alpha: float = 0.1, beta: float = 0.9, loss_weight: float = 0.5, iou_threshold: float = 0.5,
-                      r_norm: Optional[float] = None, center_weight: float = 1.0, emb_grad_scale: float = 1.0):
+                      r_norm: Optional[float] = None, center_weight: float = 1.0, emb_grad_scale: float = 1.0,
+                      distance_type="COS"):
     """Functional form: labels already id-mapped ([0,K) known, anything else ignored)."""
     cfg = (int(num_known_classes), int(reps_per_class), float(alpha), float(beta), float(loss_weight),
-           float(iou_threshold), r_norm, float(center_weight), float(emb_grad_scale))
+           float(iou_threshold), r_norm, float(center_weight), float(emb_grad_scale), _dist_code(distance_type))
     return _PlnLossFn.apply(emb, reps, labels, ious, cfg)
 
 
 def pln_nearest(emb, reps, *, num_known_classes: int, reps_per_class: int, unk_thr: float, unknown_id: int,
-                class_id: Optional[torch.Tensor] = None):
+                class_id: Optional[torch.Tensor] = None, distance_type="COS"):
     lib = _lib.lib()
     _lib.require_cuda(emb, reps)
     emb_c = emb.contiguous().float()
@@ -197,7 +213,7 @@ def pln_nearest(emb, reps, *, num_known_classes: int, reps_per_class: int, unk_t
     md = torch.empty(R, dtype=torch.float32, device=emb_c.device)
     cid = None if class_id is None else class_id.contiguous().to(torch.int64)
     rc = lib.osr_pln_nearest(emb_c.data_ptr(), reps_c.data_ptr(), R, D, num_known_classes, reps_per_class,
-                             float(unk_thr), int(unknown_id), _lib.ptr(cid), pred.data_ptr(), md.data_ptr(),
+                             _dist_code(distance_type), float(unk_thr), int(unknown_id), _lib.ptr(cid), pred.data_ptr(), md.data_ptr(),
                              _lib.stream_ptr(emb_c.device))
     _lib.check(rc, "osr_pln_nearest")
     return pred, md
@@ -212,10 +228,7 @@ class PLN(nn.Module):
                  opendet_benchmark: bool = True, known_class_ids: Optional[Sequence[int]] = None,
                  device="cuda", gather: bool = False, process_group=None, encoder_impl: str = "fp32"):
         super().__init__()
-        if distance_type != "COS":
-            raise NotImplementedError(
-                "osr_b200.PLN implements DISTANCE_TYPE 'COS' (what both shipped configs use, "
-                "configs/*/openset_rcnn_R50_FPN_128k.yaml:42)")
+        _dist_code(distance_type)   # 'COS' | 'L1' | 'L2' (:156-161); anything else is a config error
         self.num_classes = num_classes
         self.num_known_classes = num_known_classes
         self.feature_dim = feature_dim
@@ -286,7 +299,8 @@ class PLN(nn.Module):
             gt_classes = self.id_map[gt_classes]             # :146-147
         R_local = gt_classes.numel()
         kw = dict(num_known_classes=self.num_known_classes, reps_per_class=self.reps_per_class, alpha=self.alpha,
-                  beta=self.beta, loss_weight=self.loss_weight, iou_threshold=self.iou_threshold)
+                  beta=self.beta, loss_weight=self.loss_weight, iou_threshold=self.iou_threshold,
+                  distance_type=self.distance_type)
         if self.gather:
             from .dist import gathered_pln_loss
             loss = gathered_pln_loss(emb_features, self.representatives, gt_classes, ious,
@@ -317,7 +331,8 @@ class PLN(nn.Module):
         unknown_id = 80 if self.opendet_benchmark else 1000
         pred, _ = pln_nearest(emb, self.representatives, num_known_classes=self.num_known_classes,
                               reps_per_class=self.reps_per_class, unk_thr=self.unk_thr, unknown_id=unknown_id,
-                              class_id=None if self.opendet_benchmark else self.class_id)
+                              class_id=None if self.opendet_benchmark else self.class_id,
+                              distance_type=self.distance_type)
         results, o = [], 0
         for inst, s in zip(fg_instances, sizes):
             inst.features = rec[o:o + s]

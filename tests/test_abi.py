@@ -57,9 +57,12 @@ def test_argument_errors_are_reported_without_a_gpu():
     rc = h.osr_roi_align_fwd(fl, 1, 1, 16, C.c_void_p(256), 4, 14, 0, 1, 224, 4, 2, C.c_void_p(256), C.c_void_p(256),
                              None, 0, None)
     assert rc == -2 and b"pooler resolution" in h.osr_last_error()
-    rc = h.osr_pln_loss_fwd(None, None, None, None, 4, 512, 20, 1, 0.1, 0.9, 0.5, 0.5, 4.0, 1.0, None, None, None, None,
-                            None, None, None, 0, None)
+    rc = h.osr_pln_loss_fwd(None, None, None, None, 4, 512, 20, 1, 0, 0.1, 0.9, 0.5, 0.5, 4.0, 1.0, None, None, None, None,
+                            None, None, None, None, 0, None)
     assert rc == -2 and b"embedding dim" in h.osr_last_error()
+    rc = h.osr_pln_loss_fwd(None, None, None, None, 4, 256, 20, 1, 7, 0.1, 0.9, 0.5, 0.5, 4.0, 1.0, None, None, None, None,
+                            None, None, None, None, 0, None)
+    assert rc == -1 and b"distance_type" in h.osr_last_error()
     assert h.osr_pln_workspace(8192, 256, 20, 1) >= 8 * 20 * 256 * 4
     assert h.osr_nms_workspace(1000, 2, 1000) > 2 * 1000 * 16 * 8
 

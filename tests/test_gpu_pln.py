@@ -225,3 +225,62 @@ def test_zero_rows_gives_separation_term_only():
     lb = opln.pln_loss_from_emb(emb.detach().cpu(), pi.reps.cpu(), labels.cpu(), ious.cpu(), **_kw())
     torch.testing.assert_close(la.cpu(), lb, rtol=1e-5, atol=1e-8)
     assert torch.isfinite(reps.grad).all()
+
+
+@pytest.mark.parametrize("dist,rpc,R,K", [("L1", 1, 4096, 20), ("L2", 1, 4096, 20), ("L2", 2, 1500, 28), ("L1", 5, 333, 28)])
+def test_l1_l2_distances_loss_and_gradients_match_oracle(dist, rpc, R, K):
+    """MODEL.PLN.DISTANCE_TYPE L1 / L2 (prototype_learning_network.py:156-161,171-176) at training sizes against the
+    oracle's torch.cdist + autograd; alpha / beta sit at the medians of the intra / inter distances so that both hinges are
+    half active.  Rows within 1e-5 of a decision boundary are taken out of the foreground on both sides."""
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_from_emb, pln_loss_fwd_bwd, pln_nearest
+    pi = synth.make_pln_inputs(R, num_known=K, num_classes=81 if K == 20 else 88, seed=R + rpc, device="cuda:0")
+    emb0 = (pi.roi_features @ pi.enc_w.t()).detach()
+    g = torch.Generator(device="cuda:0").manual_seed(R)
+    reps = torch.randn(K * rpc, emb0.shape[1], device="cuda:0", generator=g)
+    eh, rh = torch.nn.functional.normalize(emb0), torch.nn.functional.normalize(reps)
+    d3 = opln.pln_distance(eh, rh, dist).reshape(R, K, rpc)
+    clear = torch.ones(R, dtype=torch.bool, device="cuda:0")
+    if rpc > 1:
+        t2 = torch.topk(d3, 2, dim=2, largest=False).values
+        clear = ((t2[:, :, 1] - t2[:, :, 0]) > 1e-5).all(dim=1)
+    dmin = d3.min(dim=2)[0]
+    fg = (pi.gt_classes >= 0) & (pi.gt_classes < K) & (pi.ious > 0.5)
+    y = pi.gt_classes.clamp(0, K - 1)
+    intra = dmin.gather(1, y[:, None])[:, 0]
+    dm = dmin.clone(); dm.scatter_(1, y[:, None], 1000.0)
+    top2 = torch.topk(dm, 2, dim=1, largest=False).values
+    alpha, beta = float(intra[fg].median()), float(top2[fg, 0].median())
+    safe = ((intra - alpha).abs() > 1e-5) & ((beta - top2[:, 0]).abs() > 1e-5) & ((top2[:, 1] - top2[:, 0]) > 1e-5) & clear
+    ious = torch.where(safe | ~fg, pi.ious, torch.zeros_like(pi.ious))
+    kw = dict(num_known_classes=K, reps_per_class=rpc, alpha=alpha, beta=beta, loss_weight=0.5, iou_threshold=0.5,
+              distance_type=dist)
+    ea = emb0.clone().requires_grad_(True); ra = reps.clone().requires_grad_(True)
+    la = pln_loss_from_emb(ea, ra, pi.gt_classes, ious, **kw)
+    (la * 1.3).backward()
+    eb = emb0.clone().requires_grad_(True); rb = reps.clone().requires_grad_(True)
+    lb = opln.pln_loss_from_emb(eb, rb, pi.gt_classes, ious, **kw)
+    (lb * 1.3).backward()
+    torch.testing.assert_close(la, lb, rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(ea.grad, eb.grad, rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(ra.grad, rb.grad, rtol=1e-3, atol=1e-6)
+    assert float(ea.grad.abs().max()) > 0 and float(ra.grad.abs().max()) > 0
+    # fused forward + backward: bit-identical to the autograd pair
+    l2, ge, gr = pln_loss_fwd_bwd(emb0, reps, pi.gt_classes, ious, grad_loss=torch.full((1,), 1.3, device="cuda:0"), **kw)
+    assert torch.equal(l2, la.detach()) and torch.equal(ge, ea.grad) and torch.equal(gr, ra.grad)
+    # nearest prototype under the same distance
+    thr = float(dmin.min(dim=1)[0].median())
+    pred, md = pln_nearest(emb0, reps, num_known_classes=K, reps_per_class=rpc, unk_thr=thr, unknown_id=80, distance_type=dist)
+    best, arg = dmin.min(dim=1)
+    exp = torch.where(best > thr, torch.full_like(arg, 80), arg)
+    t2 = torch.topk(dmin, 2, dim=1, largest=False).values
+    ok = ((best - thr).abs() > 1e-5) & ((t2[:, 1] - t2[:, 0]) > 1e-5)
+    assert torch.equal(pred[ok], exp[ok])
+    torch.testing.assert_close(md, best, rtol=1e-5, atol=1e-6)
+
+
+def test_unknown_distance_type_is_a_config_error():
+    from osr_b200.pln import PLN
+    with pytest.raises(ValueError, match="DISTANCE_TYPE"):
+        PLN(num_classes=81, num_known_classes=20, feature_dim=64, embedding_dim=256, distance_type="L3", reps_per_class=1,
+            alpha=0.1, beta=0.9, loss_weight=0.5)
