@@ -60,8 +60,8 @@ def _pln_fwd(emb, reps, labels, ious, cfg):
     rc = lib.osr_pln_loss_fwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(),
                               R, D, K, rpc, dist, alpha, beta, loss_weight, iou_thr, rn, center_weight,
                               terms.data_ptr(), emb_inv.data_ptr(), rep_inv.data_ptr(), intra.data_ptr(),
-                              inter.data_ptr(), center.data_ptr(), sdist.data_ptr(), ws.data_ptr(), ws.numel(),
-                              _lib.stream_ptr(dev))
+                              inter.data_ptr(), center.data_ptr(), sdist.data_ptr() if dist == 2 else None, ws.data_ptr(),
+                              ws.numel(), _lib.stream_ptr(dev))   # (only the L2 backward reads the saved distances)
     _lib.check(rc, "osr_pln_loss_fwd")
     saved = (emb_c, reps_c, labels_c, emb_inv, rep_inv, intra, inter, center, sdist)
     return terms[0], saved, (K, rpc, loss_weight, rn, center_weight, emb_grad_scale, dist)
@@ -79,8 +79,8 @@ def _pln_bwd(saved, bcfg, grad_loss):
     grad_reps = torch.empty_like(reps)
     ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
     rc = lib.osr_pln_loss_bwd(emb.data_ptr(), reps.data_ptr(), labels.data_ptr(), emb_inv.data_ptr(),
-                              rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(), sdist.data_ptr(),
-                              gl.data_ptr(), R, D, K, rpc, dist, loss_weight, rn, center_weight,
+                              rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
+                              sdist.data_ptr() if dist == 2 else None, gl.data_ptr(), R, D, K, rpc, dist, loss_weight, rn, center_weight,
                               grad_emb.data_ptr(), grad_reps.data_ptr(), ws.data_ptr(), ws.numel(),
                               _lib.stream_ptr(dev))
     _lib.check(rc, "osr_pln_loss_bwd")
@@ -136,7 +136,7 @@ def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_pe
                                       R, D, K, rpc, _dist_code(distance_type), float(alpha), float(beta), float(loss_weight),
                                       float(iou_threshold), rn, float(center_weight), terms.data_ptr(), emb_inv.data_ptr(),
                                       rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
-                                      sdist.data_ptr(), grad_emb.data_ptr(),
+                                      sdist.data_ptr() if _dist_code(distance_type) == 2 else None, grad_emb.data_ptr(),
                                       grad_reps.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "osr_pln_loss_fwd_bwd")
         if emb_grad_scale != 1.0:
