@@ -593,6 +593,33 @@ def run_ours(args, rank, local_rank, world):
             bh = {"error": repr(e)[:300]}
         barrier(world)
 
+    # ---- the same step with the PLN encoder as the reference runs it: a plain fp32 nn.Linear (library GEMM, no TF32) ------------
+    f32enc = None
+    if not infer and not args.quick:
+        try:
+            import dataclasses
+            f_path = RoiPathStep(dataclasses.replace(cfg, encoder_impl="fp32"), dev)
+            for _ in range(3):
+                f_path.step()
+            torch.cuda.synchronize(dev)
+            barrier(world)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(10):
+                f_path.step()
+            f1.record()
+            torch.cuda.synchronize(dev)
+            f_ms = max_over_ranks(f0.elapsed_time(f1), world, dev) / 10
+            f32enc = {"ms_per_step": f_ms, "value": world * N * 1e3 / f_ms, "steps": 10, "launch": "eager",
+                      "note": "encoder = fp32 library GEMM (torch, allow_tf32 off) instead of the tcgen05 kind::tf32 kernel; everything "
+                              "else identical; compare with `eager`"}
+            del f_path
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            f32enc = {"error": repr(e)[:300]}
+        barrier(world)
+    _EXTRA["fp32_encoder"] = f32enc
+
     if infer or args.quick:
         if rank == 0:
             line = _line(args, world, cfg, N, value, ms_step, clocks, None, launches, roof, stages, alt, gbase, gathered, None,
@@ -632,6 +659,9 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+_EXTRA = {}   # optional keys of the JSON line filled in by the measurement blocks
+
+
 def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stages, alt, gbase, gathered, cpu, eager,
           graph_err, api, bh=None):
     infer = args.config == "cfg4"
@@ -666,6 +696,8 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
         line["api_step"] = api
     if bh is not None:
         line["with_box_head"] = bh
+    if _EXTRA.get("fp32_encoder") is not None:
+        line["fp32_encoder"] = _EXTRA["fp32_encoder"]
     if gathered is not None:
         line["gathered_pln"] = gathered
     if cpu is not None:
