@@ -88,31 +88,45 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
     if N == 0:
         return []
     dev = proposals[0].get("proposal_boxes").tensor.device
-    box_list, logit_list, counts, gcounts = [], [], [], []
-    for p, t in zip(proposals, targets):
-        b = p.get("proposal_boxes").tensor
-        lg = p.get("objectness_logits")
-        g = t.get("gt_boxes").tensor.to(dev)
+    # ONE concatenation for the whole batch, laid out [proposals_0, gt_0, proposals_1, gt_1, ...] (add_ground_truth_to_proposals:
+    # GT boxes after the proposals of their image, logit log((1-1e-10)/1e-10)); the per-image lists are views of it
+    gts = [t.get("gt_boxes").tensor.to(dev) for t in targets]
+    for g in gts:
         if len(g) == 0:
             raise IndexError("index 0 is out of bounds for dimension 0 with size 0 "
                              "(image without ground truth: osrcnn_roi_heads.py:193)")
-        if proposal_append_gt:   # add_ground_truth_to_proposals: GT boxes after the proposals, logit log((1-1e-10)/1e-10)
-            b = torch.cat((b, g), dim=0)
-            lg = torch.cat((lg, GT_LOGIT * torch.ones(len(g), device=dev)), dim=0)
-        box_list.append(b)
-        logit_list.append(lg)
-        counts.append(b.shape[0])
+    gt_logits = GT_LOGIT * torch.ones(sum(len(g) for g in gts), device=dev) if proposal_append_gt else None
+    parts_b, parts_l, counts, gcounts = [], [], [], []
+    go = 0
+    for p, g in zip(proposals, gts):
+        b = p.get("proposal_boxes").tensor
+        parts_b.append(b)
+        parts_l.append(p.get("objectness_logits"))
+        c = b.shape[0]
+        if proposal_append_gt:
+            parts_b.append(g)
+            parts_l.append(gt_logits[go:go + len(g)])
+            c += len(g)
+            go += len(g)
+        counts.append(c)
         gcounts.append(len(g))
-    boxes = torch.cat(box_list, dim=0)
-    gt_boxes = torch.cat([t.get("gt_boxes").tensor.to(dev) for t in targets], dim=0)
+    boxes = torch.cat(parts_b, dim=0)
+    logits = torch.cat(parts_l, dim=0)
+    gt_boxes = torch.cat(gts, dim=0)
     gt_classes = torch.cat([t.get("gt_classes").to(dev) for t in targets], dim=0)
-    off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0).tolist()), dtype=torch.int32, device=dev)
-    goff = torch.tensor([0] + list(torch.tensor(gcounts).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    offs, goffs = [0], [0]
+    for c, gc in zip(counts, gcounts):
+        offs.append(offs[-1] + c)
+        goffs.append(goffs[-1] + gc)
+    both = torch.tensor([offs, goffs], dtype=torch.int32).to(dev, non_blocking=True)   # one small H2D copy
+    off, goff = both[0], both[1]
     midx, miou, mlab, mcls = match_proposals(boxes, off, gt_boxes, gt_classes, goff, max(counts),
                                              iou_threshold=iou_threshold, background_label=num_classes)
     if randperm is None:
-        return _finish_batched(proposals, targets, box_list, logit_list, counts, off, midx, miou, mcls,
+        return _finish_batched(proposals, targets, boxes, logits, counts, offs, off, goff, midx, miou, mcls,
                                num_classes, batch_size_per_image, positive_fraction, proposal_append_gt, generator)
+    box_list = [boxes[offs[n]:offs[n + 1]] for n in range(N)]
+    logit_list = [logits[offs[n]:offs[n + 1]] for n in range(N)]
     out = []
     b0 = 0
     for n, (p, t) in enumerate(zip(proposals, targets)):
@@ -163,25 +177,39 @@ def sample_labels_batched(labels: torch.Tensor, valid: torch.Tensor, num_samples
     return torch.where(from_pos, gp, gn), npos + nneg
 
 
-def _finish_batched(proposals, targets, box_list, logit_list, counts, off, midx, miou, mcls, num_classes,
+def _finish_batched(proposals, targets, boxes, logits, counts, offs, off, goff, midx, miou, mcls, num_classes,
                     batch_size_per_image, positive_fraction, proposal_append_gt, generator):
     """Sampling + field gathering of ``label_and_sample_proposals`` for the whole batch: padded (N, Pmax) label matrix,
-    ``sample_labels_batched``, ONE host read of the per-image sample counts, then views."""
+    ``sample_labels_batched``, batched gathers of every sampled field (the targets' ``gt_*`` fields are concatenated once
+    and gathered once), ONE host read of the per-image sample counts, then views."""
     N = len(proposals)
     dev = mcls.device
     Pmax = max(counts)
-    cnt_t = torch.tensor(counts, device=dev)
-    img = torch.repeat_interleave(torch.arange(N, device=dev), cnt_t, output_size=int(sum(counts)))
-    local = torch.arange(int(sum(counts)), device=dev) - off.long()[img]
-    labels = torch.full((N, Pmax), -2, dtype=torch.int64, device=dev)
-    labels[img, local] = mcls
-    valid = torch.arange(Pmax, device=dev)[None, :] < cnt_t[:, None]
+    total = offs[-1]
+    if min(counts) == Pmax:       # equal counts: the label matrix is a view
+        labels = mcls.view(N, Pmax)
+        valid = torch.ones((N, Pmax), dtype=torch.bool, device=dev)
+    else:
+        cnt_t = (off[1:] - off[:-1]).long()
+        ar = torch.arange(Pmax, device=dev)
+        valid = ar[None, :] < cnt_t[:, None]
+        src = (off[:-1].long()[:, None] + ar[None, :]).clamp(max=total - 1)   # padded gather instead of a scatter
+        labels = torch.where(valid, mcls[src], torch.full((), -2, dtype=mcls.dtype, device=dev))
     idx, cnt = sample_labels_batched(labels, valid, batch_size_per_image, positive_fraction, num_classes, generator)
-    flat = idx + off.long()[:N, None]                         # positions in the concatenated proposal list
-    boxes = torch.cat(box_list, dim=0)
-    logits = torch.cat(logit_list, dim=0)
-    flat_c = flat.clamp(max=boxes.shape[0] - 1)
-    sb, sl, sc, si, sm = boxes[flat_c], logits[flat_c], mcls[flat_c], miou[flat_c], midx[flat_c].long()
+    flat_c = (idx + off[:-1].long()[:, None]).clamp(max=total - 1)     # positions in the concatenated proposal list
+    sb, sl, sc, si = boxes[flat_c], logits[flat_c], mcls[flat_c], miou[flat_c]
+    sm_g = midx[flat_c].long() + goff[:-1].long()[:, None]              # matched GT rows in the concatenated targets
+    # the targets' gt_* fields, concatenated once and gathered once (tensor / Boxes fields; anything else per image below)
+    gt_names = [name for name in targets[0].get_fields() if name.startswith("gt_")]
+    batched, per_image = {}, []
+    for name in gt_names:
+        vals = [t.get(name) for t in targets]
+        if all(isinstance(v, Boxes) for v in vals):
+            batched[name] = ("boxes", torch.cat([v.tensor.to(dev) for v in vals], dim=0)[sm_g])
+        elif all(torch.is_tensor(v) for v in vals):
+            batched[name] = ("tensor", torch.cat([v.to(dev) for v in vals], dim=0)[sm_g])
+        else:
+            per_image.append(name)
     n_s = cnt.tolist()                                        # the one host sync of the stage
     out = []
     for n, (p, t) in enumerate(zip(proposals, targets)):
@@ -195,9 +223,15 @@ def _finish_batched(proposals, targets, box_list, logit_list, counts, off, midx,
                     q.set(name, value[idx[n, :k]])
         q.set("gt_classes", sc[n, :k])
         q.set("ious", si[n, :k])
-        st = sm[n, :k]
-        for name, value in t.get_fields().items():
-            if name.startswith("gt_") and not q.has(name):
+        for name in gt_names:
+            if q.has(name):
+                continue
+            if name in batched:
+                kind, v = batched[name]
+                q.set(name, Boxes(v[n, :k]) if kind == "boxes" else v[n, :k])
+            else:
+                value = t.get(name)
+                st = sm_g[n, :k] - goff[n].long()
                 q.set(name, value.to(dev)[st] if hasattr(value, "to") else value[st])
         out.append(q)
     return out
