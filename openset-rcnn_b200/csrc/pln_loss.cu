@@ -81,6 +81,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// four independent butterfly reductions, interleaved (the distance loops are bound by the latency of these chains)
+__device__ __forceinline__ void warp_sum4(float (&v)[4]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+  }
+}
+
 // Normalise the prototypes into shared memory: rh[j][d] = r[j][d] / max(||r_j||, eps).  One warp per prototype.
 __device__ __forceinline__ void load_unit_reps(const PlnParams& p, float* rh, float* inv_norm_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,30 +152,47 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
     // distances to all prototypes; min over the reps of each class (:164)
     float intra = 0.f, inter = 1000.f;   // sentinel 1000 as in :168
     int intra_j = -1, inter_j = -1;
-    for (int c = 0; c < p.K; ++c) {
+    {
+      // prototypes in index order, four at a time (their reductions overlap); per class the first minimum wins (:164), the
+      // own class feeds intra, the first minimum over the other classes inter (:166-169)
       float best = 0.f;
-      int best_j = -1;
-      for (int r = 0; r < p.rpc; ++r) {
-        const int j = c * p.rpc + r;
-        float dot = 0.f;
+      int best_j = -1, r = 0, c = 0;
+      for (int j0 = 0; j0 < p.Kr; j0 += 4) {
+        float dd[4];
 #pragma unroll
-        for (int q = 0; q < kMaxD / 32; ++q) {
-          const int d = q * 32 + lane;
-          if (d < p.D) dot = dist_acc<kDist>(e[q], rh[j * p.D + d], dot);
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(j0 + u, p.Kr - 1);
+          float dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < kMaxD / 32; ++q) {
+            const int d = q * 32 + lane;
+            if (d < p.D) dot = dist_acc<kDist>(e[q], rh[j * p.D + d], dot);
+          }
+          dd[u] = dot;
         }
-        dot = warp_sum(dot);
-        const float dist = dist_finish<kDist>(dot);
-        if (best_j < 0 || dist < best) {
-          best = dist;
-          best_j = j;
+        warp_sum4(dd);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          if (j < p.Kr) {
+            const float dist = dist_finish<kDist>(dd[u]);
+            if (r == 0 || dist < best) {
+              best = dist;
+              best_j = j;
+            }
+            if (++r == p.rpc) {   // class c complete
+              if (c == (int)y) {
+                intra = best;
+                intra_j = best_j;
+              } else if (best < inter) {
+                inter = best;
+                inter_j = best_j;
+              }
+              r = 0;
+              ++c;
+            }
+          }
         }
-      }
-      if (c == (int)y) {
-        intra = best;
-        intra_j = best_j;
-      } else if (best < inter) {
-        inter = best;
-        inter_j = best_j;
       }
     }
     const bool intra_on = (intra - p.alpha) > 0.f;
@@ -234,15 +260,25 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
   for (int k = blockIdx.x * kWarps + warp; k < p.Kr; k += gridDim.x * kWarps) {
     float best = 1000.f;
     int best_j = -1;
-    for (int j = 0; j < p.Kr; ++j) {
-      if (j / p.rpc == k / p.rpc) continue;  // own-class block masked with 1000 (:179-180)
-      float dot = 0.f;
-      for (int d = lane; d < p.D; d += 32) dot = dist_acc<kDist>(rh[k * p.D + d], rh[j * p.D + d], dot);
-      dot = warp_sum(dot);
-      const float dist = dist_finish<kDist>(dot);
-      if (dist < best) {
-        best = dist;
-        best_j = j;
+    for (int j0 = 0; j0 < p.Kr; j0 += 4) {
+      float dd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, p.Kr - 1);
+        float dot = 0.f;
+        for (int d = lane; d < p.D; d += 32) dot = dist_acc<kDist>(rh[k * p.D + d], rh[j * p.D + d], dot);
+        dd[u] = dot;
+      }
+      warp_sum4(dd);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j >= p.Kr || j / p.rpc == k / p.rpc) continue;  // own-class block masked with 1000 (:179-180)
+        const float dist = dist_finish<kDist>(dd[u]);
+        if (dist < best) {
+          best = dist;
+          best_j = j;
+        }
       }
     }
     const float h = (p.beta + p.alpha) - best;
@@ -485,20 +521,29 @@ __global__ void __launch_bounds__(kThreads) pln_nearest_kernel(const __grid_cons
     for (int t = 0; t < kMaxD / 32; ++t) e[t] = e[t] / denom;
     float best = 0.f;
     int best_c = -1;
-    for (int c = 0; c < p.K; ++c) {
-      for (int r = 0; r < p.rpc; ++r) {
-        const int j = c * p.rpc + r;
+    for (int j0 = 0; j0 < p.Kr; j0 += 4) {
+      float dd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, p.Kr - 1);
         float dot = 0.f;
 #pragma unroll
         for (int t = 0; t < kMaxD / 32; ++t) {
           const int d = t * 32 + lane;
           if (d < p.D) dot = dist_acc<kDist>(e[t], rh[j * p.D + d], dot);
         }
-        dot = warp_sum(dot);
-        const float dist = dist_finish<kDist>(dot);
-        if (best_c < 0 || dist < best) {
-          best = dist;
-          best_c = c;
+        dd[u] = dot;
+      }
+      warp_sum4(dd);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u;
+        if (j < p.Kr) {
+          const float dist = dist_finish<kDist>(dd[u]);
+          if (best_c < 0 || dist < best) {   // first minimum over all prototypes = first minimum over the class minima (:217-218)
+            best = dist;
+            best_c = j / p.rpc;
+          }
         }
       }
     }
