@@ -635,7 +635,6 @@ __device__ __forceinline__ float2 f2_fma_s(float2 a, float s, float2 c) { return
 //   [16..71] float  x-tap weights of each bin padded to 8
 //   [72..327] float4 per footprint row: (w(ph0), w(ph0+1), w(ph0+2), ph0)
 //   [328..391] float the x-tap weights again, pair-interleaved for the packed row loop (Tables::wt2)
-// Record j describes RoI order[j] (the j-th RoI in processing order), so consumers walk the records sequentially.
 constexpr int kRecRows = 64;
 constexpr int kRecW2 = 72 + 4 * kRecRows;
 constexpr int kRecFloats = kRecW2 + 64;
@@ -650,15 +649,12 @@ struct PrepScratch {
   int yb[kP], ny[kP], xb[kP], nx[kP];
 };
 
-__global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __grid_constant__ FwdParams p) {
-  __shared__ PrepScratch S4[kPrepWarpsF];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * kPrepWarpsF + warp;
-  if (j == 0 && lane == 0 && p.counter != nullptr) *p.counter = p.pers_grid;   // work counter of the persistent kernel
-  if (j >= p.M) return;   // warp-uniform, no block barrier below
-  const int m = p.order ? p.order[j] : j;
-  PrepScratch& T = S4[warp];
-  float* rec = p.rec + (int64_t)j * kRecFloats;
+// one warp per RoI m (no block-level barrier inside)
+__device__ __forceinline__ void roi_fwd_prep_body(const FwdParams& p, int m, PrepScratch& T) {
+  const int lane = threadIdx.x & 31;
+  if (m == 0 && lane == 0 && p.counter != nullptr) *p.counter = p.pers_grid;   // work counter of the persistent kernel
+  if (m >= p.M) return;   // warp-uniform
+  float* rec = p.rec + (int64_t)m * kRecFloats;
   const float* roi = p.rois + (int64_t)m * 5;
   const float fimg = __ldg(roi), x1 = __ldg(roi + 1), y1 = __ldg(roi + 2), x2 = __ldg(roi + 3), y2 = __ldg(roi + 4);
   const int img = (int)fimg;
@@ -745,6 +741,12 @@ __global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __
   }
 }
 
+__global__ void __launch_bounds__(kPrepWarpsF * 32) roi_fwd_prep_kernel(const __grid_constant__ FwdParams p) {
+  __shared__ PrepScratch S4[kPrepWarpsF];
+  const int warp = threadIdx.x >> 5;
+  roi_fwd_prep_body(p, blockIdx.x * kPrepWarpsF + warp, S4[warp]);
+}
+
 // One RoI (record j) by one 256-thread CTA.  kUseRec = false ignores the prep record (the persistent kernel calls this form
 // for the records that are not FAST; the barriers must then be fresh, i.e. invalidated by the caller).
 template <int kC, bool kUseRec>   // kC > 0: compile-time channel count (immediate LDS offsets); 0: run-time C
@@ -769,7 +771,7 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
   int4 h0 = make_int4(0, 0, 0, 0);
   const float* rec = nullptr;
   if (kUseRec && p.rec != nullptr) {
-    rec = p.rec + (int64_t)j * kRecFloats;
+    rec = p.rec + (int64_t)m * kRecFloats;
     h0 = __ldg(reinterpret_cast<const int4*>(rec));
     pre = (h0.x & 1) != 0;
   }
@@ -1294,7 +1296,8 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
   const int tile_off = p.ring_floats - kTileCols * C;   // floats; the ring is 96 columns, the tile its upper 49
   const int fit_cols = tile_off / C;                    // early stages of the next RoI must end below the tile
   const uint32_t rec_bytes = kRecFloats * 4;
-  int jn = 0;   // (thread 0) the record this CTA fetches next
+  int jn = 0, mn = -1;   // (thread 0) the position in processing order this CTA handles next, and its RoI
+  auto roi_at = [&](int j) { return j < p.M ? (p.order ? __ldg(p.order + j) : j) : -1; };
   if (tid == 0) {
     for (int i = 0; i < kNhwcMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -1308,8 +1311,9 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
     s_ctl[0] = blockIdx.x;   // the host launches at most M CTAs
     s_ctl[1] = -1;
     mbar_expect_tx(&rec_bar[0], rec_bytes);
-    bulk_load_1d(recbuf, p.rec + (int64_t)blockIdx.x * kRecFloats, rec_bytes, &rec_bar[0]);
+    bulk_load_1d(recbuf, p.rec + (int64_t)roi_at(blockIdx.x) * kRecFloats, rec_bytes, &rec_bar[0]);
     jn = atomicAdd(p.counter, 1);
+    mn = roi_at(jn);
   }
   // Zero-weight padded taps read whatever the ring holds: zero it once, afterwards it only ever holds feature values and
   // output tiles (finite whenever the inputs are).
@@ -1333,8 +1337,9 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
       if (jn < p.M) {
         s_ctl[nb] = jn;
         mbar_expect_tx(&rec_bar[nb], rec_bytes);
-        bulk_load_1d(recbuf + nb * kRecFloats, p.rec + (int64_t)jn * kRecFloats, rec_bytes, &rec_bar[nb]);
+        bulk_load_1d(recbuf + nb * kRecFloats, p.rec + (int64_t)mn * kRecFloats, rec_bytes, &rec_bar[nb]);
         jn = atomicAdd(p.counter, 1);
+        mn = roi_at(jn);   // consumed one RoI later
       } else {
         s_ctl[nb] = -1;
       }
@@ -1524,9 +1529,7 @@ constexpr int kSortThreads = 1024;
 constexpr int kYBands = 16;
 constexpr int kMaxBuckets = 8192;
 
-__global__ void __launch_bounds__(kSortThreads) roi_order_kernel(const __grid_constant__ FwdParams p, int32_t* order,
-                                                                int32_t* keys, int ybands) {
-  __shared__ int hist[kMaxBuckets];
+__device__ __forceinline__ void roi_order_body(const FwdParams& p, int32_t* order, int32_t* keys, int ybands, int* hist) {
   const int tid = threadIdx.x;
   const int nb = p.L.num_images * p.L.num_levels * ybands;
   for (int i = tid; i < nb; i += kSortThreads) hist[i] = 0;
@@ -1565,6 +1568,27 @@ __global__ void __launch_bounds__(kSortThreads) roi_order_kernel(const __grid_co
   }
   __syncthreads();
   for (int m = tid; m < p.M; m += kSortThreads) order[atomicAdd(&hist[keys[m]], 1)] = m;
+}
+
+__global__ void __launch_bounds__(kSortThreads) roi_order_kernel(const __grid_constant__ FwdParams p, int32_t* order,
+                                                                int32_t* keys, int ybands) {
+  __shared__ int hist[kMaxBuckets];
+  roi_order_body(p, order, keys, ybands, hist);
+}
+
+// Ordering and table records in ONE launch: CTA 0 runs the counting sort, every other CTA (32 warps) writes the records of
+// 32 RoIs.  The two are independent (records are indexed by RoI, the order only says who goes first) and both are
+// latency-bound single passes: 13 + 14 us back to back, ~14 us side by side.
+constexpr int kFusedPrepWarps = kSortThreads / 32;
+__global__ void __launch_bounds__(kSortThreads) roi_order_prep_kernel(const __grid_constant__ FwdParams p, int32_t* order,
+                                                                     int32_t* keys, int ybands) {
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  if (blockIdx.x == 0) {
+    roi_order_body(p, order, keys, ybands, reinterpret_cast<int*>(prep_smem));
+    return;
+  }
+  const int warp = threadIdx.x >> 5;
+  roi_fwd_prep_body(p, (blockIdx.x - 1) * kFusedPrepWarps + warp, reinterpret_cast<PrepScratch*>(prep_smem)[warp]);
 }
 
 size_t fwd_smem_bytes(int ring_floats) {
@@ -1665,18 +1689,27 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
   p.order = nullptr;
   p.rec = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // locality ordering (optional: skipped without a workspace, or for tiny problems where it cannot pay)
+  // locality ordering (optional: skipped without a workspace, or for tiny problems where it cannot pay); launched below,
+  // fused with the table records when the channels_last kernel runs
+  int ybands = 0;
+  int32_t* order = nullptr;
+  int32_t* keys = nullptr;
   if (workspace && workspace_bytes >= osr_roi_align_fwd_workspace(M) && M >= 256) {
-    int ybands = kYBands;
+    ybands = kYBands;
     while (ybands > 1 && num_images * num_levels * ybands > kMaxBuckets) ybands >>= 1;
     if (num_images * num_levels * ybands <= kMaxBuckets) {
-      int32_t* order = static_cast<int32_t*>(workspace);
-      int32_t* keys = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + osr::align256((size_t)M * 4));
+      order = static_cast<int32_t*>(workspace);
+      keys = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + osr::align256((size_t)M * 4));
+    }
+  }
+  auto launch_order_alone = [&]() -> int {
+    if (order) {
       roi_order_kernel<<<1, kSortThreads, 0, s>>>(p, order, keys, ybands);
       OSR_LAUNCH_CHECK();
       p.order = order;
     }
-  }
+    return 0;
+  };
   // TMA staging is opt-in (OSR_TUNE_FWD_VARIANT=1): on NCHW maps a footprint row is only ~50-130 bytes, and the TMA unit's
   // per-row request rate makes it slower than the LDG path (2.20 ms vs 1.71 ms at cfg2 on B200).
   // channels_last maps (sC == 1, a pixel's C channels contiguous, 16-byte aligned) take the bulk-copy NHWC kernel
@@ -1705,8 +1738,18 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
         p.pers_grid = std::min(M, 2 * sms);
         p.counter = reinterpret_cast<int*>(wsb + 2 * osr::align256((size_t)M * 4) + osr::align256((size_t)M * kRecFloats * 4));
       }
-      roi_fwd_prep_kernel<<<osr::ceil_div(M, kPrepWarpsF), kPrepWarpsF * 32, 0, s>>>(p);
-      OSR_LAUNCH_CHECK();
+      if (order) {   // counting sort (CTA 0) and records (the other CTAs) side by side in one launch
+        const size_t psm = std::max(sizeof(PrepScratch) * (size_t)kFusedPrepWarps, sizeof(int) * (size_t)kMaxBuckets);
+        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_order_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        roi_order_prep_kernel<<<1 + osr::ceil_div(M, kFusedPrepWarps), kSortThreads, psm, s>>>(p, order, keys, ybands);
+        OSR_LAUNCH_CHECK();
+        p.order = order;   // (the prep CTAs do not read it)
+      } else {
+        roi_fwd_prep_kernel<<<osr::ceil_div(M, kPrepWarpsF), kPrepWarpsF * 32, 0, s>>>(p);
+        OSR_LAUNCH_CHECK();
+      }
+    } else if ((rc = launch_order_alone())) {
+      return rc;
     }
     if (pers) {
       p.ring_floats = kNhwcRingCols * C;   // 96 columns; the upper 49 double as the output tile
@@ -1734,6 +1777,7 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
     OSR_LAUNCH_CHECK();
     return 0;
   }
+  if ((rc = launch_order_alone())) return rc;
   FwdTma tm;
   memset(&tm, 0, sizeof(tm));
   const bool use_tma = osr::tuning(osr::kTuneFwdVariant) == 1;
