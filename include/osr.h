@@ -161,6 +161,20 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
                       const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
                       int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The same in two calls.  osr_roi_align_bwd's first kernel (per-RoI level, footprint box and weight rows into the workspace,
+ * ~11 us for 8192 RoIs) depends on the RoIs and the map GEOMETRY only - not on grad_out - so a training step can run it as
+ * soon as the RoIs are sampled, on another stream, while the forward / loss kernels run:
+ *   osr_roi_align_bwd_prepare  fills the workspace (h_levels: shapes / strides / scales as for the gradient maps; data unused);
+ *   osr_roi_align_bwd_prepared runs the gather on a workspace prepared for the SAME rois / offsets / geometry.
+ * prepare + prepared == osr_roi_align_bwd, bit for bit. */
+int osr_roi_align_bwd_prepare(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                              const int32_t* roi_batch_offsets, int M, int P, int sampling_ratio, int aligned,
+                              int canonical_box_size, int canonical_level, int min_level, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int osr_roi_align_bwd_prepared(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
+                               const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
+                               int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Layout staging for NCHW callers (the reference's backbone emits NCHW maps): tiled transposes between
  * (N, C, H*W) and (N, H*W, C) contiguous fp32 buffers.  osr_b200.poolers.ROIPooler uses them to run the channels_last

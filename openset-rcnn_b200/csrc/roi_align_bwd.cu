@@ -1262,10 +1262,11 @@ size_t osr_roi_align_bwd_workspace(const osr_feat_level_t* h_levels, int num_lev
   return osr::align256(m * sizeof(RoiInfoPacked)) + osr::align256(m * kWRoi * sizeof(float));
 }
 
-int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
-                      const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
-                      int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+// mode 0: prepare + gather; 1: prepare only (grad_out / level data pointers unused); 2: gather only (workspace prepared)
+static int roi_align_bwd_impl(int mode, const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
+                              const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
+                              int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   osr::DeviceGuard device_guard(workspace);
   BwdParams p;
   int rc = fill_bwd(p, h_grad_levels, num_levels, num_images, C, P, sampling_ratio, aligned, canonical_box_size,
@@ -1273,7 +1274,7 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   if (rc) return rc;
   if (M < 0) return osr::fail_arg(OSR_E_ARG, "roi_align_bwd: M < 0");
   if (num_images == 0) return 0;
-  if (!roi_batch_offsets || !workspace || (M > 0 && (!grad_out || !rois)))
+  if (!roi_batch_offsets || !workspace || (M > 0 && ((mode != 1 && !grad_out) || !rois)))
     return osr::fail_arg(OSR_E_ARG, "roi_align_bwd: null pointer argument");
   if (workspace_bytes < osr_roi_align_bwd_workspace(h_grad_levels, num_levels, num_images, C, M))
     return osr::fail_arg(OSR_E_WORKSPACE, "roi_align_bwd: workspace too small");
@@ -1284,10 +1285,11 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   p.info = static_cast<RoiInfoPacked*>(workspace);
   p.wfull = reinterpret_cast<float*>(static_cast<char*>(workspace) + osr::align256((size_t)(M > 0 ? M : 1) * sizeof(RoiInfoPacked)));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (M > 0) {
+  if (M > 0 && mode != 2) {
     roi_bwd_prep_kernel<<<osr::ceil_div(M, kPrepWarps), kPrepWarps * 32, 0, s>>>(p);
     OSR_LAUNCH_CHECK();
   }
+  if (mode == 1) return 0;
   // channels_last gradient maps with whole 32-channel groups: thread-per-channel kernel
   bool cl = (C % 32 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) && osr::tuning(osr::kTuneBwdVariant) != 3;
   for (int l = 0; l < num_levels; ++l) cl = cl && (p.L.lv[l].sC == 1);
@@ -1319,6 +1321,30 @@ int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int
   roi_align_bwd_kernel<<<tiles, kThreads, smem, s>>>(p);
   OSR_LAUNCH_CHECK();
   return 0;
+}
+
+int osr_roi_align_bwd(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
+                      const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
+                      int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return roi_align_bwd_impl(0, h_grad_levels, num_levels, num_images, C, grad_out, rois, roi_batch_offsets, M, P, sampling_ratio,
+                            aligned, canonical_box_size, canonical_level, min_level, workspace, workspace_bytes, stream);
+}
+
+int osr_roi_align_bwd_prepare(const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, const float* rois,
+                              const int32_t* roi_batch_offsets, int M, int P, int sampling_ratio, int aligned,
+                              int canonical_box_size, int canonical_level, int min_level, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return roi_align_bwd_impl(1, h_levels, num_levels, num_images, C, nullptr, rois, roi_batch_offsets, M, P, sampling_ratio,
+                            aligned, canonical_box_size, canonical_level, min_level, workspace, workspace_bytes, stream);
+}
+
+int osr_roi_align_bwd_prepared(const osr_feat_level_t* h_grad_levels, int num_levels, int num_images, int C,
+                               const float* grad_out, const float* rois, const int32_t* roi_batch_offsets, int M, int P,
+                               int sampling_ratio, int aligned, int canonical_box_size, int canonical_level, int min_level,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  return roi_align_bwd_impl(2, h_grad_levels, num_levels, num_images, C, grad_out, rois, roi_batch_offsets, M, P, sampling_ratio,
+                            aligned, canonical_box_size, canonical_level, min_level, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -68,6 +68,12 @@ SIGNATURES = {
     "osr_roi_align_bwd": (C.c_int, [
         C.POINTER(FeatLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "osr_roi_align_bwd_prepare": (C.c_int, [
+        C.POINTER(FeatLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "osr_roi_align_bwd_prepared": (C.c_int, [
+        C.POINTER(FeatLevel), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "osr_pln_loss_fwd": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -50,6 +50,7 @@ class PathConfig:
     unk_thr: float = 0.23
     gt_per_image: int = 8
     name: str = "cfg2"
+    overlap_bwd_prep: bool = True  # the backward's RoI-only table kernel runs on a side stream next to S3 forward / S5
     box_head: bool = False        # S4 on the path: ROIAlign writes bf16, fc1 / fc2 on tcgen05 feed the PLN
 
 
@@ -157,6 +158,7 @@ class RoiPathStep:
             self.fc2_b = torch.zeros(cfg.feat_dim, device=dev)
         self.last: Dict[str, torch.Tensor] = {}
         self._fused_enc = None
+        self._side = None
         self.fused_gather_error = None
         self.events: Optional[List[torch.cuda.Event]] = None
 
@@ -184,6 +186,17 @@ class RoiPathStep:
         boxes = sel.boxes.view(-1, 4).index_select(0, self.sample_idx)
         rois = torch.cat((self.img_col, boxes), dim=1)
         self._mark(2)
+        # the backward's per-RoI tables depend on the RoIs only: issue them now on a side stream (a parallel branch of the
+        # captured graph), joined right before the backward gather
+        bwd_ws = None
+        if cfg.overlap_bwd_prep:
+            cur = torch.cuda.current_stream(rois.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=rois.device)
+            bwd_ws = self.pooler.alloc_backward_workspace(feats, rois)      # allocated on the main stream
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self.pooler.prepare_backward(feats, rois, self.roi_offsets, out=bwd_ws)
         # S3 forward (kernels are called directly, without autograd: no engine thread hop, capturable in a CUDA graph;
         # tests/test_gpu_pipeline.py checks this path against the autograd one)
         k = 3
@@ -255,7 +268,9 @@ class RoiPathStep:
             loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
         self._mark(k); k += 1
         # S3 backward
-        g_feats = self.pooler.backward_rois(self.grad_pooled, feats, rois, self.roi_offsets)
+        if bwd_ws is not None:
+            torch.cuda.current_stream(rois.device).wait_stream(self._side)
+        g_feats = self.pooler.backward_rois(self.grad_pooled, feats, rois, self.roi_offsets, prepared=bwd_ws)
         self._mark(k)
         self.last = dict(sel=sel, match=match, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
                          g_feats=g_feats)

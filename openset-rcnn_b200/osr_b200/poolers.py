@@ -114,9 +114,34 @@ class _ROIAlignFPN(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
-def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, offsets: torch.Tensor, shapes, channels_last, cfg):
+def roi_align_backward_workspace(feats, M: int, cfg) -> torch.Tensor:
+    lib = _lib.lib()
+    arr, N, C = _feat_levels(list(feats), cfg[0])
+    return torch.empty((max(int(lib.osr_roi_align_bwd_workspace(arr, len(feats), N, C, M)), 256),), dtype=torch.uint8,
+                       device=feats[0].device)
+
+
+def roi_align_backward_prepare(feats, rois: torch.Tensor, offsets: torch.Tensor, cfg, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``osr_roi_align_bwd_prepare``: the backward's per-RoI tables for maps shaped / laid out like ``feats`` (their values are
+    not read).  Returns the workspace to hand to ``roi_align_backward(..., prepared=ws)``.  Depends on the RoIs only, so a
+    training step can issue it on a side stream right after sampling."""
+    lib = _lib.lib()
+    scales, P, sampling_ratio, canon_size, canon_level, min_level = cfg
+    arr, N, C = _feat_levels(list(feats), scales)
+    M = rois.shape[0]
+    dev = rois.device
+    ws = out if out is not None else roi_align_backward_workspace(feats, M, cfg)
+    rc = lib.osr_roi_align_bwd_prepare(arr, len(feats), N, C, rois.data_ptr(), offsets.data_ptr(), M, P, sampling_ratio, 1,
+                                       canon_size, canon_level, min_level, ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+    _lib.check(rc, "osr_roi_align_bwd_prepare")
+    return ws
+
+
+def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, offsets: torch.Tensor, shapes, channels_last, cfg,
+                       prepared: Optional[torch.Tensor] = None):
     """``osr_roi_align_bwd`` without autograd: dense gradient maps (one per level, fully written - no memset) for pooled
-    gradients ``grad_out`` (M, C, P, P).  ``shapes`` / ``channels_last``: shape and memory format of each level's map."""
+    gradients ``grad_out`` (M, C, P, P).  ``shapes`` / ``channels_last``: shape and memory format of each level's map.
+    ``prepared``: a workspace from ``roi_align_backward_prepare`` for the same RoIs and map geometry."""
     lib = _lib.lib()
     scales, P, sampling_ratio, canon_size, canon_level, min_level = cfg
     dev = grad_out.device
@@ -127,6 +152,12 @@ def roi_align_backward(grad_out: torch.Tensor, rois: torch.Tensor, offsets: torc
                                  memory_format=torch.channels_last if cl else torch.contiguous_format))
     arr, N, C = _feat_levels(grads, scales)
     M = rois.shape[0]
+    if prepared is not None:
+        rc = lib.osr_roi_align_bwd_prepared(arr, len(grads), N, C, grad_out.data_ptr(), rois.data_ptr(), offsets.data_ptr(),
+                                            M, P, sampling_ratio, 1, canon_size, canon_level, min_level,
+                                            prepared.data_ptr(), prepared.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "osr_roi_align_bwd_prepared")
+        return grads
     ws_bytes = int(lib.osr_roi_align_bwd_workspace(arr, len(grads), N, C, M))
     ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
     rc = lib.osr_roi_align_bwd(arr, len(grads), N, C, grad_out.data_ptr(), rois.data_ptr(), offsets.data_ptr(),
@@ -214,11 +245,24 @@ class ROIPooler(torch.nn.Module):
     def forward(self, x: List[torch.Tensor], box_lists: List[Boxes]) -> torch.Tensor:
         return self.forward_with_levels(x, box_lists)[0]
 
-    def backward_rois(self, grad_pooled: torch.Tensor, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor):
+    def prepare_backward(self, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The RoI-only part of ``backward_rois`` (``osr_roi_align_bwd_prepare``), to be issued early / on a side stream; pass
+        the result as ``backward_rois(..., prepared=...)`` with the same ``x`` layouts, ``rois`` and ``offsets``."""
+        # (only the maps' geometry - N, C, H, W, scale - enters the tables: any memory format of x will do)
+        return roi_align_backward_prepare([f.detach() for f in x], rois.contiguous().float(), offsets, self._cfg(), out)
+
+    def alloc_backward_workspace(self, x: List[torch.Tensor], rois: torch.Tensor) -> torch.Tensor:
+        """Workspace for ``prepare_backward(..., out=)`` (allocate it on the stream that will run ``backward_rois``)."""
+        return roi_align_backward_workspace([f.detach() for f in x], rois.shape[0], self._cfg())
+
+    def backward_rois(self, grad_pooled: torch.Tensor, x: List[torch.Tensor], rois: torch.Tensor, offsets: torch.Tensor,
+                      prepared: Optional[torch.Tensor] = None):
         """Gradient of ``pool_rois`` w.r.t. the maps ``x`` (only their shapes / layouts are read), without autograd."""
         cl = [f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous() for f in x]
         if NCHW_STAGING and all(_stage_ok(f) for f in x):
             grads = roi_align_backward(grad_pooled, rois.contiguous().float(), offsets, [tuple(f.shape) for f in x],
-                                       [True] * len(x), self._cfg())
+                                       [True] * len(x), self._cfg(), prepared)
             return [channels_last_to_nchw(g) for g in grads]
-        return roi_align_backward(grad_pooled, rois.contiguous().float(), offsets, [tuple(f.shape) for f in x], cl, self._cfg())
+        return roi_align_backward(grad_pooled, rois.contiguous().float(), offsets, [tuple(f.shape) for f in x], cl, self._cfg(),
+                                  prepared)

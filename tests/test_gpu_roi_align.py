@@ -391,3 +391,26 @@ def test_nchw_staging_equals_channels_last_path_exactly():
     gb = _grads(ours, feats_cl, boxes, gout)
     for x, y in zip(ga, gb):
         assert x.is_contiguous() and torch.equal(x, y)
+
+
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_backward_prepare_then_prepared_equals_one_call(channels_last):
+    """osr_roi_align_bwd_prepare (RoI-only tables, here on a side stream) + osr_roi_align_bwd_prepared == osr_roi_align_bwd,
+    bit for bit."""
+    from osr_b200 import synth
+    ours, _ = _pooler_pair()
+    feats = synth.make_features(2, (320, 480), 64, seed=8, device="cuda:0", channels_last=channels_last)
+    rois = synth.make_rois(2, 300, (320, 480), seed=29)
+    packed = torch.cat([torch.cat([torch.full((len(r), 1), float(i)), r], dim=1) for i, r in enumerate(rois)]).cuda()
+    offsets = torch.tensor([0, 300, 600], dtype=torch.int32, device="cuda:0")
+    gout = torch.randn(600, 64, 7, 7, device="cuda:0")
+    ref = ours.backward_rois(gout, feats, packed, offsets)
+    side = torch.cuda.Stream()
+    ws = ours.alloc_backward_workspace(feats, packed)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ours.prepare_backward(feats, packed, offsets, out=ws)
+    torch.cuda.current_stream().wait_stream(side)
+    got = ours.backward_rois(gout, feats, packed, offsets, prepared=ws)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
