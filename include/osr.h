@@ -241,7 +241,7 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
                      int reps_per_class, int distance_type, float loss_weight, float r_norm, float center_weight,
                      float* grad_emb, float* grad_reps, void* workspace, size_t workspace_bytes, void* stream);
 /* Forward and closed-form backward of the loss in one call (grad_loss: device scalar, usually 1): same outputs as
- * osr_pln_loss_fwd followed by osr_pln_loss_bwd, bit for bit, in four launches (d loss / d emb is written by the row
+ * osr_pln_loss_fwd followed by osr_pln_loss_bwd, bit for bit, in three launches (d loss / d emb is written by the row
  * kernel itself).  Used by the training step when the caller does not route the loss through autograd. */
 int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
                          int R, int D, int K, int reps_per_class, int distance_type, float alpha, float beta,

@@ -38,7 +38,8 @@ struct PlnParams {
   int32_t* inter_rep;
   int32_t* center_rep;
   // workspace
-  float* partial;      // fwd: (num_ctas, 2)   bwd: (kSeg, Kr, D)
+  float* partial;      // fwd: (num_ctas, 2) + (Kr)
+  float* bpartial;     // bwd: (kSeg, Kr, D) - a separate region, so the fused call can reduce the loss after the backward partials
   int num_ctas;
   int dist_type;       // OSR_PLN_DIST_COS / _L1 / _L2 (prototype_learning_network.py:156-161,171-176)
   float* saved_dist;   // (2 R + Kr): intra distance, inter distance of every foreground row, separation distance of every
@@ -290,8 +291,8 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
   }
 }
 
-// final ordered reduction (:183-187) of the per-CTA partial sums and the per-prototype separation hinges
-__global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_constant__ PlnParams p) {
+// final ordered reduction (:183-187) of the per-CTA partial sums and the per-prototype separation hinges (one CTA)
+__device__ __forceinline__ void pln_final_body(const PlnParams& p) {
   __shared__ float s_c[kMaxReps];
   if (threadIdx.x < p.Kr) s_c[threadIdx.x] = p.partial[2 * p.num_ctas + threadIdx.x];
   // ordered sum of the per-CTA partials: thread t adds partials t, t + 256, ... in that order, then a fixed tree
@@ -324,6 +325,8 @@ __global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_consta
     p.loss_terms[3] = c;
   }
 }
+
+__global__ void __launch_bounds__(kThreads) pln_final_kernel(const __grid_constant__ PlnParams p) { pln_final_body(p); }
 
 // ------------------------------------------------------------------------------------------ backward
 template <int kDist>
@@ -454,13 +457,19 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_partial(const __grid_c
     }
     __syncthreads();
   }
-  if (tid < p.D) p.partial[((int64_t)seg * p.Kr + j) * p.D + tid] = acc[0];
+  if (tid < p.D) p.bpartial[((int64_t)seg * p.Kr + j) * p.D + tid] = acc[0];
 }
 
-template <int kDist>
+// kWithLoss: the grid has one extra CTA (blockIdx.x == Kr) that performs pln_final_kernel's reduction - the fused
+// forward + backward call saves a launch
+template <int kDist, bool kWithLoss>
 __global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_constant__ PlnParams p) {
   extern __shared__ __align__(16) float rh[];
   __shared__ float s_red[kWarps];
+  if (kWithLoss && blockIdx.x == (unsigned)p.Kr) {   // CTA-uniform
+    pln_final_body(p);
+    return;
+  }
   load_unit_reps(p, rh, nullptr);
   __syncthreads();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(kThreads) pln_grad_reps_final(const __grid_con
     const int j = blockIdx.x;   // one CTA per prototype
     float g = 0.f;
     if (tid < p.D) {
-      for (int seg = 0; seg < kSeg; ++seg) g += p.partial[((int64_t)seg * p.Kr + j) * p.D + tid];
+      for (int seg = 0; seg < kSeg; ++seg) g += p.bpartial[((int64_t)seg * p.Kr + j) * p.D + tid];
       // separation term: (Gamma + Gamma^T) r_hat, Gamma[k][j*_k] = center_weight * [hinge active]
       // relu(beta + alpha - c_dist_k): -center_weight * d dist(r_hat_k, r_hat_j*k) / d (either argument)
       const float* cd = p.saved_dist ? p.saved_dist + 2 * p.R : nullptr;
@@ -581,15 +590,14 @@ int check_dist(int distance_type, const void* saved_dist, bool need_saved) {
 
 // two rows per warp: enough CTAs to fill the GPU in one wave at R = 8192 (the stage is latency-bound)
 int fwd_ctas(int R) { return R < 2 * kWarps ? 1 : (R / (2 * kWarps) > 592 ? 592 : R / (2 * kWarps)); }
+size_t fwd_partial_bytes(int R, int Kr) { return ((size_t)fwd_ctas(R > 0 ? R : 1) * 2 + (size_t)Kr) * sizeof(float); }
 
 }  // namespace
 
 extern "C" {
 
 size_t osr_pln_workspace(int R, int D, int K, int reps_per_class) {
-  const size_t fwd = ((size_t)fwd_ctas(R > 0 ? R : 1) * 2 + (size_t)K * reps_per_class) * sizeof(float);
-  const size_t bwd = (size_t)kSeg * K * reps_per_class * D * sizeof(float);
-  return osr::align256(fwd > bwd ? fwd : bwd);
+  return osr::align256(fwd_partial_bytes(R, K * reps_per_class)) + osr::align256((size_t)kSeg * K * reps_per_class * D * sizeof(float));
 }
 
 int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, int R, int D,
@@ -615,6 +623,7 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
   p.intra_rep = intra_rep; p.inter_rep = inter_rep; p.center_rep = center_rep;
   p.dist_type = distance_type; p.saved_dist = saved_dist;
   p.partial = static_cast<float*>(workspace);
+  p.bpartial = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + osr::align256(fwd_partial_bytes(R, p.Kr)));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
   p.num_ctas = fwd_ctas(R > 0 ? R : 1);   // also launched for R == 0: the separation term does not depend on the rows
@@ -628,8 +637,8 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
   return 0;
 }
 
-// Loss forward AND closed-form backward in four launches (rows + d loss / d emb fused, loss reduction, prototype-gradient
-// partials, prototype-gradient final) instead of five plus the autograd plumbing: the training step's S5.
+// Loss forward AND closed-form backward in three launches (rows + d loss / d emb fused, prototype-gradient
+// partials, prototype-gradient final + loss reduction in an extra CTA) instead of five plus the autograd plumbing: the training step's S5.
 int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
                          int R, int D, int K, int reps_per_class, int distance_type, float alpha, float beta,
                          float loss_weight, float iou_threshold, float r_norm, float center_weight, float* loss_terms,
@@ -655,19 +664,18 @@ int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* lab
   p.grad_loss = grad_loss; p.grad_emb = grad_emb; p.grad_reps = grad_reps;
   p.dist_type = distance_type; p.saved_dist = saved_dist;
   p.partial = static_cast<float*>(workspace);
+  p.bpartial = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + osr::align256(fwd_partial_bytes(R, p.Kr)));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
   p.num_ctas = fwd_ctas(R > 0 ? R : 1);
   OSR_PLN_DISPATCH(distance_type, {
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<true, kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pln_rows_kernel<true, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
-    OSR_LAUNCH_CHECK();
-    pln_final_kernel<<<1, kThreads, 0, s>>>(p);   // reads the forward partials before the backward partials reuse the workspace
     OSR_LAUNCH_CHECK();
     pln_grad_reps_partial<kD><<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
     OSR_LAUNCH_CHECK();
-    pln_grad_reps_final<kD><<<p.Kr, kThreads, smem, s>>>(p);
+    pln_grad_reps_final<kD, true><<<p.Kr + 1, kThreads, smem, s>>>(p);   // CTA Kr reduces the loss (pln_final_kernel's job)
     OSR_LAUNCH_CHECK();
   });
   return 0;
@@ -698,11 +706,12 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
   p.grad_loss = grad_loss; p.grad_emb = grad_emb; p.grad_reps = grad_reps;
   p.dist_type = distance_type; p.saved_dist = const_cast<float*>(saved_dist);
   p.partial = static_cast<float*>(workspace);
+  p.bpartial = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + osr::align256(fwd_partial_bytes(R, p.Kr)));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)p.Kr * D * sizeof(float);
   OSR_PLN_DISPATCH(distance_type, {
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_emb_kernel<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (R > 0) {
       int ctas = osr::ceil_div(R, kWarps * 4);
       if (ctas > 592) ctas = 592;
@@ -711,7 +720,7 @@ int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels,
     }
     pln_grad_reps_partial<kD><<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
     OSR_LAUNCH_CHECK();
-    pln_grad_reps_final<kD><<<p.Kr, kThreads, smem, s>>>(p);
+    pln_grad_reps_final<kD, false><<<p.Kr, kThreads, smem, s>>>(p);
     OSR_LAUNCH_CHECK();
   });
   return 0;
