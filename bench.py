@@ -684,6 +684,9 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
                                    ("S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, "
                                     "S5 encoder+PLN loss fwd/bwd" + (" over the GLOBAL batch (encoder fused with the all-gather of the embeddings over NVLink; loss terms on local rows + one all-reduce of loss and prototype gradient)" if (args.config == "cfg3" and world > 1) else "") +
                                     ", S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))"),
+                   "side_stream": ("the ROIAlign backward's RoI-only table kernel (issued after S2) and the PLN prototype-gradient launches "
+                                   "+ loss reduction (issued after the row launch of S5) run on a side stream = parallel branches of the "
+                                   "graph; their time is inside value / ms_per_step / eager but not inside stage_ms") if not infer else None,
                    "parallelism": f"dp{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
         "stage_ms": stages, "alt_layout": alt, "gpu_baseline": gbase,

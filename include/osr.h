@@ -249,6 +249,17 @@ int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* lab
                          float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep,
                          int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* The same call in two phases on the SAME buffers: phase 1 = the row launch (loss partials, saved state, d loss / d emb),
+ * phase 2 = the prototype-gradient launches + the loss reduction (loss_terms, grad_reps).  d loss / d emb - what the rest of
+ * the backward pass (encoder, box head, ROIAlign) waits for - is complete after phase 1; phase 2 is an independent branch of
+ * the backward graph, and the training step runs it on a side stream next to the ROIAlign backward.  Phase 1 then phase 2 ==
+ * osr_pln_loss_fwd_bwd, bit for bit. */
+int osr_pln_loss_fwd_bwd_phase(int phase, const float* emb, const float* reps, const int64_t* labels, const float* ious,
+                               const float* grad_loss, int R, int D, int K, int reps_per_class, int distance_type, float alpha,
+                               float beta, float loss_weight, float iou_threshold, float r_norm, float center_weight,
+                               float* loss_terms, float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep,
+                               int32_t* inter_rep, int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 
 /*

@@ -639,12 +639,14 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
 
 // Loss forward AND closed-form backward in three launches (rows + d loss / d emb fused, prototype-gradient
 // partials, prototype-gradient final + loss reduction in an extra CTA) instead of five plus the autograd plumbing: the training step's S5.
-int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
-                         int R, int D, int K, int reps_per_class, int distance_type, float alpha, float beta,
-                         float loss_weight, float iou_threshold, float r_norm, float center_weight, float* loss_terms,
-                         float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep,
-                         int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+// phase 0: everything; 1: the row launch only (loss partials, saved state, d loss / d emb); 2: the two prototype-gradient
+// launches + loss reduction on what phase 1 left in the buffers
+static int pln_loss_fwd_bwd_impl(int phase, const float* emb, const float* reps, const int64_t* labels, const float* ious,
+                                 const float* grad_loss, int R, int D, int K, int reps_per_class, int distance_type, float alpha,
+                                 float beta, float loss_weight, float iou_threshold, float r_norm, float center_weight,
+                                 float* loss_terms, float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep,
+                                 int32_t* inter_rep, int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   osr::DeviceGuard device_guard(grad_reps);
   int rc = check_shape(R, D, K, reps_per_class);
   if (rc) return rc;
@@ -671,14 +673,43 @@ int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* lab
   OSR_PLN_DISPATCH(distance_type, {
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<true, kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pln_rows_kernel<true, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
-    OSR_LAUNCH_CHECK();
-    pln_grad_reps_partial<kD><<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
-    OSR_LAUNCH_CHECK();
-    pln_grad_reps_final<kD, true><<<p.Kr + 1, kThreads, smem, s>>>(p);   // CTA Kr reduces the loss (pln_final_kernel's job)
-    OSR_LAUNCH_CHECK();
+    if (phase != 2) {
+      pln_rows_kernel<true, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
+      OSR_LAUNCH_CHECK();
+    }
+    if (phase != 1) {
+      pln_grad_reps_partial<kD><<<dim3(p.Kr, kSeg), kThreads, 0, s>>>(p);
+      OSR_LAUNCH_CHECK();
+      pln_grad_reps_final<kD, true><<<p.Kr + 1, kThreads, smem, s>>>(p);   // CTA Kr reduces the loss (pln_final_kernel's job)
+      OSR_LAUNCH_CHECK();
+    }
   });
   return 0;
+}
+
+int osr_pln_loss_fwd_bwd(const float* emb, const float* reps, const int64_t* labels, const float* ious, const float* grad_loss,
+                         int R, int D, int K, int reps_per_class, int distance_type, float alpha, float beta,
+                         float loss_weight, float iou_threshold, float r_norm, float center_weight, float* loss_terms,
+                         float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep, int32_t* inter_rep,
+                         int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return pln_loss_fwd_bwd_impl(0, emb, reps, labels, ious, grad_loss, R, D, K, reps_per_class, distance_type, alpha, beta,
+                               loss_weight, iou_threshold, r_norm, center_weight, loss_terms, emb_inv_norm, rep_inv_norm,
+                               intra_rep, inter_rep, center_rep, saved_dist, grad_emb, grad_reps, workspace, workspace_bytes,
+                               stream);
+}
+
+int osr_pln_loss_fwd_bwd_phase(int phase, const float* emb, const float* reps, const int64_t* labels, const float* ious,
+                               const float* grad_loss, int R, int D, int K, int reps_per_class, int distance_type, float alpha,
+                               float beta, float loss_weight, float iou_threshold, float r_norm, float center_weight,
+                               float* loss_terms, float* emb_inv_norm, float* rep_inv_norm, int32_t* intra_rep,
+                               int32_t* inter_rep, int32_t* center_rep, float* saved_dist, float* grad_emb, float* grad_reps,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (phase != 1 && phase != 2) return osr::fail_arg(OSR_E_ARG, "pln_loss_fwd_bwd_phase: phase must be 1 (rows) or 2 (prototype gradient + loss)");
+  return pln_loss_fwd_bwd_impl(phase, emb, reps, labels, ious, grad_loss, R, D, K, reps_per_class, distance_type, alpha, beta,
+                               loss_weight, iou_threshold, r_norm, center_weight, loss_terms, emb_inv_norm, rep_inv_norm,
+                               intra_rep, inter_rep, center_rep, saved_dist, grad_emb, grad_reps, workspace, workspace_bytes,
+                               stream);
 }
 
 int osr_pln_loss_bwd(const float* emb, const float* reps, const int64_t* labels, const float* emb_inv_norm,

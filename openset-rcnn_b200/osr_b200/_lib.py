@@ -89,6 +89,11 @@ SIGNATURES = {
         C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_size_t, C.c_void_p]),
+    "osr_pln_loss_fwd_bwd_phase": (C.c_int, [
+        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_void_p, C.c_size_t, C.c_void_p]),
     "osr_pln_encode_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "osr_pln_encode_fwd": (C.c_int, [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -214,6 +214,7 @@ class RoiPathStep:
                 pooled, lvl = self.pooler.pool_rois([f.detach() for f in feats], rois, self.roi_offsets)
         self._mark(k); k += 1
         # S5: encoder + prototype loss forward + backward to (emb, representatives)
+        finish_reps = None
         reps = pi.reps
         kw = dict(num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta, loss_weight=cfg.loss_weight,
                   iou_threshold=cfg.iou_threshold)
@@ -265,12 +266,25 @@ class RoiPathStep:
                     emb = pln_encode_tc(roi_features, pi.enc_w, pi.enc_b)
                 else:
                     emb = F.linear(roi_features, pi.enc_w, pi.enc_b)
-            loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
+            if cfg.overlap_bwd_prep:
+                # d loss / d emb (what the rest of the backward pass waits for) is complete after the row launch; the
+                # prototype-gradient launches + loss reduction are an independent branch of the backward graph and run on the
+                # side stream next to the ROIAlign backward
+                finish_reps, g_emb = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, split=True, **kw)
+            else:
+                loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
         self._mark(k); k += 1
         # S3 backward
+        cur = torch.cuda.current_stream(rois.device)
         if bwd_ws is not None:
-            torch.cuda.current_stream(rois.device).wait_stream(self._side)
+            cur.wait_stream(self._side)          # the backward's tables (issued before the forward)
+        if finish_reps is not None:
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                loss, g_reps = finish_reps()
         g_feats = self.pooler.backward_rois(self.grad_pooled, feats, rois, self.roi_offsets, prepared=bwd_ws)
+        if finish_reps is not None:
+            cur.wait_stream(self._side)
         self._mark(k)
         self.last = dict(sel=sel, match=match, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
                          g_feats=g_feats)

@@ -106,10 +106,15 @@ class _PlnLossFn(torch.autograd.Function):
 def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_per_class: int = 1, alpha: float = 0.1,
                      beta: float = 0.9, loss_weight: float = 0.5, iou_threshold: float = 0.5, r_norm: Optional[float] = None,
                      center_weight: float = 1.0, emb_grad_scale: float = 1.0, grad_loss: Optional[torch.Tensor] = None,
-                     distance_type="COS"):
+                     distance_type="COS", split: bool = False):
     """Loss and its closed-form gradients in one call, WITHOUT autograd: ``(loss, d loss / d emb, d loss / d reps)``.
     Same kernels as ``pln_loss_from_emb`` + ``backward()``; used by the device-resident training step (no autograd engine
-    hop, capturable in a CUDA graph)."""
+    hop, capturable in a CUDA graph).
+
+    ``split=True`` runs only the row launch now (``d loss / d emb`` is complete when it returns) and returns
+    ``(finish, d loss / d emb)``: calling ``finish()`` - typically on a side stream, next to the rest of the backward pass -
+    runs the prototype-gradient launches and the loss reduction and returns ``(loss, d loss / d reps)``
+    (``osr_pln_loss_fwd_bwd_phase``; same buffers, bit-identical to the one-call form)."""
     lib = _lib.lib()
     _lib.require_cuda(emb, reps, labels, ious)
     with torch.no_grad():
@@ -132,12 +137,24 @@ def pln_loss_fwd_bwd(emb, reps, labels, ious, *, num_known_classes: int, reps_pe
         grad_reps = torch.empty_like(reps_c)
         ws = torch.empty(max(int(lib.osr_pln_workspace(R, D, K, rpc)), 256), dtype=torch.uint8, device=dev)
         rn = float(R) if r_norm is None else float(r_norm)
-        rc = lib.osr_pln_loss_fwd_bwd(emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(), gl.data_ptr(),
-                                      R, D, K, rpc, _dist_code(distance_type), float(alpha), float(beta), float(loss_weight),
-                                      float(iou_threshold), rn, float(center_weight), terms.data_ptr(), emb_inv.data_ptr(),
-                                      rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
-                                      sdist.data_ptr() if _dist_code(distance_type) == 2 else None, grad_emb.data_ptr(),
-                                      grad_reps.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        args = (emb_c.data_ptr(), reps_c.data_ptr(), labels_c.data_ptr(), ious_c.data_ptr(), gl.data_ptr(),
+                R, D, K, rpc, _dist_code(distance_type), float(alpha), float(beta), float(loss_weight),
+                float(iou_threshold), rn, float(center_weight), terms.data_ptr(), emb_inv.data_ptr(),
+                rep_inv.data_ptr(), intra.data_ptr(), inter.data_ptr(), center.data_ptr(),
+                sdist.data_ptr() if _dist_code(distance_type) == 2 else None, grad_emb.data_ptr(),
+                grad_reps.data_ptr(), ws.data_ptr(), ws.numel())
+        if split:
+            _lib.check(lib.osr_pln_loss_fwd_bwd_phase(1, *args, _lib.stream_ptr(dev)), "osr_pln_loss_fwd_bwd_phase(1)")
+            keep = (emb_c, reps_c, labels_c, ious_c, gl, small, idx, ws)   # the buffers phase 2 reads
+
+            def finish():
+                _lib.check(lib.osr_pln_loss_fwd_bwd_phase(2, *args, _lib.stream_ptr(dev)), "osr_pln_loss_fwd_bwd_phase(2)")
+                return terms[0], grad_reps
+            finish.keep = keep
+            if emb_grad_scale != 1.0:
+                grad_emb = grad_emb * float(emb_grad_scale)
+            return finish, grad_emb
+        rc = lib.osr_pln_loss_fwd_bwd(*args, _lib.stream_ptr(dev))
         _lib.check(rc, "osr_pln_loss_fwd_bwd")
         if emb_grad_scale != 1.0:
             grad_emb = grad_emb * float(emb_grad_scale)

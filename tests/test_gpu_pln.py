@@ -284,3 +284,23 @@ def test_unknown_distance_type_is_a_config_error():
     with pytest.raises(ValueError, match="DISTANCE_TYPE"):
         PLN(num_classes=81, num_known_classes=20, feature_dim=64, embedding_dim=256, distance_type="L3", reps_per_class=1,
             alpha=0.1, beta=0.9, loss_weight=0.5)
+
+
+@pytest.mark.parametrize("dist", ["COS", "L2"])
+def test_split_forward_backward_equals_one_call(dist):
+    """osr_pln_loss_fwd_bwd_phase 1 (rows) then 2 (prototype gradient + loss, here on a side stream) == osr_pln_loss_fwd_bwd."""
+    from osr_b200 import synth
+    from osr_b200.pln import pln_loss_fwd_bwd
+    pi = synth.make_pln_inputs(4096, num_known=20, num_classes=81, seed=77, device="cuda:0")
+    emb = (pi.roi_features @ pi.enc_w.t()).detach()
+    kw = dict(num_known_classes=20, alpha=0.1 if dist == "COS" else 1.40, beta=0.9 if dist == "COS" else 1.33, loss_weight=0.5,
+              iou_threshold=0.5, distance_type=dist)
+    l0, ge0, gr0 = pln_loss_fwd_bwd(emb, pi.reps, pi.gt_classes, pi.ious, **kw)
+    finish, ge1 = pln_loss_fwd_bwd(emb, pi.reps, pi.gt_classes, pi.ious, split=True, **kw)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        l1, gr1 = finish()
+    torch.cuda.current_stream().wait_stream(side)
+    assert torch.equal(l0, l1) and torch.equal(ge0, ge1) and torch.equal(gr0, gr1)
+    assert float(gr1.abs().max()) > 0
