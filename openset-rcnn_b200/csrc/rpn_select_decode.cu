@@ -154,9 +154,14 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
           uint32_t key = keys[i];
           if ((key & mask) == prefix) bin = (key >> shift) & 0xffu;
         }
-        // warp-aggregated shared-memory histogram (scores in (0,1) put most keys in 1-2 top-byte bins)
-        uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (uint32_t)__popc(peers));
+        if (pass == 0) {
+          // warp-aggregated shared-memory histogram: scores in (0,1) put most keys in 1-2 top-byte bins.  Only for the top
+          // byte - the lower bytes are spread over many bins, where match_any serialises (9 us vs 2.7 us for the pass)
+          uint32_t peers = __match_any_sync(0xffffffffu, bin);
+          if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&h[bin], (uint32_t)__popc(peers));
+        } else if (bin != 0xffffffffu) {
+          atomicAdd(&h[bin], 1u);
+        }
       }
       cluster.sync();
       if (tid < kBins) {
@@ -248,18 +253,54 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 2)
   int kp = 32;
   while (kp < k) kp <<= 1;
   for (int i = k + tid; i < kp; i += kThreads) cand[i] = 0ull;
+  // Bitonic network, two steps per pass: the steps with strides 2h and h exchange inside groups {b, b+h, b+2h, b+3h}, so a
+  // thread that owns such a group does both in registers - 33 passes over shared memory (4 loads + 4 stores per thread, one
+  // barrier each) instead of 66 (25 us -> 19 us for 2048 candidates, measured with %globaltimer stamps).  A group lies inside one `size`-aligned block, so
+  // its four elements share the sort direction.
+  auto cx = [](unsigned long long& a, unsigned long long& b, bool desc) {
+    if (desc ? (a < b) : (a > b)) {
+      const unsigned long long t = a;
+      a = b;
+      b = t;
+    }
+  };
   for (int size = 2; size <= kp; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+    int stride = size >> 1;
+    for (; stride >= 2; stride >>= 2) {
+      const int h = stride >> 1;
+      __syncthreads();
+      for (int q = tid; q < (kp >> 2); q += kThreads) {
+        const int b0 = ((q & ~(h - 1)) << 2) | (q & (h - 1));
+        const bool desc = ((b0 & size) == 0);
+        unsigned long long e0, e1, e2, e3;
+        if (h == 1) {   // four consecutive elements: 16-byte accesses (8-byte ones at a 32-byte lane pitch conflict 8-way)
+          const ulonglong2 v0 = reinterpret_cast<const ulonglong2*>(cand)[2 * q], v1 = reinterpret_cast<const ulonglong2*>(cand)[2 * q + 1];
+          e0 = v0.x; e1 = v0.y; e2 = v1.x; e3 = v1.y;
+        } else {
+          e0 = cand[b0]; e1 = cand[b0 + h]; e2 = cand[b0 + 2 * h]; e3 = cand[b0 + 3 * h];
+        }
+        cx(e0, e2, desc);
+        cx(e1, e3, desc);
+        cx(e0, e1, desc);
+        cx(e2, e3, desc);
+        if (h == 1) {
+          reinterpret_cast<ulonglong2*>(cand)[2 * q] = make_ulonglong2(e0, e1);
+          reinterpret_cast<ulonglong2*>(cand)[2 * q + 1] = make_ulonglong2(e2, e3);
+        } else {
+          cand[b0] = e0;
+          cand[b0 + h] = e1;
+          cand[b0 + 2 * h] = e2;
+          cand[b0 + 3 * h] = e3;
+        }
+      }
+    }
+    if (stride == 1) {   // odd number of steps for this size: the last one on its own
       __syncthreads();
       for (int t = tid; t < (kp >> 1); t += kThreads) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
+        const int lo = 2 * t;
         const bool desc = ((lo & size) == 0);
-        unsigned long long a = cand[lo], b = cand[hi];
-        if (desc ? (a < b) : (a > b)) {
-          cand[lo] = b;
-          cand[hi] = a;
-        }
+        ulonglong2 v = reinterpret_cast<const ulonglong2*>(cand)[t];
+        if (desc ? (v.x < v.y) : (v.x > v.y)) reinterpret_cast<ulonglong2*>(cand)[t] = make_ulonglong2(v.y, v.x);
       }
     }
   }
