@@ -91,19 +91,41 @@ __device__ __forceinline__ void warp_sum4(float (&v)[4]) {
   }
 }
 
-// Normalise the prototypes into shared memory: rh[j][d] = r[j][d] / max(||r_j||, eps).  One warp per prototype.
+// Normalise the prototypes into shared memory: rh[j][d] = r[j][d] / max(||r_j||, eps).  One warp per prototype, FOUR
+// prototypes of a warp in flight at a time (their loads and their reductions overlap): every CTA of the loss kernels runs
+// this prologue, and as a chain of one prototype after the other it cost 3.9 us of a 16 us kernel (%globaltimer stamps).
 __device__ __forceinline__ void load_unit_reps(const PlnParams& p, float* rh, float* inv_norm_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = warp; j < p.Kr; j += kWarps) {
-    float ss = 0.f;
-    for (int d = lane; d < p.D; d += 32) {
-      const float v = __ldg(p.reps + (int64_t)j * p.D + d);
-      ss = fmaf(v, v, ss);
+  for (int j0 = warp; j0 < p.Kr; j0 += 4 * kWarps) {
+    float v[4][kMaxD / 32], ss[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * kWarps;
+      ss[u] = 0.f;
+#pragma unroll
+      for (int q = 0; q < kMaxD / 32; ++q) {
+        const int d = q * 32 + lane;
+        v[u][q] = (j < p.Kr && d < p.D) ? __ldg(p.reps + (int64_t)j * p.D + d) : 0.f;
+      }
     }
-    ss = warp_sum(ss);
-    const float denom = fmaxf(sqrtf(ss), kEps);
-    for (int d = lane; d < p.D; d += 32) rh[j * p.D + d] = __ldg(p.reps + (int64_t)j * p.D + d) / denom;
-    if (inv_norm_out && lane == 0) inv_norm_out[j] = 1.0f / denom;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < kMaxD / 32; ++q) ss[u] = fmaf(v[u][q], v[u][q], ss[u]);   // same order as a strided loop over d
+    warp_sum4(ss);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * kWarps;
+      if (j < p.Kr) {
+        const float denom = fmaxf(sqrtf(ss[u]), kEps);
+#pragma unroll
+        for (int q = 0; q < kMaxD / 32; ++q) {
+          const int d = q * 32 + lane;
+          if (d < p.D) rh[j * p.D + d] = v[u][q] / denom;
+        }
+        if (inv_norm_out && lane == 0) inv_norm_out[j] = 1.0f / denom;
+      }
+    }
   }
 }
 
@@ -116,8 +138,51 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
   load_unit_reps(p, rh, blockIdx.x == 0 ? p.rep_inv_norm : nullptr);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x >= (unsigned)p.num_ctas) {
+    // Prototype-separation term (:171-181) in CTAs of its own behind the row CTAs: one warp per prototype k; hinge value to
+    // the workspace, arg-min prototype saved for the backward.  (On the first row CTAs it sat on the critical path: 6 us.)
+    for (int k = (blockIdx.x - p.num_ctas) * kWarps + warp; k < p.Kr; k += (gridDim.x - p.num_ctas) * kWarps) {
+      float rk[kMaxD / 32];
+#pragma unroll
+      for (int q = 0; q < kMaxD / 32; ++q) rk[q] = (q * 32 + lane < p.D) ? rh[k * p.D + q * 32 + lane] : 0.f;
+      float best = 1000.f;
+      int best_j = -1;
+      for (int j0 = 0; j0 < p.Kr; j0 += 4) {
+        float dd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(j0 + u, p.Kr - 1);
+          float dot = 0.f;
+#pragma unroll
+          for (int q = 0; q < kMaxD / 32; ++q) {
+            const int d = q * 32 + lane;   // same order over d as the strided loop it replaces
+            if (d < p.D) dot = dist_acc<kDist>(rk[q], rh[j * p.D + d], dot);
+          }
+          dd[u] = dot;
+        }
+        warp_sum4(dd);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          if (j >= p.Kr || j / p.rpc == k / p.rpc) continue;  // own-class block masked with 1000 (:179-180)
+          const float dist = dist_finish<kDist>(dd[u]);
+          if (dist < best) {
+            best = dist;
+            best_j = j;
+          }
+        }
+      }
+      const float h = (p.beta + p.alpha) - best;
+      if (lane == 0) {
+        p.partial[2 * p.num_ctas + k] = h > 0.f ? h : 0.f;
+        p.center_rep[k] = (h > 0.f) ? best_j : -1;
+        if (p.saved_dist) p.saved_dist[2 * p.R + k] = best;
+      }
+    }
+    return;
+  }
   float intra_sum = 0.f, inter_sum = 0.f;
-  const int rows_per_cta = osr::ceil_div(p.R, (int)gridDim.x);
+  const int rows_per_cta = osr::ceil_div(p.R, p.num_ctas);
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(p.R, row_begin + rows_per_cta);
   for (int i = row_begin + warp; i < row_end; i += kWarps) {
@@ -255,39 +320,6 @@ __global__ void __launch_bounds__(kThreads) pln_rows_kernel(const __grid_constan
     }
     p.partial[2 * blockIdx.x] = a;
     p.partial[2 * blockIdx.x + 1] = b;
-  }
-  // prototype-separation term (:171-181): one warp per prototype k, spread over the grid (the unit prototypes are
-  // already in shared memory); hinge value to the workspace, arg-min prototype saved for the backward
-  for (int k = blockIdx.x * kWarps + warp; k < p.Kr; k += gridDim.x * kWarps) {
-    float best = 1000.f;
-    int best_j = -1;
-    for (int j0 = 0; j0 < p.Kr; j0 += 4) {
-      float dd[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = min(j0 + u, p.Kr - 1);
-        float dot = 0.f;
-        for (int d = lane; d < p.D; d += 32) dot = dist_acc<kDist>(rh[k * p.D + d], rh[j * p.D + d], dot);
-        dd[u] = dot;
-      }
-      warp_sum4(dd);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u;
-        if (j >= p.Kr || j / p.rpc == k / p.rpc) continue;  // own-class block masked with 1000 (:179-180)
-        const float dist = dist_finish<kDist>(dd[u]);
-        if (dist < best) {
-          best = dist;
-          best_j = j;
-        }
-      }
-    }
-    const float h = (p.beta + p.alpha) - best;
-    if (lane == 0) {
-      p.partial[2 * gridDim.x + k] = h > 0.f ? h : 0.f;
-      p.center_rep[k] = (h > 0.f) ? best_j : -1;
-      if (p.saved_dist) p.saved_dist[2 * p.R + k] = best;
-    }
   }
 }
 
@@ -629,7 +661,7 @@ int osr_pln_loss_fwd(const float* emb, const float* reps, const int64_t* labels,
   p.num_ctas = fwd_ctas(R > 0 ? R : 1);   // also launched for R == 0: the separation term does not depend on the rows
   OSR_PLN_DISPATCH(distance_type, {
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<false, kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pln_rows_kernel<false, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
+    pln_rows_kernel<false, kD><<<p.num_ctas + osr::ceil_div(p.Kr, kWarps), kThreads, smem, s>>>(p);
   });
   OSR_LAUNCH_CHECK();
   pln_final_kernel<<<1, kThreads, 0, s>>>(p);
@@ -674,7 +706,7 @@ static int pln_loss_fwd_bwd_impl(int phase, const float* emb, const float* reps,
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_rows_kernel<true, kD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OSR_CUDA_CHECK(cudaFuncSetAttribute(pln_grad_reps_final<kD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (phase != 2) {
-      pln_rows_kernel<true, kD><<<p.num_ctas, kThreads, smem, s>>>(p);
+      pln_rows_kernel<true, kD><<<p.num_ctas + osr::ceil_div(p.Kr, kWarps), kThreads, smem, s>>>(p);
       OSR_LAUNCH_CHECK();
     }
     if (phase != 1) {
