@@ -45,8 +45,8 @@ void osr_reset_launch_count(void);
 /* Kernel-variant switches for A/B measurements (bench.py, tools/): NOT part of the drop-in surface.  Each key starts
  * at its default (0 = the shipped kernel), or at the value of the environment variable OSR_TUNE_<KEY> read ONCE when
  * the library is loaded - no entry point calls getenv.  Returns the previous value, or OSR_E_ARG for an unknown key.
- *   OSR_TUNE_BWD_VARIANT   0 register accumulators + packed fp32x2 FMAs (shipped) | 2 shared-memory accumulators
- *                          (round-1 kernel) | 3 pixel-per-thread kernel
+ *   OSR_TUNE_BWD_VARIANT   0 register accumulators + packed fp32x2 FMAs, two staging buffers per warp (shipped) | 1 the same
+ *                          with one staging buffer | 2 shared-memory accumulators (round-1 kernel) | 3 pixel-per-thread kernel
  *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records | 4 persistent channels_last kernel
  *                          | 5 one footprint row per row-loop iteration (round-1 loop; the default folds two)
  *   OSR_TUNE_PLN_VARIANT   0 encoder GEMM on fp32 operands (tcgen05 kind::tf32, no cast pass; shipped) | 1 bf16 copies (kind::f16)

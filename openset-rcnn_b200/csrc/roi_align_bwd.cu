@@ -46,8 +46,7 @@ struct __align__(16) RoiInfoPacked {   // 16 bytes: the per-tile scans read it w
   short x0, x1, y0, y1;
   int level, pad;
 };
-__device__ __forceinline__ RoiInfo load_info(const RoiInfoPacked* q) {
-  const int4 v = __ldg(reinterpret_cast<const int4*>(q));
+__device__ __forceinline__ RoiInfo unpack_info(const int4 v) {
   RoiInfo r;
   r.x0 = (short)(v.x & 0xffff); r.x1 = v.x >> 16;
   r.y0 = (short)(v.y & 0xffff); r.y1 = v.y >> 16;
@@ -55,6 +54,7 @@ __device__ __forceinline__ RoiInfo load_info(const RoiInfoPacked* q) {
   r.flags = v.w;
   return r;
 }
+__device__ __forceinline__ RoiInfo load_info(const RoiInfoPacked* q) { return unpack_info(__ldg(reinterpret_cast<const int4*>(q))); }
 
 struct BwdParams {
   RoiLevels L;
@@ -497,6 +497,10 @@ struct __align__(16) ClSmem {
   int warp_cnt[kCWarps + 1];
   int nb, next_pos;
   static constexpr bool kDenseCols = false;
+  static constexpr bool kHasInfo = false;
+  static constexpr int kNB = kCNB;
+  __device__ __forceinline__ float* scratch() { return &sg[0][0]; }
+  __device__ __forceinline__ const float* scratch() const { return &sg[0][0]; }
 };
 
 static_assert((kCNB * kCH + kCThreads) * 8 <= kCWarps * kGBlk, "table scratch must fit in the staging buffers");
@@ -510,7 +514,8 @@ template <class SM>
 __device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level, int tx0, int ty0, int pos, int r1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int filled = 0, cur = pos;
-  for (; cur < r1 && filled < kCNB; cur += 4 * kCThreads) {
+  constexpr int kNBm = SM::kNB;   // RoIs per batch of this kernel's table set
+  for (; cur < r1 && filled < kNBm; cur += 4 * kCThreads) {
     int hit[4], cnt = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -546,16 +551,18 @@ __device__ __forceinline__ void cl_collect(const BwdParams& p, SM& S, int level,
     for (int k = 0; k < 4; ++k) {
       if (hit[k]) {
         const int m = cur + tid * 4 + k;
-        if (rank < kCNB) S.e[rank].m = m;
-        else if (rank == kCNB) S.next_pos = m;   // the first hit that did not fit: the next batch resumes here
+        if (rank < kNBm) {
+          S.e[rank].m = m;
+          if constexpr (SM::kHasInfo) S.einfo[rank] = __ldg(reinterpret_cast<const int4*>(p.info + m));   // (L1 hit) spares the table pass a dependent global load
+        } else if (rank == kNBm) S.next_pos = m;   // the first hit that did not fit: the next batch resumes here
         ++rank;
       }
     }
     __syncthreads();   // warp_cnt is rewritten by the next window
   }
   if (tid == 0) {
-    S.nb = min(filled, kCNB);
-    if (filled <= kCNB) S.next_pos = min(cur, r1);   // no hit was left over: resume at the first index not scanned yet
+    S.nb = min(filled, kNBm);
+    if (filled <= kNBm) S.next_pos = min(cur, r1);   // no hit was left over: resume at the first index not scanned yet
   }
   __syncthreads();
 }
@@ -587,12 +594,14 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const
     const int r = q - j * (kCH + kCW);
     const bool isy = r < kCH;
     const int m = S.e[j].m;
-    const RoiInfo info = load_info(p.info + m);
+    RoiInfo info;
+    if constexpr (SM::kHasInfo) info = unpack_info(S.einfo[j]);
+    else info = load_info(p.info + m);
     const int pos = isy ? ty0 + r : tx0 + (r - kCH);
     const int base = isy ? info.y0 : info.x0, last = isy ? info.y1 : info.x1;
     // scratch in the idle staging buffers: y rows keep their 7 weights until the packing pass below ((j, row) slot),
     // columns only need them inside this iteration (per-thread slot behind the row slots)
-    float* wd = &S.sg[0][0] + (isy ? (j * kCH + r) * 8 : kCNB * kCH * 8 + tid * 8);
+    float* wd = S.scratch() + (isy ? (j * kCH + r) * 8 : SM::kNB * kCH * 8 + tid * 8);
     if (r == 0) S.org[j] = make_int2(info.y0, info.x0);
 #pragma unroll
     for (int b = 0; b < kP; ++b) wd[b] = 0.f;
@@ -657,7 +666,7 @@ __device__ __forceinline__ void cl_build_tables(const BwdParams& p, SM& S, const
     }
     const int pmv = min(lo, kP - 4);
     const bool fits = (hi < 0) || (hi <= pmv + 3);
-    const float* wd = &S.sg[0][0] + (j * kCH + r) * 8;
+    const float* wd = S.scratch() + (j * kCH + r) * 8;
     const float4 yw = (hi >= 0 && fits) ? make_float4(wd[pmv], wd[pmv + 1], wd[pmv + 2], wd[pmv + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (SM::kDenseCols) {   // row pairs, window weights interleaved for the packed FMAs
       float* d = reinterpret_cast<float*>(&S.yrow2[j][r >> 1][0]) + (r & 1);
@@ -949,23 +958,33 @@ __global__ void __launch_bounds__(kCThreads, 3) roi_align_bwd_cl_kernel(const __
 //   * a finished sub-tile leaves straight from registers: lane = channel, one 128-byte row segment per store.
 // Bit-identical summation order to nothing else - but deterministic (fixed RoI order, fixed FMA order) and the exact
 // adjoint arithmetic of the forward tables.
-struct __align__(16) RegSmem {
-  float sg[kCWarps][kGBlk];                 // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
-  float4 yrow2[kCNB][kCH / 2][2];           // row PAIR (2q, 2q+1): window weights interleaved (w0a,w0b,w1a,w1b | w2a,w2b,w3a,w3b)
-  float4 xd0[kCNB][kCW], xd1[kCNB][kCW];    // all 7 bin weights of the column (w0..w3 | w4..w6, 0)
-  uchar2 lohi[kCNB][kCH];
-  unsigned char pm[kCNB][kCS];
-  unsigned char xne[kCNB][kCW];             // column has weight: bit b = bin b
-  unsigned char xgm[kCNB][kCW / 4];         // OR of xne over the 4 columns of a group: bins the group's expansion must visit
-  unsigned long long mbar[kCWarps];         // per-warp transaction barrier of the bulk copy that fills sg[warp]
-  uchar2 xr[kCNB];                          // [first, last + 1) tile column with weight
-  BatchEntry e[kCNB];
-  int2 org[kCNB];
+// kNBuf staging buffers per warp.  2 = the block of the NEXT (sub-tile, RoI) pair is requested before the current pair is
+// folded (a whole pair of lead instead of the x expansion only); the table set shrinks to 30 RoIs so that three CTAs
+// still fit one SM's shared memory.
+template <int kNBuf, bool kInfo>
+struct __align__(16) RegSmemT {
+  static constexpr int kNB = kNBuf == 2 ? 30 : kCNB;
+  float sg[kCWarps][kNBuf][kGBlk];          // per-warp staging of grad_out[(roi, 32 channels), 7, 7]
+  float4 yrow2[kNB][kCH / 2][2];            // row PAIR (2q, 2q+1): window weights interleaved (w0a,w0b,w1a,w1b | w2a,w2b,w3a,w3b)
+  float4 xd0[kNB][kCW], xd1[kNB][kCW];      // all 7 bin weights of the column (w0..w3 | w4..w6, 0)
+  int4 einfo[kInfo ? kNB : 1];              // the RoI's packed footprint record, kept by the scan for the table pass
+  uchar2 lohi[kNB][kCH];
+  unsigned char pm[kNB][kCS];
+  unsigned char xne[kNB][kCW];              // column has weight: bit b = bin b
+  unsigned char xgm[kNB][kCW / 4];          // OR of xne over the 4 columns of a group: bins the group's expansion must visit
+  unsigned long long mbar[kCWarps][kNBuf];  // per-warp transaction barriers of the bulk copies that fill sg[warp][b]
+  uchar2 xr[kNB];                           // [first, last + 1) tile column with weight
+  BatchEntry e[kNB];
+  int2 org[kNB];
   unsigned stmask[kCS];
   int warp_cnt[kCWarps + 1];
   int nb, next_pos;
   static constexpr bool kDenseCols = true;
+  static constexpr bool kHasInfo = kInfo;
+  __device__ __forceinline__ float* scratch() { return &sg[0][0][0]; }
+  __device__ __forceinline__ const float* scratch() const { return &sg[0][0][0]; }
 };
+static_assert(sizeof(RegSmemT<2, true>) + 1024 <= 233472 / 3, "three CTAs of the double-buffered kernel must fit one SM");
 
 // v * s + c on both halves (SASS: FFMA2 Rd, Rv.F32x2, Rs.F32, Rc.F32x2)
 __device__ __forceinline__ float2 ffma2(float2 v, float s, float2 c) {
@@ -987,7 +1006,8 @@ __device__ __forceinline__ float2 fmul2(float2 v, float s) {
 }
 
 // rg2[q][b] = (rg[2q][b], rg[2q+1][b]) with rg[r][b] = sum_ph Wy[ph][row r] / count * g[ph][b]
-__device__ __forceinline__ void clr_fold_subtile(const float* gl, const RegSmem& S, int j, int st, const BwdParams& p, int y0,
+template <class SM>
+__device__ __forceinline__ void clr_fold_subtile(const float* gl, const SM& S, int j, int st, const BwdParams& p, int y0,
                                                  float2 (&rg2)[kCT / 2][kP]) {
   const int pmv = S.pm[j][st];
   if (pmv < 254) {   // the 4 rows share one window of 4 bins: 28 LDS, 56 FFMA2
@@ -1052,10 +1072,13 @@ __device__ __forceinline__ void clr_wait_bulk(unsigned long long* bar, unsigned 
       "}\n" ::"r"(ba), "r"(parity) : "memory");
 }
 
-template <int kSW, int kMinB>   // kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time.  kMinB: CTAs / SM the register allocation targets
+// kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time.  kMinB: CTAs / SM
+// the register allocation targets.  kNBuf: staging buffers per warp (RegSmemT), kInfo: footprint records kept in shared memory.
+template <int kSW, int kMinB, int kNBuf, bool kInfo>
 __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RegSmem& S = *reinterpret_cast<RegSmem*>(smem_raw);
+  using SM = RegSmemT<kNBuf, kInfo>;
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
 
   int t = (int)(gridDim.x - 1 - blockIdx.x), level = 0;   // coarsest level first (longest CTAs start early)
   while (level + 1 < p.L.num_levels && t >= p.cl_tile_base[level + 1]) ++level;
@@ -1069,12 +1092,16 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   const int C = p.L.C;
   const int nslab = ceil_div(C, kCWarps * 32);
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
-  float* sg = S.sg[warp];
-  unsigned long long* bar = &S.mbar[warp];
-  unsigned bar_phase = 0;
+  float* const sg = S.sg[warp][0];               // buffer b at sg + b * kGBlk
+  unsigned long long* const bar = S.mbar[warp];  // barrier b at bar + b
+  unsigned bar_phase = 0;                        // bit b: parity the next wait on barrier b expects
+  int cur = 0;                                   // buffer the next pair to be folded arrives in
   if (lane == 0) {
-    const unsigned ba = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba));
+#pragma unroll
+    for (int b = 0; b < kNBuf; ++b) {
+      const unsigned ba = (unsigned)__cvta_generic_to_shared(bar + b);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -1101,7 +1128,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
       if (c0w >= C) break;
       float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
       int nj = cl_next_pair(S, -1, 0);
-      if (nj >= 0) clr_stage_bulk(p, sg, bar, S.e[nj].m, c0w, C, lane);
+      if (nj >= 0) clr_stage_bulk(p, sg + cur * kGBlk, bar + cur, S.e[nj].m, c0w, C, lane);
       for (int st = 0; st < kCS; ++st) {
         unsigned m = S.stmask[st];
         const int ys = ty0 + st * kCT;
@@ -1149,13 +1176,21 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
         while (m != 0) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
-          clr_wait_bulk(bar, bar_phase);
-          bar_phase ^= 1u;
+          if constexpr (kNBuf == 2) {   // the other buffer was folded one pair ago (and every lane passed the __syncwarp behind that fold): request the next pair's block now
+            nj = cl_next_pair(S, st, m);
+            if (nj >= 0) clr_stage_bulk(p, sg + (cur ^ 1) * kGBlk, bar + (cur ^ 1), S.e[nj].m, c0w, C, lane);
+          }
+          clr_wait_bulk(bar + cur, (bar_phase >> cur) & 1u);
+          bar_phase ^= 1u << cur;
           float2 rg2[kCT / 2][kP];
-          clr_fold_subtile(sg + lane * (kP * kP), S, j, st, p, ty0 + st * kCT, rg2);
-          __syncwarp();   // every lane is done with the staged block: refill it while the columns are expanded
-          nj = cl_next_pair(S, st, m);
-          if (nj >= 0) clr_stage_bulk(p, sg, bar, S.e[nj].m, c0w, C, lane);
+          clr_fold_subtile(sg + cur * kGBlk + lane * (kP * kP), S, j, st, p, ty0 + st * kCT, rg2);
+          __syncwarp();   // every lane is done with the staged block
+          if constexpr (kNBuf == 2) {
+            cur ^= 1;
+          } else {        // one buffer: refill it while the columns are expanded
+            nj = cl_next_pair(S, st, m);
+            if (nj >= 0) clr_stage_bulk(p, sg, bar, S.e[nj].m, c0w, C, lane);
+          }
           const unsigned gm = *reinterpret_cast<const unsigned*>(S.xgm[j]);   // 4 x 7-bit bin masks, one per 4-column group
           const float4* xd0 = S.xd0[j];
           const float4* xd1 = S.xd1[j];
@@ -1226,6 +1261,21 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
     if (pos >= r1) break;
     __syncthreads();   // tables are rebuilt by the next batch
   }
+}
+
+template <int kNBuf, bool kInfo>
+int launch_clr(const BwdParams& p, dim3 grid, bool sw256, cudaStream_t s) {
+  const size_t smem = sizeof(RegSmemT<kNBuf, kInfo>);
+  if (sw256) {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kNBuf == 2) OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo><<<grid, kCThreads, smem, s>>>(p);
+  } else {
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kNBuf == 2) OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo><<<grid, kCThreads, smem, s>>>(p);
+  }
+  return 0;
 }
 
 int fill_bwd(BwdParams& p, const osr_feat_level_t* h_levels, int num_levels, int num_images, int C, int P,
@@ -1301,16 +1351,13 @@ static int roi_align_bwd_impl(int mode, const osr_feat_level_t* h_grad_levels, i
       OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       roi_align_bwd_cl_kernel<<<grid, kCThreads, smem, s>>>(p);
     } else {                     // register accumulators + packed fp32x2 FMAs (shipped)
-      const size_t smem = sizeof(RegSmem);
       bool sw256 = true;
       for (int l = 0; l < num_levels; ++l) sw256 = sw256 && (p.L.lv[l].sW == 256);
-      if (sw256) {
-        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roi_align_bwd_clr_kernel<256, 3><<<grid, kCThreads, smem, s>>>(p);
-      } else {
-        OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        roi_align_bwd_clr_kernel<0, 3><<<grid, kCThreads, smem, s>>>(p);
-      }
+      // 0 (shipped): two staging buffers per warp - the next pair's block is requested a whole pair ahead - and the footprint
+      // records kept in shared memory by the scan (cfg 2: 0.570 -> 0.562 ms) | 1: one buffer, refilled behind the fold
+      if (variant == 1) rc = launch_clr<1, false>(p, grid, sw256, s);
+      else rc = launch_clr<2, true>(p, grid, sw256, s);
+      if (rc) return rc;
     }
     OSR_LAUNCH_CHECK();
     return 0;

@@ -14,10 +14,11 @@ FWD_RTOL, FWD_ATOL = 1e-5, 2e-5   # features are N(0,1); outputs are means of <=
 BWD_RTOL, BWD_ATOL = 1e-4, 1e-4   # gradients accumulate up to ~hundreds of RoIs per pixel (fp32, different order)
 
 
-@pytest.fixture(params=[0, 2], ids=["bwd_reg_ffma2", "bwd_smem_r1"])
+@pytest.fixture(params=[0, 1, 2], ids=["bwd_reg_ffma2_two_buffers", "bwd_reg_ffma2_one_buffer", "bwd_smem_r1"])
 def bwd_variant(request):
     """Every channels_last backward test runs on the three thread-per-channel kernels (include/osr.h OSR_TUNE_BWD_VARIANT):
-    0 = register accumulators + packed fp32x2 FMAs (shipped), 2 = shared-memory accumulators (round-1 kernel)."""
+    0 = register accumulators + packed fp32x2 FMAs, two staging buffers per warp (shipped), 1 = the same with one staging buffer,
+    2 = shared-memory accumulators (round-1 kernel)."""
     from osr_b200 import _lib
     prev = _lib.set_tuning("bwd", request.param)
     yield request.param
