@@ -138,15 +138,18 @@ def build_cpu_path(num_images: int, cfg):
                                num_classes=cfg.num_classes, seed=cfg.seed + 2)
     g = torch.Generator().manual_seed(cfg.seed + 3)
     grad_pooled = torch.randn(R, cfg.channels, 7, 7, generator=g)
+    # ground truth as in the CUDA arm: matched to the kept proposals of a dry run of S1, so the labelled sampler fills its quota
+    from oracle import rpn as orpn
+    from oracle.structures import Boxes as OBoxes
+    props = orpn.predict_proposals([OBoxes(a) for a in ho.anchors], ho.deltas, ho.centerness, ho.image_sizes,
+                                   pre_nms_topk=cfg.pre_nms_topk, post_nms_topk=cfg.pre_nms_topk, training=True)
+    gtb, gtc, goff = synth.make_matched_gt([p.proposal_boxes.tensor for p in props], cfg.gt_per_image, num_known=cfg.num_known,
+                                           seed=cfg.seed + 5)
+    targets = [(gtb[int(goff[n]):int(goff[n + 1])], gtc[int(goff[n]):int(goff[n + 1])]) for n in range(num_images)]
     path = CpuRoiPath(ho, feats, pi, grad_pooled, None, pre_nms_topk=cfg.pre_nms_topk,
                       rois_per_image=cfg.rois_per_image, num_known=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta,
-                      loss_weight=cfg.loss_weight, iou_threshold=cfg.iou_threshold)
-    # sample positions: first dry run of S1 gives the per-image counts
-    from oracle import rpn as orpn
-    props = orpn.predict_proposals(path.anchors, ho.deltas, ho.centerness, ho.image_sizes,
-                                   pre_nms_topk=cfg.pre_nms_topk, post_nms_topk=cfg.pre_nms_topk, training=True)
-    gs = torch.Generator().manual_seed(cfg.seed + 4)
-    path.sample_idx = [torch.randperm(len(p), generator=gs)[:cfg.rois_per_image] for p in props]
+                      loss_weight=cfg.loss_weight, iou_threshold=cfg.iou_threshold, targets=targets,
+                      num_classes=cfg.num_classes)
     return path
 
 
@@ -406,6 +409,12 @@ def run_ours(args, rank, local_rank, world):
             "path_aggregate": {"alg_bytes": path_bytes, "ms": path_ms, "gbs": path_bytes / (path_ms * 1e-3) / 1e9,
                                "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak},
             "stages": per_stage, "touched_feature_pixels": U}
+
+    if not infer and path.last.get("sample") is not None:   # what the labelled sampler drew in the last step
+        _c = path.last["sample"]["count"].cpu()
+        _cls, _iou = path.last["sample"]["classes"], path.last["sample"]["ious"]
+        _EXTRA["sampled_rows"] = {"per_image_min": int(_c[:, 1].min()), "positives_per_image_mean": float(_c[:, 0].float().mean()),
+                                  "pln_foreground_rows": int(((_cls < cfg.num_known) & (_iou > cfg.iou_threshold)).sum())}
 
     # ---- the library kernels the reference runs on a GPU, same inputs, same process ---------------------
     gbase = None
@@ -681,9 +690,11 @@ def _line(args, world, cfg, N, value, ms_step, clocks, e2e, launches, roof, stag
                    "launch": ("one CUDA graph replay per step" if not (args.config == "cfg3" and world > 1) else "one CUDA graph replay per two steps") if (eager is not None) else "eager launches",
                    "timed_stages": ("S1 proposals + NMS, S3 ROIAlign fwd, S6 ROI-head post-processing (decode + NMS + PLN.inference + "
                                     "classifier NMS); box head / predictor outputs are fixed tensors") if infer else
-                                   ("S1 proposals, S2 glue (proposal<->GT matching kernel + pre-drawn sample gather), S3 ROIAlign fwd, "
+                                   ("S1 proposals, S2 labelled sampling (osr_match_label on all kept proposals + torch.rand keys + osr_sample_rois: "
+                                    "512 RoIs / image, 25 % positive quota, fresh draw every step, no host sync), S3 ROIAlign fwd, "
                                     "S5 encoder+PLN loss fwd/bwd" + (" over the GLOBAL batch (encoder fused with the all-gather of the embeddings over NVLink; loss terms on local rows + one all-reduce of loss and prototype gradient)" if (args.config == "cfg3" and world > 1) else "") +
-                                    ", S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))"),
+                                    " on the SAMPLED rows' matcher classes / IoUs, S3 ROIAlign bwd; box-head FC excluded (SURVEY.md 8(d))"),
+                   "sampled_rows": _EXTRA.get("sampled_rows"),
                    "side_stream": ("the ROIAlign backward's RoI-only table kernel (issued after S2) and the PLN prototype-gradient launches "
                                    "+ loss reduction (issued after the row launch of S5) run on a side stream = parallel branches of the "
                                    "graph; their time is inside value / ms_per_step / eager but not inside stage_ms") if not infer else None,

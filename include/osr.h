@@ -314,6 +314,35 @@ int osr_match_label(const float* boxes, const int32_t* box_offsets, const int32_
                     int64_t* matched_class, void* stream);
 
 /*
+ * Labelled RoI sampling for ALL images in one launch, fused with the gather of the sampled fields.
+ * Replaces the per-image detectron2 subsample_labels (two torch.randperm draws + nonzero, host syncs) inside
+ * ROIHeads._sample_proposals and the per-image field gathers of label_and_sample_proposals
+ *   openset_rcnn/modeling/roi_heads/osrcnn_roi_heads.py:136-175 (_sample_proposals), :203-226 (sampled fields)
+ *   labels   (P) int64 = matched_class of osr_match_label: -1 ignored, background_label = negative, else positive
+ *   keys     (P) fp32 random keys, one per row (e.g. one torch.rand draw): per image the kept positives are the
+ *            min(#pos, num_pos_max) rows with the SMALLEST keys, the kept negatives the min(#neg, num_samples - kept
+ *            positives) smallest - ties by lower row index - i.e. positive[perm[:num_pos]] of the reference with
+ *            perm = stable argsort of the kind's keys: a uniformly random subset in uniformly random order
+ *   box_offsets / box_counts / box_counts_stride: row layout as in osr_match_label; max_boxes_per_image: host upper
+ *            bound of an image's row count (shared-memory sizing: up to ~40 000 rows are cached on chip; 0 or more = the
+ *            rows are re-read from global memory in every pass - same result)
+ *   boxes (P,4), logits (P), ious (P), matched_idx (P) int32, gt_offsets (N+1) int32: sources of the optional outputs
+ * Outputs: out_index (N, num_samples) int32 = sampled row inside its image, positives first, each kind in ascending
+ *   (key, row) order, -1 beyond the image's count; out_count (N, 2) int32 = (kept positives, kept rows);
+ *   optional (NULL to skip), each (N, num_samples[, 4]) and undefined beyond the count: out_boxes, out_logits,
+ *   out_classes int64 (= labels), out_ious, out_gt int64 (= gt_offsets[n] + matched_idx: row in the concatenated targets),
+ *   out_rois (N, num_samples, 5) fp32 = (image n, x1, y1, x2, y2): the `rois` rows of osr_roi_align_fwd.
+ * num_samples <= 4096.  No workspace, one launch, no host sync.
+ */
+int osr_sample_rois(const int64_t* labels, const float* keys, const int32_t* box_offsets, const int32_t* box_counts,
+                    int box_counts_stride, int num_images, int max_boxes_per_image, int num_samples, int num_pos_max,
+                    int64_t background_label,
+                    const float* boxes, const float* logits, const float* ious, const int32_t* matched_idx,
+                    const int32_t* gt_offsets, int32_t* out_index, int32_t* out_count, float* out_boxes,
+                    float* out_logits, int64_t* out_classes, float* out_ious, int64_t* out_gt, float* out_rois,
+                    void* stream);
+
+/*
  * ROI-head inference post-processing, stage 1 (osrcnn_fast_rcnn.py:380-450 and :89-126), all images in one launch:
  * detectron2 Box2BoxTransform(weights = wx,wy,ww,wh; scale_clamp = log(1000/16)).apply_deltas on the class-agnostic
  * (R,4) deltas, objectness = sqrt(iou * centerness) (geometric_mean != 0) or (iou + centerness) / 2, isfinite filter,

@@ -2,8 +2,9 @@
 
 Training step (BASELINE.json configs[1]):
   S1  CF-RPN proposal stage        osr_rpn_select_decode        (classification_free_rpn.py:545 -> :558-610)
-  S2  RoI sampling glue            fixed pre-drawn indices      (osrcnn_roi_heads.py:136-230 is a section 8(f) "next" row;
-                                                                 the timed step gathers 512 proposals/img with torch)
+  S2  RoI sampling glue            osr_match_label + osr_sample_rois   (osrcnn_roi_heads.py:136-230: matcher labels of ALL kept
+                                                                 proposals, then the labelled 512-per-image sample of the whole
+                                                                 batch in one launch, fresh random keys every step)
   S3  ROIPooler forward            osr_roi_align_fwd            (osrcnn_roi_heads.py:306)
   S4  box head FC                  NOT on the path (library GEMM, osrcnn_roi_heads.py:308): a fixed (R,1024) tensor
                                    stands in for its output and a fixed (M,C,7,7) tensor for its input gradient
@@ -22,7 +23,7 @@ from . import _lib, synth
 from .poolers import ROIPooler
 from .pln import pln_encode_tc, pln_loss_from_emb, pln_loss_fwd_bwd
 from .proposals import rpn_select_decode
-from .sampling import match_proposals
+from .sampling import match_proposals, sample_rois
 from .dist import FusedEncoderGather, fused_gathered_pln_loss, gathered_pln_loss
 
 
@@ -128,22 +129,19 @@ class RoiPathStep:
         self.grad_pooled = torch.randn(R, cfg.channels, 7, 7, device=dev, generator=g)
         self.pooler = ROIPooler(7, synth.POOL_SCALES, 0, "ROIAlignV2")
         self.roi_offsets = torch.arange(0, R + 1, cfg.rois_per_image, dtype=torch.int32, device=dev)
-        self.img_col = torch.arange(N, dtype=torch.float32, device=dev).repeat_interleave(cfg.rois_per_image)[:, None]
-        # S2 stand-in: pre-drawn sample positions inside each image's kept proposals (dry run gives the counts)
+        # S2 inputs: ground truth that the kept proposals actually match (a dry run of S1 gives them), so the labelled sampler
+        # fills the reference's positive quota and the prototype loss sees its nominal foreground share
         sel = rpn_select_decode(self.anchors, self.deltas, self.ctr, self.image_hw_dev, cfg.pre_nms_topk)
         counts = sel.counts.cpu()
         L = sel.num_levels
-        gs = torch.Generator().manual_seed(cfg.seed + 4)
-        idx = []
+        kept = []
         for n in range(N):
             c = int(counts[n, L])
             assert c >= cfg.rois_per_image, f"image {n}: only {c} proposals"
-            idx.append(torch.randperm(c, generator=gs)[:cfg.rois_per_image] + n * sel.kmax)
-        self.sample_idx = torch.cat(idx).to(dev)
+            kept.append(sel.boxes[n, :c])
         self.kmax = sel.kmax
-        # S2 matching inputs: synthetic ground truth + the static offsets of the padded proposal layout
-        self.gt_boxes, self.gt_classes, self.gt_off = synth.make_gt(N, 8, cfg.image_hw, num_known=cfg.num_known,
-                                                                   seed=cfg.seed + 5, device=dev)
+        self.gt_boxes, self.gt_classes, self.gt_off = synth.make_matched_gt(kept, cfg.gt_per_image, num_known=cfg.num_known,
+                                                                           seed=cfg.seed + 5)
         self.prop_off = torch.arange(0, (N + 1) * sel.kmax, sel.kmax, dtype=torch.int32, device=dev)
         self.count_col = sel.num_levels
         if cfg.box_head:
@@ -167,7 +165,9 @@ class RoiPathStep:
         if self.events is not None:
             self.events[i].record()
 
-    def step(self, deltas=None, ctr=None, feats=None, stage_events: bool = False, gather_pln: bool = False):
+    def step(self, deltas=None, ctr=None, feats=None, stage_events: bool = False, gather_pln: bool = False, keys=None):
+        """One pass of the path.  ``keys``: the sampler's random keys, one per padded proposal row (N * kmax) - drawn afresh
+        with ``torch.rand`` when omitted (tests pass fixed keys to compare an eager step with a graph replay)."""
         cfg = self.cfg
         deltas = self.deltas if deltas is None else deltas
         ctr = self.ctr if ctr is None else ctr
@@ -177,14 +177,22 @@ class RoiPathStep:
         # S1
         sel = rpn_select_decode(self.anchors, deltas, ctr, self.image_hw_dev, cfg.pre_nms_topk)
         self._mark(1)
-        # S2 (glue): proposal <-> GT matching of ALL kept proposals (osr_match_label, as label_and_sample_proposals
-        # does), then the sampling stand-in: pre-drawn indices (the reference's randperm needs a host sync per image)
+        # S2 (glue): proposal <-> GT matching of ALL kept proposals (osr_match_label), then the labelled sampling of the
+        # whole batch in one launch (osr_sample_rois: fresh random keys, the matcher's classes; positives first, 25 % quota)
+        # which also emits ROIAlign's (image, box) rows and the sampled classes / IoUs the prototype loss consumes -
+        # label_and_sample_proposals (osrcnn_roi_heads.py:136-230) without Instances and without a host sync
         L2 = sel.counts.shape[1]
+        cnt_col = sel.counts[:, self.count_col]
         match = match_proposals(sel.boxes.view(-1, 4), self.prop_off, self.gt_boxes, self.gt_classes, self.gt_off,
                                 self.kmax, iou_threshold=cfg.iou_threshold, background_label=cfg.num_classes,
-                                box_counts=sel.counts[:, self.count_col], box_counts_stride=L2)
-        boxes = sel.boxes.view(-1, 4).index_select(0, self.sample_idx)
-        rois = torch.cat((self.img_col, boxes), dim=1)
+                                box_counts=cnt_col, box_counts_stride=L2)
+        if keys is None:
+            keys = torch.rand(match[3].shape[0], device=match[3].device)
+        smp = sample_rois(match[3], keys, self.prop_off, cfg.rois_per_image, int(cfg.rois_per_image * 0.25), cfg.num_classes,
+                          box_counts=cnt_col, box_counts_stride=L2, boxes=sel.boxes.view(-1, 4), ious=match[1], want_rois=True,
+                          max_boxes_per_image=self.kmax)
+        rois = smp["rois"].view(-1, 5)
+        s_cls, s_iou = smp["classes"].view(-1), smp["ious"].view(-1)
         self._mark(2)
         # the backward's per-RoI tables depend on the RoIs only: issue them now on a side stream (a parallel branch of the
         # captured graph), joined right before the backward gather
@@ -243,14 +251,14 @@ class RoiPathStep:
                            else F.linear(roi_features, pi.enc_w, pi.enc_b))
                     emb_all = all_gather_rows(emb) if W > 1 else emb
                 if W > 1 and gather_pln != "reduce":
-                    labels_all, ious_all = _gather_meta(pi.gt_classes, pi.ious, None)
+                    labels_all, ious_all = _gather_meta(s_cls, s_iou, None)
                 else:
-                    labels_all, ious_all = pi.gt_classes, pi.ious
+                    labels_all, ious_all = s_cls, s_iou
             if gather_pln == "reduce":
                 # embeddings are gathered (fused into the encoder epilogue above) but every row term depends only on (its
                 # embedding, the prototypes): per-rank loss + ONE all-reduce of (loss, representatives.grad) gives the same
                 # value and gradients as evaluating the loss kernels on all W*R rows (dist.reduced_pln_loss; tested)
-                loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
+                loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, s_cls, s_iou, **kw)
                 if W > 1:
                     packed = torch.cat((loss.reshape(1), g_reps.reshape(-1)))
                     tdist.all_reduce(packed)
@@ -270,9 +278,9 @@ class RoiPathStep:
                 # d loss / d emb (what the rest of the backward pass waits for) is complete after the row launch; the
                 # prototype-gradient launches + loss reduction are an independent branch of the backward graph and run on the
                 # side stream next to the ROIAlign backward
-                finish_reps, g_emb = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, split=True, **kw)
+                finish_reps, g_emb = pln_loss_fwd_bwd(emb, reps, s_cls, s_iou, split=True, **kw)
             else:
-                loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, pi.gt_classes, pi.ious, **kw)
+                loss, g_emb, g_reps = pln_loss_fwd_bwd(emb, reps, s_cls, s_iou, **kw)
         self._mark(k); k += 1
         # S3 backward
         cur = torch.cuda.current_stream(rois.device)
@@ -286,7 +294,7 @@ class RoiPathStep:
         if finish_reps is not None:
             cur.wait_stream(self._side)
         self._mark(k)
-        self.last = dict(sel=sel, match=match, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
+        self.last = dict(sel=sel, match=match, sample=smp, keys=keys, rois=rois, pooled=pooled, level=lvl, loss=loss, g_emb=g_emb, g_reps=g_reps,
                          g_feats=g_feats)
         return loss, sel.counts
 

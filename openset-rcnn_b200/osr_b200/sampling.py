@@ -4,8 +4,10 @@ Drop-in for ``OpensetROIHeads.label_and_sample_proposals`` (``osrcnn_roi_heads.p
 returned ``List[Instances]`` (fields ``proposal_boxes``, ``objectness_logits``, ``gt_classes``, ``ious`` and the
 targets' ``gt_*`` fields).  The per-image ``pairwise_iou`` matrix + ``Matcher`` + matched-IoU gather + class assignment
 run as ONE kernel launch for the whole batch (``osr_match_label``: one thread per proposal, GT boxes in shared memory,
-the G x P matrix is never materialised).  The random subsampling keeps detectron2's ``subsample_labels`` with
-``torch.randperm`` (positives first, then negatives, per image) so a seeded run draws what the reference draws.
+the G x P matrix is never materialised).  The random subsampling of the whole batch + the gather of every sampled field
+is a second launch (``osr_sample_rois``: one random key per row, the rows with the smallest keys of each kind are kept -
+the subset detectron2's ``subsample_labels`` keeps when its permutation is the arg-sort of those keys).  With an injected
+``randperm`` the reference's per-image ``subsample_labels`` is replayed draw for draw instead (parity tests).
 
 ``match_proposals`` is the batched tensor-level entry (no ``Instances``), used by the pipeline / bench.
 """
@@ -73,7 +75,8 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
                                batch_size_per_image: int = 512, positive_fraction: float = 0.25,
                                iou_threshold: float = 0.5, proposal_append_gt: bool = True,
                                randperm: Optional[Callable[[int], torch.Tensor]] = None,
-                               generator: Optional[torch.Generator] = None) -> List[Instances]:
+                               generator: Optional[torch.Generator] = None,
+                               keys: Optional[Sequence[torch.Tensor]] = None) -> List[Instances]:
     """``OpensetROIHeads.label_and_sample_proposals(proposals, targets)`` (``osrcnn_roi_heads.py:136-230``); the
     keyword arguments are the module attributes it reads (``num_classes``, ``batch_size_per_image``,
     ``positive_fraction``, ``proposal_matcher`` threshold, ``proposal_append_gt``).  Like the reference it raises
@@ -81,8 +84,10 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
 
     Sampling: with ``randperm`` given (a callable standing for ``torch.randperm``) the reference's per-image
     ``subsample_labels`` is replayed draw for draw (parity tests inject the reference's own permutations).  Without it the
-    whole batch is sampled at once on the device (``sample_labels_batched``: same distribution and order, its own random
-    stream, no per-image host syncs - the stage then has ONE host read, the per-image sample counts)."""
+    whole batch is sampled at once on the device (``sample_rois`` = ``osr_sample_rois``: one ``torch.rand`` key per row, or
+    ``keys`` = one fp32 tensor per image over its proposals followed by its appended ground truth; same distribution and
+    order as the reference's two permutations per image, no per-image host syncs - the stage then has ONE host read, the
+    per-image sample counts)."""
     N = len(proposals)
     assert len(targets) == N
     if N == 0:
@@ -124,7 +129,7 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
                                              iou_threshold=iou_threshold, background_label=num_classes)
     if randperm is None:
         return _finish_batched(proposals, targets, boxes, logits, counts, offs, off, goff, midx, miou, mcls,
-                               num_classes, batch_size_per_image, positive_fraction, proposal_append_gt, generator)
+                               num_classes, batch_size_per_image, positive_fraction, proposal_append_gt, generator, keys)
     box_list = [boxes[offs[n]:offs[n + 1]] for n in range(N)]
     logit_list = [logits[offs[n]:offs[n + 1]] for n in range(N)]
     out = []
@@ -148,6 +153,58 @@ def label_and_sample_proposals(proposals: List[Instances], targets: List[Instanc
                 q.set(name, value.to(dev)[st] if hasattr(value, "to") else value[st])
         out.append(q)
         b0 = b1
+    return out
+
+
+def sample_rois(labels: torch.Tensor, keys: torch.Tensor, box_offsets: torch.Tensor, num_samples: int, num_pos_max: int,
+                bg_label: int, *, box_counts: Optional[torch.Tensor] = None, box_counts_stride: int = 1,
+                boxes: Optional[torch.Tensor] = None, logits: Optional[torch.Tensor] = None,
+                ious: Optional[torch.Tensor] = None, matched_idx: Optional[torch.Tensor] = None,
+                gt_offsets: Optional[torch.Tensor] = None, want_rois: bool = False, max_boxes_per_image: int = 0):
+    """``osr_sample_rois``: detectron2 ``subsample_labels`` for all images in ONE launch (no host sync) + the gather of the
+    sampled fields.  ``labels`` (P) int64 (= ``matched_class``), ``keys`` (P) fp32 random keys, ``box_offsets`` (N+1) int32.
+    Per image the ``min(#pos, num_pos_max)`` positives and ``min(#neg, num_samples - kept positives)`` negatives with the
+    smallest keys are kept (ties: lower row), positives first, each kind in ascending key order.  Returns a dict:
+    ``index`` (N, num_samples) int32 (row inside the image, -1 beyond the count), ``count`` (N, 2) int32 = (kept positives,
+    kept rows) and - for every source given - ``boxes`` / ``logits`` / ``classes`` / ``ious`` / ``gt`` (row in the
+    concatenated targets), each (N, num_samples[, 4]), undefined beyond the count; ``want_rois``: also ``rois``
+    (N, num_samples, 5) = (image, x1, y1, x2, y2), the rows ROIAlign consumes.  ``max_boxes_per_image``: host upper bound
+    of an image's row count (lets the kernel keep the rows in shared memory; 0 = unknown, rows are re-read)."""
+    _lib.require_cuda(labels, keys, box_offsets)
+    lib = _lib.lib()
+    dev = labels.device
+    assert labels.dtype == torch.int64 and keys.dtype == torch.float32 and box_offsets.dtype == torch.int32
+    labels, keys = labels.contiguous(), keys.contiguous()
+    N = box_offsets.numel() - 1
+    S = int(num_samples)
+    out = dict(index=torch.empty((N, S), dtype=torch.int32, device=dev), count=torch.empty((N, 2), dtype=torch.int32, device=dev))
+    if boxes is not None:
+        boxes = boxes.contiguous().float()
+        if not want_rois:
+            out["boxes"] = torch.empty((N, S, 4), dtype=torch.float32, device=dev)
+    if logits is not None:
+        logits = logits.contiguous().float()
+        out["logits"] = torch.empty((N, S), dtype=torch.float32, device=dev)
+    if ious is not None:
+        ious = ious.contiguous().float()
+        out["ious"] = torch.empty((N, S), dtype=torch.float32, device=dev)
+    if matched_idx is not None:
+        assert matched_idx.dtype == torch.int32
+        matched_idx = matched_idx.contiguous()
+        out["gt"] = torch.empty((N, S), dtype=torch.int64, device=dev)
+    out["classes"] = torch.empty((N, S), dtype=torch.int64, device=dev)
+    if want_rois:
+        assert boxes is not None
+        out["rois"] = torch.empty((N, S, 5), dtype=torch.float32, device=dev)
+    if N > 0:
+        rc = lib.osr_sample_rois(labels.data_ptr(), keys.data_ptr(), box_offsets.data_ptr(), _lib.ptr(box_counts),
+                                 int(box_counts_stride), int(N), int(max_boxes_per_image), S, int(num_pos_max), int(bg_label),
+                                 _lib.ptr(boxes),
+                                 _lib.ptr(logits), _lib.ptr(ious), _lib.ptr(matched_idx), _lib.ptr(gt_offsets),
+                                 out["index"].data_ptr(), out["count"].data_ptr(), _lib.ptr(out.get("boxes")),
+                                 _lib.ptr(out.get("logits")), out["classes"].data_ptr(), _lib.ptr(out.get("ious")),
+                                 _lib.ptr(out.get("gt")), _lib.ptr(out.get("rois")), _lib.stream_ptr(dev))
+        _lib.check(rc, "osr_sample_rois")
     return out
 
 
@@ -178,39 +235,42 @@ def sample_labels_batched(labels: torch.Tensor, valid: torch.Tensor, num_samples
 
 
 def _finish_batched(proposals, targets, boxes, logits, counts, offs, off, goff, midx, miou, mcls, num_classes,
-                    batch_size_per_image, positive_fraction, proposal_append_gt, generator):
-    """Sampling + field gathering of ``label_and_sample_proposals`` for the whole batch: padded (N, Pmax) label matrix,
-    ``sample_labels_batched``, batched gathers of every sampled field (the targets' ``gt_*`` fields are concatenated once
-    and gathered once), ONE host read of the per-image sample counts, then views."""
+                    batch_size_per_image, positive_fraction, proposal_append_gt, generator, keys=None):
+    """Sampling + field gathering of ``label_and_sample_proposals`` for the whole batch: ONE launch (``osr_sample_rois``)
+    draws the samples of every image and gathers boxes / logits / classes / IoUs / matched ground-truth rows, the targets'
+    ``gt_*`` fields are concatenated once and gathered once, ONE host read of the per-image sample counts, then views."""
     N = len(proposals)
     dev = mcls.device
-    Pmax = max(counts)
     total = offs[-1]
-    if min(counts) == Pmax:       # equal counts: the label matrix is a view
-        labels = mcls.view(N, Pmax)
-        valid = torch.ones((N, Pmax), dtype=torch.bool, device=dev)
+    if keys is None:
+        keys_t = torch.rand(total, device=dev, generator=generator)
     else:
-        cnt_t = (off[1:] - off[:-1]).long()
-        ar = torch.arange(Pmax, device=dev)
-        valid = ar[None, :] < cnt_t[:, None]
-        src = (off[:-1].long()[:, None] + ar[None, :]).clamp(max=total - 1)   # padded gather instead of a scatter
-        labels = torch.where(valid, mcls[src], torch.full((), -2, dtype=mcls.dtype, device=dev))
-    idx, cnt = sample_labels_batched(labels, valid, batch_size_per_image, positive_fraction, num_classes, generator)
-    flat_c = (idx + off[:-1].long()[:, None]).clamp(max=total - 1)     # positions in the concatenated proposal list
-    sb, sl, sc, si = boxes[flat_c], logits[flat_c], mcls[flat_c], miou[flat_c]
-    sm_g = midx[flat_c].long() + goff[:-1].long()[:, None]              # matched GT rows in the concatenated targets
+        keys_t = torch.cat([k.to(dev).float().reshape(-1) for k in keys]) if not torch.is_tensor(keys) else keys.to(dev).float()
+        assert keys_t.numel() == total, "keys: one value per proposal (+ appended ground truth) of every image"
+    S = int(batch_size_per_image)
+    smp = sample_rois(mcls, keys_t, off, S, int(S * positive_fraction), num_classes, boxes=boxes, logits=logits, ious=miou,
+                      matched_idx=midx, gt_offsets=goff, max_boxes_per_image=max(counts))
+    cnt_dev = smp["count"][:, 1]
+    idx, sb, sl, sc, si, sm_g = smp["index"], smp["boxes"], smp["logits"], smp["classes"], smp["ious"], smp["gt"]
     # the targets' gt_* fields, concatenated once and gathered once (tensor / Boxes fields; anything else per image below)
     gt_names = [name for name in targets[0].get_fields() if name.startswith("gt_")]
     batched, per_image = {}, []
+    safe_g = None
     for name in gt_names:
+        if name == "gt_classes":      # already there: the sampled class column (label_and_sample_proposals sets it first)
+            continue
         vals = [t.get(name) for t in targets]
-        if all(isinstance(v, Boxes) for v in vals):
-            batched[name] = ("boxes", torch.cat([v.tensor.to(dev) for v in vals], dim=0)[sm_g])
-        elif all(torch.is_tensor(v) for v in vals):
-            batched[name] = ("tensor", torch.cat([v.to(dev) for v in vals], dim=0)[sm_g])
+        if all(isinstance(v, Boxes) for v in vals) or all(torch.is_tensor(v) for v in vals):
+            if safe_g is None:        # slots beyond an image's count hold garbage rows: clamp before gathering
+                n_gt = sum(len(v) for v in vals)
+                safe_g = sm_g.clamp(min=0, max=max(n_gt - 1, 0))
+            if isinstance(vals[0], Boxes):
+                batched[name] = ("boxes", torch.cat([v.tensor.to(dev) for v in vals], dim=0)[safe_g])
+            else:
+                batched[name] = ("tensor", torch.cat([v.to(dev) for v in vals], dim=0)[safe_g])
         else:
             per_image.append(name)
-    n_s = cnt.tolist()                                        # the one host sync of the stage
+    n_s = cnt_dev.tolist()                                    # the one host sync of the stage
     out = []
     for n, (p, t) in enumerate(zip(proposals, targets)):
         k = n_s[n]
@@ -220,7 +280,7 @@ def _finish_batched(proposals, targets, boxes, logits, counts, offs, off, goff, 
         if not proposal_append_gt:
             for name, value in p.get_fields().items():
                 if name not in ("proposal_boxes", "objectness_logits"):
-                    q.set(name, value[idx[n, :k]])
+                    q.set(name, value[idx[n, :k].long()])
         q.set("gt_classes", sc[n, :k])
         q.set("ious", si[n, :k])
         for name in gt_names:

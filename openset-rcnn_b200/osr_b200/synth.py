@@ -156,6 +156,31 @@ def make_gt(num_images: int, gt_per_image: int = 8, image_hw=(800, 1333), *, num
     return boxes.to(device), classes.to(device), off.to(device)
 
 
+def make_matched_gt(kept_boxes, gt_per_image: int = 8, *, num_known: int = 20, seed: int = 5, candidates: int = 512):
+    """Ground truth that the proposals actually match: per image, ``gt_per_image`` of its kept proposals - those (among
+    ``candidates`` random ones) that the most other kept proposals overlap at IoU >= 0.5 - with classes U{0..K-1}.
+    Random ground truth (``make_gt``) leaves the labelled sampler almost no positives; with this one the positive quota of
+    the reference (25 % of 512) fills, so the sampled labels / IoUs give the prototype loss its nominal foreground share.
+    ``kept_boxes``: list of (P_n, 4) tensors.  Returns ``(boxes (G,4), classes (G) int64, offsets (N+1) int32)``."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out_b, out_c = [], []
+    for b in kept_boxes:
+        P = b.shape[0]
+        cand = b[torch.randperm(P, generator=g)[:min(candidates, P)].to(b.device)]
+        area_c = (cand[:, 2] - cand[:, 0]) * (cand[:, 3] - cand[:, 1])
+        area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+        lt = torch.maximum(cand[:, None, :2], b[None, :, :2])
+        rb = torch.minimum(cand[:, None, 2:], b[None, :, 2:])
+        wh = (rb - lt).clamp(min=0)
+        inter = wh[..., 0] * wh[..., 1]
+        iou = inter / (area_c[:, None] + area_b[None, :] - inter).clamp(min=1e-9)
+        hits = (iou >= 0.5).sum(dim=1)
+        out_b.append(cand[hits.topk(min(gt_per_image, cand.shape[0])).indices])
+        out_c.append(torch.randint(0, num_known, (out_b[-1].shape[0],), generator=g).to(b.device))
+    off = torch.tensor([0] + [int(x.shape[0]) for x in out_b]).cumsum(0).to(torch.int32).to(kept_boxes[0].device)
+    return torch.cat(out_b).contiguous(), torch.cat(out_c), off
+
+
 @dataclass
 class PLNInputs:
     roi_features: torch.Tensor   # (R, feat_dim)

@@ -60,6 +60,20 @@ def subsample_labels(labels: torch.Tensor, num_samples: int, positive_fraction: 
     return positive[perm1], negative[perm2]
 
 
+def keyed_randperm(keys_per_call):
+    """The permutation stream under which ``subsample_labels`` keeps, per kind, the rows with the SMALLEST random keys in
+    ascending (key, row) order - the contract of the one-launch CUDA sampler (``osr_sample_rois``): call i returns the
+    stable arg-sort of ``keys_per_call[i]`` (the keys of the image's positives, then of its negatives, image after image:
+    the order ``subsample_labels`` draws its permutations in)."""
+    it = iter(keys_per_call)
+
+    def rp(n):
+        k = next(it)
+        assert k.numel() == n
+        return torch.argsort(k, stable=True)
+    return rp
+
+
 def sample_proposals(matched_idxs, matched_labels, gt_classes, *, num_classes, batch_size_per_image,
                      positive_fraction, randperm):
     """detectron2 ``ROIHeads._sample_proposals``."""

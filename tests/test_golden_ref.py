@@ -266,6 +266,30 @@ def test_gpu_sampling_matches_reference():
 
 
 @pytest.mark.gpu
+def test_gpu_keyed_sampling_kernel_matches_reference():
+    """The one-launch sampler (osr_sample_rois, the default path of label_and_sample_proposals) against the unmodified
+    reference's run: the random keys are built so that their arg-sort over an image's positives / negatives is the
+    permutation the reference drew (fixture ``sample_perm*``); the sampled Instances must then be the reference's, bit for bit."""
+    from osr_b200 import sampling as S, structures as st
+    keys = []
+    for n in range(N):
+        boxes = torch.cat((t(f"rpn_train_boxes{n}"), t(f"gt_boxes{n}")))          # proposals + appended ground truth
+        m = ost.pairwise_iou(ost.Boxes(t(f"gt_boxes{n}")), ost.Boxes(boxes))
+        idx, lab = osamp.matcher(m, 0.5)
+        cls = t(f"gt_classes{n}")[idx].clone()
+        cls[lab == 0] = 81
+        k = torch.full((boxes.shape[0],), 2.0)
+        for rows, perm in ((torch.nonzero(cls != 81).flatten(), t(f"sample_perm{2 * n}")),
+                           (torch.nonzero(cls == 81).flatten(), t(f"sample_perm{2 * n + 1}"))):
+            assert perm.numel() == rows.numel()
+            k[rows[perm]] = (torch.arange(rows.numel(), dtype=torch.float32) + 0.5) / max(rows.numel(), 1)
+        keys.append(k)
+    res = S.label_and_sample_proposals(proposals_of(st, "train", "cuda"), targets_of(st, "cuda"), num_classes=81,
+                                       batch_size_per_image=64, positive_fraction=0.25, keys=keys)
+    check_sampled(res)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_gpu_training_forward_matches_reference(channels_last):
     from osr_b200 import structures as st

@@ -26,7 +26,9 @@ def test_direct_step_equals_autograd_formulation():
     pi = path.pln
     emb = pln_encode_tc(pi.roi_features, pi.enc_w, pi.enc_b).requires_grad_(True)
     reps = pi.reps.detach().clone().requires_grad_(True)
-    l2 = pln_loss_from_emb(emb, reps, pi.gt_classes, pi.ious, num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta,
+    s_cls, s_iou = last["sample"]["classes"].view(-1), last["sample"]["ious"].view(-1)   # the matcher's, via the sampler
+    assert int(((s_cls < cfg.num_known) & (s_iou > cfg.iou_threshold)).sum()) > 0
+    l2 = pln_loss_from_emb(emb, reps, s_cls, s_iou, num_known_classes=cfg.num_known, alpha=cfg.alpha, beta=cfg.beta,
                            loss_weight=cfg.loss_weight, iou_threshold=cfg.iou_threshold)
     ge, gr = torch.autograd.grad(l2, [emb, reps])
     assert torch.equal(l2.detach(), loss.detach())
@@ -35,17 +37,18 @@ def test_direct_step_equals_autograd_formulation():
 
 def test_step_replays_from_a_cuda_graph():
     cfg, path = _path()
-    loss, _ = path.step()
+    keys = torch.rand(cfg.num_images * path.kmax, device="cuda:0")   # fixed sampler keys: eager step and replay draw the same sample
+    loss, _ = path.step(keys=keys)
     ref = dict(loss=loss.detach().clone(), g=[g.clone() for g in path.last["g_feats"]], pooled=path.last["pooled"].clone())
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        path.step()
+        path.step(keys=keys)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        loss_g, _ = path.step()
+        loss_g, _ = path.step(keys=keys)
     out = path.last
     for t in out["g_feats"]:
         t.zero_()
@@ -54,3 +57,31 @@ def test_step_replays_from_a_cuda_graph():
     assert torch.equal(loss_g, ref["loss"]) and torch.equal(out["pooled"], ref["pooled"])
     for a, b in zip(out["g_feats"], ref["g"]):
         assert torch.equal(a, b)
+
+
+def test_graph_replay_draws_a_fresh_sample_every_step():
+    """Without fixed keys the captured step holds the torch.rand launch: every replay samples anew (a graph-safe generator
+    offset), always 512-style full samples with the positives first."""
+    cfg, path = _path()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        path.step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        path.step()
+    out = path.last
+    seen = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        seen.append(out["sample"]["index"].clone())
+        cnt = out["sample"]["count"]
+        assert int(cnt[:, 1].min()) == cfg.rois_per_image
+        cls = out["sample"]["classes"]
+        for n in range(cfg.num_images):
+            k = int(cnt[n, 0])
+            assert bool((cls[n, :k] != cfg.num_classes).all()) and bool((cls[n, k:] == cfg.num_classes).all())
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])

@@ -153,3 +153,110 @@ def test_label_and_sample_batched_path_is_consistent_with_the_matcher():
         n_fg = int((q.get("gt_classes") != 80).sum())
         assert n_fg <= 32 and bool((q.get("gt_classes")[:n_fg] != 80).all()) and bool((q.get("gt_classes")[n_fg:] == 80).all())
         assert len(q) == min(128, n_fg + int((cls == 80).sum()))
+
+
+def _keyed_randperm(keys_of_kind):
+    """The permutation detectron2's subsample_labels would have to draw so that it keeps the rows with the smallest keys in
+    ascending (key, row) order: the stable arg-sort of the kind's keys.  `keys_of_kind` is consumed in call order
+    (positives, then negatives, image after image) - the order subsample_labels calls randperm in."""
+    it = iter(keys_of_kind)
+
+    def rp(n):
+        k = next(it)
+        assert k.numel() == n
+        return torch.argsort(k, stable=True)
+    return rp
+
+
+@pytest.mark.parametrize("case", ["mixed", "ties", "few_rows", "all_positive", "no_positive_quota", "counts_column"])
+def test_sample_rois_equals_subsample_labels_with_the_keyed_permutation(case):
+    """osr_sample_rois against the restatement of detectron2's subsample_labels (oracle/sampling.py), fed with the
+    permutation that the keys define; bit-exact indices, counts and gathered fields, no tolerance."""
+    from osr_b200.sampling import sample_rois
+    g = torch.Generator().manual_seed(hash(case) % 1000 + 3)
+    S, frac, bg = 128, 0.25, 80
+    sizes = {"mixed": [7323, 500, 40, 0, 2000], "ties": [3000, 700], "few_rows": [50, 5, 1],
+             "all_positive": [600, 90], "no_positive_quota": [900], "counts_column": [300, 2000, 17]}[case]
+    if case == "no_positive_quota":
+        frac = 0.0
+    labels, keys = [], []
+    for P in sizes:
+        r = torch.rand(P, generator=g)
+        lab = torch.full((P,), bg, dtype=torch.int64)
+        lab[r < 0.15] = torch.randint(0, 20, (int((r < 0.15).sum()),), generator=g)
+        lab[(r >= 0.15) & (r < 0.2)] = -1
+        if case == "all_positive":
+            lab = torch.randint(0, 20, (P,), generator=g)
+        k = torch.rand(P, generator=g)
+        if case == "ties":
+            k = torch.floor(k * 16) / 16          # 16 distinct keys: the threshold bucket always holds ties
+            k[::7] = -k[::7]                      # negative keys order below positive ones
+        labels.append(lab); keys.append(k)
+    N = len(sizes)
+    kmax = max(sizes) + 5
+    padded = case == "counts_column"
+    if padded:   # (N, kmax) padded rows + a strided counts column, as osr_rpn_select_decode leaves them
+        lab_t = torch.full((N, kmax), 7, dtype=torch.int64); key_t = torch.zeros(N, kmax)
+        for n, (l, k) in enumerate(zip(labels, keys)):
+            lab_t[n, :len(l)] = l; key_t[n, :len(k)] = k
+        off = torch.arange(0, (N + 1) * kmax, kmax, dtype=torch.int32)
+        cnt = torch.zeros(N, 3, dtype=torch.int32); cnt[:, 1] = torch.tensor(sizes, dtype=torch.int32)
+        lab_t, key_t = lab_t.view(-1), key_t.view(-1)
+    else:
+        lab_t, key_t = torch.cat(labels), torch.cat(keys)
+        off = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int32)
+        cnt = None
+    T = lab_t.numel()
+    boxes = torch.rand(T, 4, generator=g) * 100
+    logits, ious = torch.randn(T, generator=g), torch.rand(T, generator=g)
+    midx = torch.randint(0, 4, (T,), generator=g, dtype=torch.int32)
+    goff = torch.arange(0, 4 * (N + 1), 4, dtype=torch.int32)
+    dev = "cuda:0"
+    # both instantiations: rows cached in shared memory (host bound given) / re-read from global memory in every pass
+    bound = max(sizes) if case in ("mixed", "ties", "all_positive", "counts_column") else 0
+    out = sample_rois(lab_t.to(dev), key_t.to(dev), off.to(dev), S, int(S * frac), bg,
+                      box_counts=None if cnt is None else cnt.to(dev)[:, 1], box_counts_stride=3,
+                      boxes=boxes.to(dev), logits=logits.to(dev), ious=ious.to(dev), matched_idx=midx.to(dev),
+                      gt_offsets=goff.to(dev), max_boxes_per_image=bound)
+    other = sample_rois(lab_t.to(dev), key_t.to(dev), off.to(dev), S, int(S * frac), bg,
+                        box_counts=None if cnt is None else cnt.to(dev)[:, 1], box_counts_stride=3,
+                        max_boxes_per_image=0 if bound else max(sizes))
+    assert torch.equal(other["index"], out["index"]) and torch.equal(other["count"], out["count"])
+    rois = sample_rois(lab_t.to(dev), key_t.to(dev), off.to(dev), S, int(S * frac), bg,
+                       box_counts=None if cnt is None else cnt.to(dev)[:, 1], box_counts_stride=3,
+                       boxes=boxes.to(dev), want_rois=True)["rois"].cpu()
+    index, count = out["index"].cpu(), out["count"].cpu()
+    for n, (lab, k) in enumerate(zip(labels, keys)):
+        pos = torch.nonzero((lab != -1) & (lab != bg)).flatten()
+        neg = torch.nonzero(lab == bg).flatten()
+        fg, bgi = osamp.subsample_labels(lab, S, frac, bg, _keyed_randperm([k[pos], k[neg]]))
+        want = torch.cat([fg, bgi])
+        c = len(want)
+        assert count[n].tolist() == [len(fg), c]
+        assert torch.equal(index[n, :c].long(), want) and bool((index[n, c:] == -1).all())
+        b0 = int(off[n])
+        assert torch.equal(out["boxes"][n, :c].cpu(), boxes[b0 + want])
+        assert torch.equal(out["logits"][n, :c].cpu(), logits[b0 + want])
+        assert torch.equal(out["ious"][n, :c].cpu(), ious[b0 + want])
+        assert torch.equal(out["classes"][n, :c].cpu(), lab[want])
+        assert torch.equal(out["gt"][n, :c].cpu(), midx[b0 + want].long() + 4 * n)
+        assert torch.equal(rois[n, :c, 1:], boxes[b0 + want]) and bool((rois[n, :c, 0] == n).all())
+
+
+def test_sample_rois_is_a_uniform_draw():
+    """Distribution: over many key draws every negative row is kept with probability quota / population (5 sigma)."""
+    from osr_b200.sampling import sample_rois
+    dev = "cuda:0"
+    P, S, trials = 400, 64, 600
+    lab = torch.full((P,), 80, dtype=torch.int64, device=dev)
+    lab[:40] = 3                                   # 40 positives, quota 16
+    off = torch.tensor([0, P], dtype=torch.int32, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    hits = torch.zeros(P, device=dev)
+    for _ in range(trials):
+        idx = sample_rois(lab, torch.rand(P, device=dev, generator=g), off, S, 16, 80)["index"][0].long()
+        hits[idx] += 1
+    p_pos, p_neg = 16 / 40, 48 / 360
+    for sl, pr in ((slice(0, 40), p_pos), (slice(40, P), p_neg)):
+        sd = (trials * pr * (1 - pr)) ** 0.5
+        assert float((hits[sl] - trials * pr).abs().max()) < 5 * sd
