@@ -50,13 +50,17 @@ void osr_reset_launch_count(void);
  *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records | 4 persistent channels_last kernel
  *                          | 5 one footprint row per row-loop iteration (round-1 loop; the default folds two)
  *   OSR_TUNE_PLN_VARIANT   0 encoder GEMM on fp32 operands (tcgen05 kind::tf32, no cast pass; shipped) | 1 bf16 copies (kind::f16)
- *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu */
+ *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu
+ *   OSR_TUNE_BWD_SPLIT     0 one CTA per 16x16 tile of the ROIAlign backward (shipped) | > 0: one hex digit per level
+ *                          (finest first) = log2 of the CTAs per tile (slab groups first, then sub-tile groups; measured
+ *                          slower, csrc/roi_align_bwd.cu fill_bwd) */
 #define OSR_TUNE_BWD_VARIANT 0
 #define OSR_TUNE_FWD_VARIANT 1
 #define OSR_TUNE_PLN_VARIANT 2
 #define OSR_TUNE_RPN_VARIANT 3
 #define OSR_TUNE_NMS_VARIANT 4
-#define OSR_TUNE_COUNT 5
+#define OSR_TUNE_BWD_SPLIT 5
+#define OSR_TUNE_COUNT 6
 int osr_set_tuning(int key, int value);
 int osr_get_tuning(int key);
 

@@ -22,7 +22,7 @@ void count_launch(int n) { g_launches += n; }
 
 // variant switches: initialised once (static initialiser of this translation unit) from OSR_TUNE_<KEY>
 static const char* const kTuneNames[OSR_TUNE_COUNT] = {"OSR_TUNE_BWD_VARIANT", "OSR_TUNE_FWD_VARIANT", "OSR_TUNE_PLN_VARIANT",
-                                                       "OSR_TUNE_RPN_VARIANT", "OSR_TUNE_NMS_VARIANT"};
+                                                       "OSR_TUNE_RPN_VARIANT", "OSR_TUNE_NMS_VARIANT", "OSR_TUNE_BWD_SPLIT"};
 static std::atomic<int> g_tune[OSR_TUNE_COUNT];
 static const bool g_tune_init = [] {
   for (int k = 0; k < OSR_TUNE_COUNT; ++k) {

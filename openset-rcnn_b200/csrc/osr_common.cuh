@@ -17,7 +17,7 @@ void count_launch(int n = 1);
 // kernel-variant switches (osr_set_tuning / OSR_TUNE_* read once at load): A/B measurement only
 enum TuneKey { kTuneBwdVariant = OSR_TUNE_BWD_VARIANT, kTuneFwdVariant = OSR_TUNE_FWD_VARIANT,
                kTunePlnVariant = OSR_TUNE_PLN_VARIANT, kTuneRpnVariant = OSR_TUNE_RPN_VARIANT,
-               kTuneNmsVariant = OSR_TUNE_NMS_VARIANT };
+               kTuneNmsVariant = OSR_TUNE_NMS_VARIANT, kTuneBwdSplit = OSR_TUNE_BWD_SPLIT };
 int tuning(int key);
 
 inline int fail_arg(int code, const char* fmt, ...) {

@@ -68,6 +68,10 @@ struct BwdParams {
   int tiles_x[OSR_MAX_LEVELS], tiles_y[OSR_MAX_LEVELS];
   int cl_tile_base[OSR_MAX_LEVELS + 1];  // same for the channels_last kernel's 16x16 tiles
   int cl_tiles_x[OSR_MAX_LEVELS], cl_tiles_y[OSR_MAX_LEVELS];
+  // register-accumulator kernel: a tile of level l is worked by ps[l] * pt[l] CTAs - ps slab groups x pt sub-tile groups
+  // (coarse levels hold few, heavily covered tiles: one CTA per tile made them the critical path of the launch)
+  int clr_cta_base[OSR_MAX_LEVELS + 1];
+  int clr_ps[OSR_MAX_LEVELS], clr_pt[OSR_MAX_LEVELS];
 };
 
 // one bin of one axis: visit its valid samples as (low row, high row, weight at low, weight at high) - the sample
@@ -801,9 +805,9 @@ __device__ __forceinline__ void cl_stage(const BwdParams& p, float* sg, int m, i
 
 // next (sub-tile, RoI) pair after sub-tile st with remaining mask m; returns the RoI slot or -1
 template <class SM>
-__device__ __forceinline__ int cl_next_pair(const SM& S, int st, unsigned m) {
+__device__ __forceinline__ int cl_next_pair(const SM& S, int st, unsigned m, int st_end = kCS) {
   while (m == 0) {
-    if (++st >= kCS) return -1;
+    if (++st >= st_end) return -1;
     m = S.stmask[st];
   }
   return __ffs(m) - 1;
@@ -1081,8 +1085,11 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   SM& S = *reinterpret_cast<SM*>(smem_raw);
 
   int t = (int)(gridDim.x - 1 - blockIdx.x), level = 0;   // coarsest level first (longest CTAs start early)
-  while (level + 1 < p.L.num_levels && t >= p.cl_tile_base[level + 1]) ++level;
-  t -= p.cl_tile_base[level];
+  while (level + 1 < p.L.num_levels && t >= p.clr_cta_base[level + 1]) ++level;
+  t -= p.clr_cta_base[level];
+  const int ps = p.clr_ps[level], pt = p.clr_pt[level];
+  const int part = t % (ps * pt);     // which share of the tile this CTA works: slab group x sub-tile group
+  t /= ps * pt;
   const int per_img = p.cl_tiles_x[level] * p.cl_tiles_y[level];
   const int n = t / per_img;
   t -= n * per_img;
@@ -1091,6 +1098,8 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.L.C;
   const int nslab = ceil_div(C, kCWarps * 32);
+  const int slab0 = (part % ps) * nslab / ps, slab1 = ((part % ps) + 1) * nslab / ps;     // my slabs
+  const int st0 = (part / ps) * (kCS / pt), st1 = st0 + kCS / pt;                         // my sub-tiles
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   float* const sg = S.sg[warp][0];               // buffer b at sg + b * kGBlk
   unsigned long long* const bar = S.mbar[warp];  // barrier b at bar + b
@@ -1123,13 +1132,13 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
       if (tid < kCS) S.stmask[tid] = 0;
       __syncthreads();
     }
-    for (int slab = 0; slab < nslab; ++slab) {
+    for (int slab = slab0; slab < slab1; ++slab) {
       const int c0w = slab * (kCWarps * 32) + warp * 32;
       if (c0w >= C) break;
       float* gimg = lv.data + (int64_t)n * lv.sN + c0w;
-      int nj = cl_next_pair(S, -1, 0);
+      int nj = cl_next_pair(S, st0 - 1, 0, st1);
       if (nj >= 0) clr_stage_bulk(p, sg + cur * kGBlk, bar + cur, S.e[nj].m, c0w, C, lane);
-      for (int st = 0; st < kCS; ++st) {
+      for (int st = st0; st < st1; ++st) {
         unsigned m = S.stmask[st];
         const int ys = ty0 + st * kCT;
         const int ny = min(kCT, lv.H - ys);
@@ -1177,7 +1186,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
           const int j = __ffs(m) - 1;
           m &= m - 1;
           if constexpr (kNBuf == 2) {   // the other buffer was folded one pair ago (and every lane passed the __syncwarp behind that fold): request the next pair's block now
-            nj = cl_next_pair(S, st, m);
+            nj = cl_next_pair(S, st, m, st1);
             if (nj >= 0) clr_stage_bulk(p, sg + (cur ^ 1) * kGBlk, bar + (cur ^ 1), S.e[nj].m, c0w, C, lane);
           }
           clr_wait_bulk(bar + cur, (bar_phase >> cur) & 1u);
@@ -1188,7 +1197,7 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
           if constexpr (kNBuf == 2) {
             cur ^= 1;
           } else {        // one buffer: refill it while the columns are expanded
-            nj = cl_next_pair(S, st, m);
+            nj = cl_next_pair(S, st, m, st1);
             if (nj >= 0) clr_stage_bulk(p, sg, bar, S.e[nj].m, c0w, C, lane);
           }
           const unsigned gm = *reinterpret_cast<const unsigned*>(S.xgm[j]);   // 4 x 7-bit bin masks, one per 4-column group
@@ -1299,6 +1308,25 @@ int fill_bwd(BwdParams& p, const osr_feat_level_t* h_levels, int num_levels, int
     base += p.cl_tiles_x[l] * p.cl_tiles_y[l] * num_images;
   }
   p.cl_tile_base[num_levels] = base;
+  // CTAs per tile of the register-accumulator kernel: ONE (shipped).  OSR_TUNE_BWD_SPLIT (A/B only): one hex digit per level
+  // (digit l = level l, finest first) = log2 of the tile's CTA count.  Measured at cfg 2 with the sampler's clustered RoIs
+  // (the coarse levels' 16x16 tiles collect 60 - 260 (sub-tile, RoI) pairs each): every split is SLOWER - 0x2110 0.607 ms,
+  // 0x3310 0.662 ms against 0.583 ms - each extra CTA repeats the tile's RoI scan and table build for all its batches, and
+  // the heavy tiles are not the launch's critical path (they start first and finish inside the launch).
+  const int nslab = osr::ceil_div(C, kCWarps * 32);
+  const int code = osr::tuning(osr::kTuneBwdSplit);
+  base = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    int lg = code > 0 ? ((code >> (4 * l)) & 0xf) : 0;
+    int ps = 1, pt = 1;
+    while (lg > 0 && ps * 2 <= nslab && nslab % (ps * 2) == 0 && ps < 2) { ps *= 2; --lg; }   // slabs first: no table work is repeated for pixels a CTA does not own
+    while (lg > 0 && pt * 2 <= kCS) { pt *= 2; --lg; }
+    p.clr_ps[l] = ps;
+    p.clr_pt[l] = pt;
+    p.clr_cta_base[l] = base;
+    base += p.cl_tiles_x[l] * p.cl_tiles_y[l] * num_images * ps * pt;
+  }
+  p.clr_cta_base[num_levels] = base;
   return 0;
 }
 
@@ -1344,8 +1372,8 @@ static int roi_align_bwd_impl(int mode, const osr_feat_level_t* h_grad_levels, i
   bool cl = (C % 32 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) && osr::tuning(osr::kTuneBwdVariant) != 3;
   for (int l = 0; l < num_levels; ++l) cl = cl && (p.L.lv[l].sC == 1);
   if (cl) {
-    dim3 grid(p.cl_tile_base[num_levels], 1);
     const int variant = osr::tuning(osr::kTuneBwdVariant);
+    dim3 grid(variant == 2 ? p.cl_tile_base[num_levels] : p.clr_cta_base[num_levels], 1);
     if (variant == 2) {          // shared-memory accumulators (round-1 kernel)
       const size_t smem = sizeof(ClSmem);
       OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -182,7 +182,7 @@ def reset_launch_count() -> None:
     lib().osr_reset_launch_count()
 
 
-TUNE_KEYS = {"bwd": 0, "fwd": 1, "pln": 2, "rpn": 3, "nms": 4}
+TUNE_KEYS = {"bwd": 0, "fwd": 1, "pln": 2, "rpn": 3, "nms": 4, "bwd_split": 5}
 
 
 def set_tuning(key: str, value: int) -> int:

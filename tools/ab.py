@@ -53,7 +53,7 @@ def main():
         key, vals = sw.split("=")
         ref = None
         for v in vals.split(","):
-            prev = _lib.set_tuning(key, int(v))
+            prev = _lib.set_tuning(key, int(v, 0))
             try:
                 t = time_steps(path, a.steps)
                 cur = dict(loss=path.last["loss"].detach().clone(), g=[g.clone() for g in path.last["g_feats"]],
