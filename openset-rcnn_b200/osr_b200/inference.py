@@ -16,15 +16,15 @@ import torch
 
 from . import _lib
 from .nms import _MAX_SORT, _segmented
-from .structures import Boxes, Instances
+from .structures import Boxes, Instances, cat_rows, flat_prefixes
 
 SCALE_CLAMP = math.log(1000.0 / 16)
 
 
 def _decode(proposal_deltas, ious, proposals, weights, mean_type, score_thresh):
     lib = _lib.lib()
-    pb = torch.cat([p.get("proposal_boxes").tensor for p in proposals], dim=0).contiguous().float()
-    ctr = torch.cat([p.get("objectness_logits") for p in proposals]).contiguous().float()
+    pb = cat_rows([p.get("proposal_boxes").tensor for p in proposals]).contiguous().float()
+    ctr = cat_rows([p.get("objectness_logits") for p in proposals]).contiguous().float()
     _lib.require_cuda(pb, proposal_deltas, ious)
     dev = pb.device
     deltas = proposal_deltas.contiguous().float()
@@ -94,18 +94,30 @@ def inference(predictions: Tuple[torch.Tensor, torch.Tensor], proposals: List[In
     fin_pos = torch.cumsum(finite.long(), 0) - 1
     fin_base = torch.cat((torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(finite.long(), 0)))[off[:-1].long()]
     counts = n_ok.cpu().tolist()   # the one host sync
+    # every image's output rows in ONE gather per field (global indices from the host-known counts); the per-image
+    # Instances are split views of those tensors, which the next stages recognise and do not copy again (cat_rows)
+    ks = [c if topk_per_image < 0 else min(c, topk_per_image) for c in counts]
+    begins, o = [], 0
+    for l in lens:
+        begins.append(o)
+        o += l
+    P, B = flat_prefixes(begins, ks, dev)
+    g = keep_idx.index_select(0, P) + B
+    out_boxes = boxes.index_select(0, g).split(ks)
+    out_scores = scores.index_select(0, g).split(ks)
+    out_feats = feats.index_select(0, g).split(ks)
+    out_cls = torch.zeros(len(g), dtype=torch.int64, device=dev).split(ks)
+    kept_all = fin_pos.index_select(0, g) - fin_base.index_select(0, seg.index_select(0, g))
+    out_kept = kept_all.split(ks)
     results, kept = [], []
     for n, p in enumerate(proposals):
-        b0 = int(sum(lens[:n]))
-        k = counts[n] if topk_per_image < 0 else min(counts[n], topk_per_image)
-        g = keep_idx[b0:b0 + k] + b0
         r = Instances(p.image_size)
-        r.set("pred_boxes", Boxes(boxes[g]))
-        r.set("scores", scores[g])
-        r.set("pred_classes", torch.zeros(k, dtype=torch.int64, device=dev))
-        r.set("features", feats[g])
+        r.set("pred_boxes", Boxes(out_boxes[n]))
+        r.set("scores", out_scores[n])
+        r.set("pred_classes", out_cls[n])
+        r.set("features", out_feats[n])
         results.append(r)
-        kept.append(fin_pos[g] - fin_base[n])
+        kept.append(out_kept[n])
     return results, kept
 
 
@@ -132,22 +144,25 @@ def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, un
 
     The whole batch is processed at once: the per-image Python loop of the reference (masks, finite filters, clip,
     threshold, ``nonzero``: ~25 launches and 3 host syncs per image) becomes one pass over the concatenated detections
-    with per-row image ids, and its two per-image NMS loops (``fast_rcnn_inference_single_image_known/unknown``,
-    ``:47-168``) one segmented NMS call each (``batched_nms_images``: segments = images, torchvision's per-image
-    coordinate trick preserved).  Four host reads per batch (known counts, candidate counts, two NMS keep counts).  Only
-    the classifier GEMM + softmax stay per image, on exactly the rows the reference feeds it (a batched GEMM may pick
-    another algorithm and round differently, and the score threshold / NMS order would see it)."""
-    from .nms import batched_nms_images
+    with per-row image ids, its two per-image NMS loops (``fast_rcnn_inference_single_image_known/unknown``,
+    ``:47-168``) one segmented NMS call each (``batched_nms_flat``: segments = images, torchvision's per-image
+    coordinate trick preserved), and the per-image result assembly one gather per field in a host-built output order
+    (the per-image ``Instances`` are split views).  Four host reads per batch (known counts, candidate counts, two NMS
+    keep counts).  Only the classifier GEMM stays per image, on exactly the rows the reference feeds it (a batched GEMM
+    may pick another algorithm and round differently, and the score threshold / NMS order would see it); the softmax is
+    row-wise and runs once on the concatenated logits."""
+    from .nms import batched_nms_flat
     if not fg_instances:
         return []
+    import numpy as np
     N = len(fg_instances)
     dev = fg_instances[0].get("scores").device
     sizes = [len(x) for x in fg_instances]
     T = int(sum(sizes))
-    boxes = torch.cat([x.get("pred_boxes").tensor for x in fg_instances], dim=0)
-    scores = torch.cat([x.get("scores") for x in fg_instances], dim=0)
-    pcls = torch.cat([x.get("pred_classes") for x in fg_instances], dim=0)
-    feats = torch.cat([x.get("features") for x in fg_instances], dim=0)
+    boxes = cat_rows([x.get("pred_boxes").tensor for x in fg_instances])
+    scores = cat_rows([x.get("scores") for x in fg_instances])
+    pcls = cat_rows([x.get("pred_classes") for x in fg_instances])
+    feats = cat_rows([x.get("features") for x in fg_instances])
     img = torch.repeat_interleave(torch.arange(N, device=dev), torch.tensor(sizes, device=dev), output_size=T)
     hw = torch.tensor([[float(x.image_size[0]), float(x.image_size[1])] for x in fg_instances], device=dev)
     known = pcls != unknown_id
@@ -162,12 +177,13 @@ def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, un
         return torch.stack((torch.minimum(torch.maximum(b[:, 0], zero), w), torch.minimum(torch.maximum(b[:, 1], zero), h),
                             torch.minimum(torch.maximum(b[:, 2], zero), w), torch.minimum(torch.maximum(b[:, 3], zero), h)), dim=-1)
 
-    # ---- known detections: classifier (per image), finite filter, clip, score threshold -> (row, class) candidates
-    probs_l, o = [], 0
+    # ---- known detections: classifier (one gather, then per image), finite filter, clip, score threshold -> (row, class) candidates
+    fk = feats.index_select(0, kidx)
+    logits_l, o = [], 0
     for n in range(N):
-        probs_l.append(torch.softmax(cls_score(feats.index_select(0, kidx[o:o + n_known[n]])), dim=-1))
+        logits_l.append(cls_score(fk[o:o + n_known[n]]))
         o += n_known[n]
-    probs = torch.cat(probs_l, dim=0)
+    probs = torch.softmax(torch.cat(logits_l, dim=0), dim=-1)
     kb = boxes.index_select(0, kidx)
     kimg = img.index_select(0, kidx)
     valid_k = torch.isfinite(kb).all(dim=1) & torch.isfinite(probs).all(dim=1)
@@ -185,28 +201,39 @@ def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, un
     c_boxes = kb_c.index_select(0, inds[:, 0])
     c_scores = probs[inds[:, 0], inds[:, 1]]
     c_cls = inds[:, 1]
+    c_img = kimg.index_select(0, inds[:, 0])
     usel = _nonzero_known_size(keep_u_mask, sum(cnt_u))[:, 0]
     u_boxes = clip(ub, uimg).index_select(0, usel)
     u_scores = us.index_select(0, usel)
-    kb_l, ks_l, kc_l = list(c_boxes.split(cnt_k)), list(c_scores.split(cnt_k)), list(c_cls.split(cnt_k))
-    ub_l, us_l = list(u_boxes.split(cnt_u)), list(u_scores.split(cnt_u))
-    uc_l = [torch.zeros(c, dtype=torch.int64, device=dev) for c in cnt_u]
-    keep_k = batched_nms_images(kb_l, ks_l, kc_l, known_nms_thresh, topk_per_image=known_topk)      # host read 3
-    keep_u = batched_nms_images(ub_l, us_l, uc_l, unknown_nms_thresh, topk_per_image=unknown_topk)  # host read 4
+    u_img = uimg.index_select(0, usel)
+    u_cls = torch.zeros(u_img.shape[0], dtype=torch.int64, device=dev)
+    gk, kk = batched_nms_flat(c_boxes, c_scores, c_cls, c_img, cnt_k, known_nms_thresh, topk_per_image=known_topk)        # host read 3
+    gu, ku = batched_nms_flat(u_boxes, u_scores, u_cls, u_img, cnt_u, unknown_nms_thresh, topk_per_image=unknown_topk)   # host read 4
+    # ---- result: per image the unknown detections first, then the known ones (:330-342).  Images without unknown
+    # FOREGROUND rows take the reference's known-only branch - the same tensors, since their unknown block is empty.
+    kcls = c_cls.index_select(0, gk)
+    if class_id is not None:
+        kcls = class_id[kcls]
+    all_boxes = torch.cat((u_boxes.index_select(0, gu), c_boxes.index_select(0, gk)))
+    all_scores = torch.cat((u_scores.index_select(0, gu), c_scores.index_select(0, gk)))
+    all_cls = torch.cat((torch.full((gu.shape[0],), int(unknown_id), dtype=torch.int64, device=dev), kcls))
+    ku_a, kk_a = np.asarray(ku, dtype=np.int64), np.asarray(kk, dtype=np.int64)
+    tot = ku_a + kk_a
+    u_first, k_first = np.cumsum(ku_a) - ku_a, int(ku_a.sum()) + np.cumsum(kk_a) - kk_a
+    out_first = np.cumsum(tot) - tot
+    within = np.arange(int(tot.sum()), dtype=np.int64) - np.repeat(out_first, tot)
+    ku_r = np.repeat(ku_a, tot)
+    perm = np.where(within < ku_r, np.repeat(u_first, tot) + within, np.repeat(k_first, tot) + within - ku_r)
+    perm = torch.from_numpy(perm).to(dev)
+    tot_l = tot.tolist()
+    ob = all_boxes.index_select(0, perm).split(tot_l)
+    osc = all_scores.index_select(0, perm).split(tot_l)
+    oc = all_cls.index_select(0, perm).split(tot_l)
     out = []
     for n, inst in enumerate(fg_instances):
         res = Instances(inst.image_size)
-        kcls = kc_l[n][keep_k[n]]
-        if class_id is not None:
-            kcls = class_id[kcls]
-        if n_unknown[n] > 0:   # `not known.all()` in the reference
-            ucls = (torch.zeros(len(keep_u[n]), device=dev) + unknown_id).long()
-            res.set("pred_boxes", Boxes(torch.cat([ub_l[n][keep_u[n]], kb_l[n][keep_k[n]]])))
-            res.set("scores", torch.cat([us_l[n][keep_u[n]], ks_l[n][keep_k[n]]]))
-            res.set("pred_classes", torch.cat([ucls, kcls]))
-        else:
-            res.set("pred_boxes", Boxes(kb_l[n][keep_k[n]]))
-            res.set("scores", ks_l[n][keep_k[n]])
-            res.set("pred_classes", kcls)
+        res.set("pred_boxes", Boxes(ob[n]))
+        res.set("scores", osc[n])
+        res.set("pred_classes", oc[n])
         out.append(res)
     return out

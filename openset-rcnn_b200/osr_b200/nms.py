@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .structures import Boxes, Instances
+from .structures import Boxes, Instances, flat_prefixes
 
 _MAX_SORT = 16384
 
@@ -126,6 +126,40 @@ def batched_nms_images(boxes_list: Sequence[torch.Tensor], scores_list: Sequence
     return out
 
 
+def batched_nms_flat(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, img: torch.Tensor,
+                     lens: Sequence[int], iou_threshold: float, topk_per_image: int = -1) -> Tuple[torch.Tensor, List[int]]:
+    """``batched_nms_images`` on CONCATENATED inputs: ``boxes`` (T, 4) / ``scores`` / ``idxs`` hold the images one after
+    the other (``lens[n]`` rows each, host-known), ``img`` (T,) int64 is the image of every row.  Returns the GLOBAL row
+    indices of the kept boxes - image-major, score-descending inside an image, first ``topk_per_image`` of each - and the
+    per-image counts.  No per-image launches: torchvision's coordinate trick needs every image's own ``boxes.max()``,
+    which is one ``scatter_reduce(amax)`` here (max is exact, so the fp32 offsets - and with them the IoU rounding - are
+    the ones ``[batched_nms(b, s, i, thr) for b, s, i in ...]`` computes); one host read (the keep counts)."""
+    n_img = len(lens)
+    dev = boxes.device
+    lens = [int(l) for l in lens]
+    begins, o = [], 0
+    for l in lens:
+        begins.append(o)
+        o += l
+    if n_img == 0 or o == 0:
+        return torch.empty((0,), dtype=torch.int64, device=dev), [0] * n_img
+    boxes = boxes.float()
+    if max(lens) > _MAX_SORT or max(lens) * 4 > 100_000:   # torchvision switches to its per-class loop: per-image calls
+        keeps = [batched_nms(boxes[b:b + l], scores[b:b + l], idxs[b:b + l], iou_threshold)[:topk_per_image if topk_per_image >= 0 else None] + b
+                 for b, l in zip(begins, lens)]
+        return torch.cat(keeps), [int(k.numel()) for k in keeps]
+    mx = torch.full((n_img,), float("-inf"), dtype=torch.float32, device=dev)
+    mx.scatter_reduce_(0, img, boxes.amax(dim=1), "amax", include_self=True)
+    off = idxs.to(boxes) * (mx.index_select(0, img) + torch.tensor(1).to(boxes))
+    allb = (boxes + off[:, None]).contiguous()
+    seg = torch.tensor([begins, lens], dtype=torch.int32).to(dev, non_blocking=True)
+    keep_idx, keep_cnt, _ = _segmented(allb, scores.float().contiguous(), seg[0], seg[1], max(lens), iou_threshold, False)
+    cnt = keep_cnt.cpu().tolist()  # one sync for the whole batch
+    ks = [c if topk_per_image < 0 else min(c, topk_per_image) for c in cnt[:n_img]]
+    P, B = flat_prefixes(begins, ks, dev)
+    return keep_idx.index_select(0, P) + B, ks
+
+
 def rpn_nominal_nms(sel, image_sizes, nms_thresh: float, post_nms_topk: int, training: bool) -> List[Instances]:
     """Stock detectron2 tail of ``find_top_rpn_proposals`` (``find_top_proposals.py:112-120``, commented out in
     the reference): ``keep = batched_nms(boxes, scores, lvl, thr)[:post_nms_topk]`` per image.
@@ -160,13 +194,17 @@ def rpn_nominal_nms(sel, image_sizes, nms_thresh: float, post_nms_topk: int, tra
     host = torch.stack((n_keep.to(torch.int32), sel.counts[:, L + 1])).cpu()   # the single host sync
     if training and bool((host[1] != 0).any()):
         raise FloatingPointError("Predicted boxes or scores contain Inf/NaN. Training has diverged.")
+    # all images' survivors in one gather per field; the per-image Instances are split views
+    ks = host[0].tolist()
+    P, B = flat_prefixes([n * kmax for n in range(N)], ks, dev)
+    flat = order.reshape(-1).index_select(0, P) + B
+    out_boxes = sel.boxes.reshape(-1, 4).index_select(0, flat).split(ks)
+    out_scores = sel.scores.reshape(-1).index_select(0, flat).split(ks)
     results = []
     for n, image_size in enumerate(image_sizes):
-        k = int(host[0, n])
-        idx = order[n, :k]
         res = Instances(tuple(image_size))
-        res.proposal_boxes = Boxes(sel.boxes[n].index_select(0, idx))
-        res.objectness_logits = sel.scores[n].index_select(0, idx)
+        res.proposal_boxes = Boxes(out_boxes[n])
+        res.objectness_logits = out_scores[n]
         results.append(res)
     return results
 

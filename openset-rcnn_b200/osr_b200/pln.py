@@ -20,7 +20,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import _lib
-from .structures import Instances
+from .structures import Instances, cat_rows
 
 
 DISTANCE_TYPES = {"COS": 0, "L1": 1, "L2": 2}   # include/osr.h OSR_PLN_DIST_*  (MODEL.PLN.DISTANCE_TYPE)
@@ -342,7 +342,7 @@ class PLN(nn.Module):
         if len(fg_instances) == 0:
             return []
         sizes = [len(x) for x in fg_instances]
-        feats = torch.cat([x.features for x in fg_instances], dim=0)
+        feats = cat_rows([x.features for x in fg_instances])   # no copy when the fields are split views of one tensor
         emb = self.encoder(feats)
         rec = self.decoder(emb)
         unknown_id = 80 if self.opendet_benchmark else 1000

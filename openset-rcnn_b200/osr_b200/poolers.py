@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import FeatLevel
-from .structures import Boxes
+from .structures import Boxes, cat_rows
 
 
 def _feat_levels(x: Sequence[torch.Tensor], scales: Sequence[float]):
@@ -41,7 +41,7 @@ def convert_boxes_to_pooler_format(box_lists: List[Boxes]) -> Tuple[torch.Tensor
     tensors = [b.tensor if hasattr(b, "tensor") else b for b in box_lists]
     sizes = [int(t.shape[0]) for t in tensors]
     dev = tensors[0].device
-    boxes = torch.cat(tensors, dim=0)
+    boxes = cat_rows(tensors)
     offs = [0]
     for s in sizes:
         offs.append(offs[-1] + s)

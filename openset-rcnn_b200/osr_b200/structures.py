@@ -140,3 +140,52 @@ except Exception:  # noqa: BLE001
         def __repr__(self) -> str:
             return "Instances(num_instances={}, image_size={}, fields=[{}])".format(
                 len(self) if len(self._fields) else 0, self._image_size, ", ".join(self._fields.keys()))
+
+
+def cat_rows(tensors) -> torch.Tensor:
+    """``torch.cat(tensors, dim=0)`` - without the copy when the tensors are CONSECUTIVE row slices of one buffer.
+
+    The batched stages of this package hand their per-image results out as ``torch.split`` views of one tensor
+    (``Instances`` fields of image n = rows ``[off[n], off[n+1])``); the next stage of the reference's loop structure
+    concatenates exactly those fields again (``PLN.inference``, ``SoftMaxClassifier.inference``, ``ROIPooler.forward``).
+    Recognising the views (same storage, contiguous rows, offsets that follow on) turns that 130 MB feature copy into
+    pointer arithmetic on the host; anything else falls through to ``torch.cat``."""
+    tensors = list(tensors)
+    if len(tensors) == 1:
+        return tensors[0]
+    t0 = tensors[0]
+    if t0.dim() >= 1 and not t0.requires_grad and t0.is_contiguous():
+        tail = t0.shape[1:]
+        row = 1
+        for d in tail:
+            row *= int(d)
+        base = t0.untyped_storage().data_ptr()
+        off = t0.storage_offset()
+        rows = 0
+        ok = row > 0
+        if ok:
+            for t in tensors:
+                if (t.dtype != t0.dtype or t.shape[1:] != tail or t.requires_grad or not t.is_contiguous()
+                        or t.device != t0.device or t.untyped_storage().data_ptr() != base
+                        or t.storage_offset() != off + rows * row):
+                    ok = False
+                    break
+                rows += int(t.shape[0])
+        if ok:
+            return t0.as_strided((rows,) + tuple(tail), t0.stride(), off)
+    return torch.cat(tensors, dim=0)
+
+
+def flat_prefixes(begins, counts, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Rows ``[begins[n], begins[n] + counts[n])`` of every segment n, concatenated: ``(positions, begin of the row's
+    segment)`` as int64 device tensors, built on the host from host-known counts (one small H2D copy) - the batched
+    replacement for a Python loop of per-image slices."""
+    import numpy as np
+    b = np.asarray(begins, dtype=np.int64)
+    c = np.asarray(counts, dtype=np.int64)
+    total = int(c.sum())
+    seg_first = np.cumsum(c) - c                       # output position of each segment's first row
+    within = np.arange(total, dtype=np.int64) - np.repeat(seg_first, c)
+    rep_b = np.repeat(b, c)
+    both = torch.from_numpy(np.stack((rep_b + within, rep_b))).to(device, non_blocking=False)
+    return both[0], both[1]

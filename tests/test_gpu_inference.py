@@ -106,3 +106,47 @@ def test_softmax_classifier_inference_matches_oracle(class_table):
         assert torch.equal(a.get("pred_boxes").tensor, b.get("pred_boxes").tensor)
         assert torch.equal(a.get("scores"), b.get("scores"))
         assert torch.equal(a.get("pred_classes"), b.get("pred_classes"))
+
+
+def test_chained_stages_on_split_views_equal_the_copying_path():
+    """inference -> PLN.inference -> SoftMaxClassifier.inference: the first stage hands out split views of its batched
+    gathers and the next stages recognise them (cat_rows, no copy).  The results must equal the run in which every
+    field is cloned in between (so that the stages take the torch.cat path)."""
+    from osr_b200.inference import inference, softmax_classifier_inference
+    from osr_b200.pln import PLN
+    from osr_b200.structures import Boxes, Instances, cat_rows
+    torch.manual_seed(3)
+    K = 20
+    ours_p, _, preds, _ = _inputs([400, 0, 250, 31], seed=9, bad=True)
+    R = 400 + 250 + 31
+    feats = torch.relu(torch.randn(R, 64, device=DEV))
+    pln = PLN(81, K, 64, 32, "COS", 1, 0.1, 0.9, 0.5, "synthetic", 0.5, 0.23, True, device=DEV).eval()
+    with torch.no_grad():
+        pln.representatives.copy_(pln.encoder(feats[:K * 7:7]))
+    cls = torch.nn.Linear(64, K + 1).to(DEV)
+    kw = dict(unknown_id=80, known_score_thresh=0.05, known_nms_thresh=0.5, known_topk=50, unknown_score_thresh=0.0,
+              unknown_nms_thresh=0.5, unknown_topk=50)
+
+    def cloned(insts, copy=True):   # PLN.inference writes its fields into the Instances it is given: hand it fresh ones
+        out = []
+        for x in insts:
+            y = Instances(x.image_size)
+            for k, v in x.get_fields().items():
+                if copy:
+                    v = Boxes(v.tensor.clone()) if hasattr(v, "tensor") else v.clone()
+                y.set(k, v)
+            out.append(y)
+        return out
+
+    with torch.no_grad():
+        fg, kept = inference(preds, ours_p, feats, score_thresh=0.05, nms_thresh=0.9, topk_per_image=300)
+        f_views = [x.get("features") for x in fg]
+        assert cat_rows(f_views).data_ptr() == f_views[0].data_ptr()      # the views really are recognised
+        a = softmax_classifier_inference(pln.inference(cloned(fg, copy=False)), cls, **kw)          # view path
+        b = softmax_classifier_inference(cloned(pln.inference(cloned(fg))), cls, **kw)              # torch.cat path
+    assert sum(len(x) for x in a) > 0
+    for x, y in zip(a, b):
+        assert len(x) == len(y)
+        assert torch.equal(x.get("pred_boxes").tensor, y.get("pred_boxes").tensor)
+        assert torch.equal(x.get("scores"), y.get("scores"))
+        assert torch.equal(x.get("pred_classes"), y.get("pred_classes"))

@@ -99,6 +99,30 @@ def test_batched_nms_images_one_call():
         assert torch.equal(g_, exp)
 
 
+@pytest.mark.parametrize("topk", [-1, 100])
+def test_batched_nms_flat_equals_the_per_image_calls(topk):
+    """Concatenated inputs, per-image coordinate trick from one scatter-max: global keep indices equal
+    [batched_nms(b, s, i, thr)[:topk] + first row of the image]."""
+    from osr_b200.nms import batched_nms_flat
+    bl, sl, il, lens = [], [], [], [500, 0, 1200, 37, 0]
+    for n, k in enumerate(lens):
+        b, s = _rand_boxes(k, seed=30 + n, spread=300.0 + 100.0 * n)
+        bl.append(b); sl.append(s)
+        il.append(torch.randint(0, 5, (k,), generator=torch.Generator().manual_seed(n)).cuda())
+    img = torch.repeat_interleave(torch.arange(len(lens)), torch.tensor(lens)).cuda()
+    keep, counts = batched_nms_flat(torch.cat(bl), torch.cat(sl), torch.cat(il), img, lens, 0.5, topk_per_image=topk)
+    exp, o = [], 0
+    for b, s, i in zip(bl, sl, il):
+        e = onms.batched_nms(b, s, i, 0.5) if len(b) else torch.empty(0, dtype=torch.int64, device="cuda:0")
+        exp.append((e[:topk] if topk >= 0 else e) + o)
+        o += len(b)
+    assert counts == [int(e.numel()) for e in exp]
+    assert torch.equal(keep, torch.cat(exp))
+    keep, counts = batched_nms_flat(torch.empty(0, 4).cuda(), torch.empty(0).cuda(), torch.empty(0, dtype=torch.int64).cuda(),
+                                    torch.empty(0, dtype=torch.int64).cuda(), [0, 0], 0.5)
+    assert keep.numel() == 0 and counts == [0, 0]
+
+
 @pytest.mark.parametrize("thr", [0.7, 1.0])
 def test_rpn_nominal_mode_matches_oracle_on_gpu(thr):
     """find_top_proposals.py:112-120 executed (stock detectron2): ours vs oracle run on the same GPU

@@ -80,3 +80,37 @@ def test_sample_labels_batched_contract():
     # a different generator state draws a different subset (it is a random sample, not a prefix)
     idx2, _ = sample_labels_batched(labels, valid, B, 0.25, 81, generator=g)
     assert not torch.equal(idx, idx2)
+
+
+def test_cat_rows_recognises_consecutive_views_and_falls_back_otherwise():
+    from osr_b200.structures import cat_rows
+    x = torch.arange(40.0).reshape(10, 4)
+    parts = list(x.split([3, 0, 5, 2]))
+    y = cat_rows(parts)
+    assert y.data_ptr() == x.data_ptr() and torch.equal(y, x)                     # all rows: the buffer itself
+    y = cat_rows(parts[1:])
+    assert y.data_ptr() == x[3:].data_ptr() and torch.equal(y, x[3:])             # a suffix, empty view in front
+    y = cat_rows([parts[0], parts[3]])                                            # rows missing in between: a real cat
+    assert y.data_ptr() != x.data_ptr() and torch.equal(y, torch.cat([parts[0], parts[3]]))
+    y = cat_rows([parts[2], parts[0]])                                            # wrong order
+    assert torch.equal(y, torch.cat([parts[2], parts[0]]))
+    y = cat_rows([x[:3], torch.empty(0, 4), x[3:]])                               # a foreign (empty) tensor
+    assert torch.equal(y, x)
+    y = cat_rows([x[:3].clone(), x[3:]])
+    assert torch.equal(y, x) and y.data_ptr() != x.data_ptr()
+    xt = x.t()                                                                    # non-contiguous views
+    assert torch.equal(cat_rows([xt[:2], xt[2:]]), xt)
+    z = torch.arange(10)
+    assert torch.equal(cat_rows(list(z.split([4, 6]))), z)                        # 1-D fields (scores, classes)
+    w = x.clone().requires_grad_()
+    y = cat_rows([w[:3], w[3:]])                                                  # autograd inputs are never aliased
+    assert y.requires_grad and y.data_ptr() != w.data_ptr()
+    assert cat_rows([x]) is x
+
+
+def test_flat_prefixes_lists_the_first_rows_of_every_segment():
+    from osr_b200.structures import flat_prefixes
+    P, B = flat_prefixes([0, 10, 20, 30], [2, 0, 3, 1], "cpu")
+    assert P.tolist() == [0, 1, 20, 21, 22, 30] and B.tolist() == [0, 0, 20, 20, 20, 30]
+    P, B = flat_prefixes([0, 5], [0, 0], "cpu")
+    assert P.numel() == 0 and B.numel() == 0 and P.dtype == torch.int64
