@@ -121,6 +121,8 @@ size_t osr_nms_workspace(int64_t total_boxes, int num_segments, int max_segment_
  *                         RELATIVE to seg_begin[s], in score-descending (stable: ties by lower index) order
  *   keep_counts (S) int32
  *   keep_mask  (T) uint8 or NULL: 1 for kept boxes (indexed like boxes), 0 for suppressed ones inside segments
+ *   iou_threshold >= 1 (the reference's shipped TEST thresholds): this arithmetic never yields an IoU above 1.0f, so
+ *       nothing is suppressed and the call reduces to the stable sort (no mask, no sweep) - same result, bit for bit
  */
 int osr_nms_segmented(const float* boxes, const float* scores, int64_t total_boxes, const int32_t* seg_begin,
                       const int32_t* seg_len, int num_segments, int max_segment_len, float iou_threshold,

@@ -100,14 +100,18 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const __grid_constant__ Nm
     const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     unsigned long long t = 0;
     const int start = (row_start == col_start) ? tid + 1 : 0;
+    const bool neg_thr = !(p.thr >= 0.f);
     for (int i = start; i < col_size; ++i) {
       const float4 b = cb[i];
       const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
       const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
       const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
       const float inter = __fmul_rn(w, h);
-      const float uni = __fsub_rn(__fmaf_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y), sa), inter);
-      if (__fdiv_rn(inter, uni) > p.thr) t |= 1ull << i;
+      // disjoint boxes (inter == 0: most pairs): 0 / uni is +-0 or NaN, never above a threshold >= 0 - skip the IEEE division
+      if (inter > 0.f || neg_thr) {
+        const float uni = __fsub_rn(__fmaf_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y), sa), inter);
+        if (__fdiv_rn(inter, uni) > p.thr) t |= 1ull << i;
+      }
     }
     p.mask[((int64_t)s * p.max_len + row) * p.wpr + col_start] = t;
   }
@@ -184,6 +188,21 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep_kernel(const __grid_c
   if (tid == 0) p.keep_counts[s] = s_count;
 }
 
+// iou_threshold >= 1 (the reference's shipped TEST.NMS thresholds, osrcnn_fast_rcnn.py:135 with test_nms_thresh = 1.0):
+// the kernel's IoU can not exceed 1.0f - w <= min(aw, bw) and h <= min(ah, bh) after monotonic rounding, so
+// inter = rn(w h) <= rn(aw ah) and rn(bw bh + rn(aw ah)) >= 2 inter (ties go to the even 2 inter), hence uni >= inter -
+// and `iou > thr` never holds (nor for NaN / degenerate boxes: 0 / x and NaN compare false).  Greedy NMS then keeps every
+// box: the result is the sorted order itself, no mask, no sweep.
+__global__ void __launch_bounds__(256) nms_keep_all_kernel(const __grid_constant__ NmsParams p) {
+  const int s = blockIdx.x;
+  const int begin = p.seg_begin[s], len = min(p.seg_len[s], p.max_len);
+  for (int i = threadIdx.x; i < len; i += 256) {
+    p.keep_idx[begin + i] = p.presorted ? (int64_t)i : (int64_t)p.order[begin + i];
+    if (p.keep_mask) p.keep_mask[begin + i] = 1;
+  }
+  if (threadIdx.x == 0) p.keep_counts[s] = len;
+}
+
 size_t ws_layout(int64_t T, int S, int max_len, size_t* off_sorted, size_t* off_order, size_t* off_mask) {
   const int wpr = (max_len + 63) / 64;
   size_t o = 0;
@@ -239,6 +258,11 @@ int osr_nms_segmented(const float* boxes, const float* scores, int64_t total_box
     OSR_CUDA_CHECK(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_sort_kernel<<<num_segments, kSortThreads, smem, st>>>(p);
     OSR_LAUNCH_CHECK();
+  }
+  if (!(iou_threshold < 1.0f)) {   // nothing can be suppressed (see nms_keep_all_kernel): sorted order = keep list
+    nms_keep_all_kernel<<<num_segments, 256, 0, st>>>(p);
+    OSR_LAUNCH_CHECK();
+    return 0;
   }
   const int nb = (p.max_len + 63) / 64;
   nms_mask_kernel<<<dim3(nb, nb, num_segments), 64, 0, st>>>(p);
