@@ -51,9 +51,11 @@ void osr_reset_launch_count(void);
  *                          | 5 one footprint row per row-loop iteration (round-1 loop; the default folds two)
  *   OSR_TUNE_PLN_VARIANT   0 encoder GEMM on fp32 operands (tcgen05 kind::tf32, no cast pass; shipped) | 1 bf16 copies (kind::f16)
  *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu
- *   OSR_TUNE_BWD_SPLIT     0 one CTA per 16x16 tile of the ROIAlign backward (shipped) | > 0: one hex digit per level
- *                          (finest first) = log2 of the CTAs per tile (slab groups first, then sub-tile groups; measured
- *                          slower, csrc/roi_align_bwd.cu fill_bwd) */
+ *   OSR_TUNE_BWD_SPLIT     0 shipped: for batches of <= 12 images the two coarsest levels launch two CTAs per 16x16 tile of
+ *                          the ROIAlign backward (one 128-channel slab each) that only share DENSE tiles (>= 30 RoIs; the
+ *                          sibling leaves a sparse tile after the RoI scan), larger batches one CTA per tile | -1 one CTA
+ *                          per tile | > 0: hex digit l (finest level first) = log2 of level l's CTAs per tile, bits 20-27 =
+ *                          dense-tile threshold in RoIs, 0 = static split (measurements: csrc/roi_align_bwd.cu fill_bwd) */
 #define OSR_TUNE_BWD_VARIANT 0
 #define OSR_TUNE_FWD_VARIANT 1
 #define OSR_TUNE_PLN_VARIANT 2

@@ -72,6 +72,7 @@ struct BwdParams {
   // (coarse levels hold few, heavily covered tiles: one CTA per tile made them the critical path of the launch)
   int clr_cta_base[OSR_MAX_LEVELS + 1];
   int clr_ps[OSR_MAX_LEVELS], clr_pt[OSR_MAX_LEVELS];
+  int clr_dyn_min;   // > 0: a tile is only worked by several CTAs when its first batch holds at least this many RoIs
 };
 
 // one bin of one axis: visit its valid samples as (low row, high row, weight at low, weight at high) - the sample
@@ -1098,8 +1099,8 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.L.C;
   const int nslab = ceil_div(C, kCWarps * 32);
-  const int slab0 = (part % ps) * nslab / ps, slab1 = ((part % ps) + 1) * nslab / ps;     // my slabs
-  const int st0 = (part / ps) * (kCS / pt), st1 = st0 + kCS / pt;                         // my sub-tiles
+  int slab0 = (part % ps) * nslab / ps, slab1 = ((part % ps) + 1) * nslab / ps;     // my slabs
+  int st0 = (part / ps) * (kCS / pt), st1 = st0 + kCS / pt;                         // my sub-tiles
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   float* const sg = S.sg[warp][0];               // buffer b at sg + b * kGBlk
   unsigned long long* const bar = S.mbar[warp];  // barrier b at bar + b
@@ -1125,6 +1126,13 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   while (true) {
     cl_collect(p, S, level, tx0, ty0, pos, r1);
     const int nb = S.nb, next = S.next_pos;
+    if (first && ps * pt > 1 && p.clr_dyn_min > 0 && nb < p.clr_dyn_min) {
+      // dynamic split: only DENSE tiles (RoIs clustered on a ground-truth box: 100+ RoIs on one coarse-level tile are
+      // one warp's 0.3 ms serial chain) are shared by the tile's CTAs; on every other tile CTA 0 does all the work and
+      // its siblings leave after this one scan (block-uniform: nb is shared)
+      if (part != 0) return;
+      slab0 = 0; slab1 = nslab; st0 = 0; st1 = kCS;
+    }
     if (nb > 0) {
       cl_build_tables(p, S, lv, tx0, ty0);   // (uses the staging buffers as scratch: generic-proxy accesses ...)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // ... ordered before the bulk copies that refill them
@@ -1308,16 +1316,35 @@ int fill_bwd(BwdParams& p, const osr_feat_level_t* h_levels, int num_levels, int
     base += p.cl_tiles_x[l] * p.cl_tiles_y[l] * num_images;
   }
   p.cl_tile_base[num_levels] = base;
-  // CTAs per tile of the register-accumulator kernel: ONE (shipped).  OSR_TUNE_BWD_SPLIT (A/B only): one hex digit per level
-  // (digit l = level l, finest first) = log2 of the tile's CTA count.  Measured at cfg 2 with the sampler's clustered RoIs
-  // (the coarse levels' 16x16 tiles collect 60 - 260 (sub-tile, RoI) pairs each): every split is SLOWER - 0x2110 0.607 ms,
-  // 0x3310 0.662 ms against 0.583 ms - each extra CTA repeats the tile's RoI scan and table build for all its batches, and
-  // the heavy tiles are not the launch's critical path (they start first and finish inside the launch).
+  // CTAs per tile of the register-accumulator kernel.  The labelled sampler clusters RoIs on the ground-truth boxes, and a
+  // coarse-level 16x16 tile (a quarter of the image on P5) then collects 100+ RoIs: one CTA's serial chain of 0.2 - 0.35 ms,
+  // which IS the launch time when the batch is small (measured, backward only: 8 images 0.43 ms, 1 image 0.36 ms) - the
+  // chain's length follows the RoIs per image, the launch's total work the RoIs per batch.  Shipped for batches of up to 12
+  // images: the two coarsest levels launch TWO CTAs per tile (one 128-channel slab each - no pixel is visited twice) and the
+  // split is DYNAMIC: the siblings only share a tile whose first batch is full (>= 30 RoIs); everywhere else CTA 0 does all
+  // the work and its sibling leaves after the RoI scan.  cfg 2 shapes, backward ms, one CTA -> two: 12 images 0.488 -> 0.468,
+  // 8: 0.430 -> 0.326, 4: 0.366 -> 0.248, 1: 0.356 -> 0.255; cfg 3 (8 images) step 0.766 -> 0.685 ms.  At 16 images the dense
+  // tiles start first and finish inside the launch, and the siblings' repeated scan / table builds only cost (bench cfg 2:
+  // 0.584 -> 0.611, cfg 5: 1.081 -> 1.137), so larger batches keep one CTA per tile.  Every STATIC split (all tiles of a
+  // level, up to 8 CTAs) was slower at 16 images too (0x2110 0.607, 0x3310 0.662 against 0.583).
+  // OSR_TUNE_BWD_SPLIT (A/B): -1 = one CTA per tile; > 0: hex digit l (finest level first) = log2 of level l's CTAs per tile
+  // (slabs first, then sub-tile groups), bits 20-27 = the dynamic threshold in RoIs (0 = static split).
   const int nslab = osr::ceil_div(C, kCWarps * 32);
-  const int code = osr::tuning(osr::kTuneBwdSplit);
+  int code = osr::tuning(osr::kTuneBwdSplit);
+  if (code == 0 && num_images <= 12) {
+    code = 30 << 20;
+    int c0 = -1, c1 = -1;   // the two coarsest levels (smallest scale), whatever order the caller lists them in
+    for (int l = 0; l < num_levels && l < 5; ++l) {
+      if (c0 < 0 || p.L.lv[l].scale < p.L.lv[c0].scale) { c1 = c0; c0 = l; }
+      else if (c1 < 0 || p.L.lv[l].scale < p.L.lv[c1].scale) c1 = l;
+    }
+    if (c0 >= 0) code |= 1 << (4 * c0);
+    if (c1 >= 0) code |= 1 << (4 * c1);
+  }
+  p.clr_dyn_min = code > 0 ? ((code >> 20) & 0xff) : 0;
   base = 0;
   for (int l = 0; l < num_levels; ++l) {
-    int lg = code > 0 ? ((code >> (4 * l)) & 0xf) : 0;
+    int lg = (code > 0 && l < 5) ? ((code >> (4 * l)) & 0xf) : 0;
     int ps = 1, pt = 1;
     while (lg > 0 && ps * 2 <= nslab && nslab % (ps * 2) == 0 && ps < 2) { ps *= 2; --lg; }   // slabs first: no table work is repeated for pixels a CTA does not own
     while (lg > 0 && pt * 2 <= kCS) { pt *= 2; --lg; }

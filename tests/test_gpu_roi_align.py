@@ -415,3 +415,39 @@ def test_backward_prepare_then_prepared_equals_one_call(channels_last):
     got = ours.backward_rois(gout, feats, packed, offsets, prepared=ws)
     for a, b in zip(got, ref):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C", [256, 128])
+def test_backward_dense_tiles_shared_by_two_ctas_equal_one_cta_per_tile(C):
+    """RoIs clustered on a few boxes (what the labelled sampler produces): the coarse levels' dense tiles are worked by
+    two CTAs (dynamic split, shipped); every other setting of OSR_TUNE_BWD_SPLIT - one CTA per tile, static splits, a
+    threshold of one RoI - must give the same gradient bit for bit (each (pixel, channel) is summed by exactly one warp in
+    RoI order whichever CTA owns it), and it must match torchvision."""
+    from osr_b200 import _lib, synth
+    ours, ref = _pooler_pair()
+    hw = (512, 640)
+    feats = synth.make_features(2, hw, C, seed=29, device="cuda:0", channels_last=True)
+    g = torch.Generator().manual_seed(11)
+    rois = []
+    for n in range(2):
+        ctr = torch.tensor([[200.0, 180.0], [420.0, 330.0]])[torch.randint(0, 2, (300,), generator=g)]
+        size = torch.tensor([[360.0, 300.0], [90.0, 120.0]])[torch.randint(0, 2, (300,), generator=g)]
+        c = ctr + torch.randn(300, 2, generator=g) * 12
+        wh = size * (1 + 0.2 * torch.rand(300, 2, generator=g))
+        b = torch.cat([c - wh / 2, c + wh / 2], dim=1)
+        b[:, 0::2].clamp_(0, hw[1]); b[:, 1::2].clamp_(0, hw[0])
+        rois.append(b)
+    boxes = [OBoxes(r.cuda()) for r in rois]
+    gout = torch.randn(600, C, 7, 7, device="cuda:0")
+    base = _grads(ours, feats, boxes, gout)            # shipped: dynamic two-CTA split on the two coarsest levels
+    for code in (-1, 0x2211, 0x0102211, 0x1E03320):
+        prev = _lib.set_tuning("bwd_split", code)
+        try:
+            other = _grads(ours, feats, boxes, gout)
+        finally:
+            _lib.set_tuning("bwd_split", prev)
+        for a, b in zip(base, other):
+            assert torch.equal(a, b), hex(code & 0xffffffff)
+    for a, b in zip(base, _grads(ref, feats, boxes, gout)):
+        scale = max(1.0, float(b.abs().max()))
+        torch.testing.assert_close(a, b, rtol=BWD_RTOL, atol=BWD_ATOL * scale)
