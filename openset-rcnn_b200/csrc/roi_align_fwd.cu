@@ -44,6 +44,7 @@ struct FwdParams {
   int tma_ok[OSR_MAX_LEVELS];  // level's map satisfies the TMA rules AND the TMA path is enabled for this call
   int ring_floats;             // floats of the staging ring at the start of dynamic shared memory
   int two_rows;                // NHWC kernel: 2 footprint rows per row-loop iteration
+  int max_stages;              // NHWC kernel: most row stages the ring is cut into (<= kNhwcMaxStages)
   int* counter;                // persistent NHWC kernel: next unclaimed record (set to the grid size by roi_fwd_prep_kernel)
   int pers_grid;               // grid size of the persistent NHWC kernel (0: not used)
 };
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, OSR_FWD_MINB) roi_align_fwd_kernel(c
 // The per-RoI tables come from roi_fwd_prep_kernel's records in the common case (in-CTA derivation otherwise).
 // The 49 x C tile is transposed through shared memory and stored with 16-byte coalesced writes (C-major output).
 constexpr int kNhwcRingCols = 96;   // ring capacity in pixel columns (x C floats); split per RoI into 2..6 row stages
-constexpr int kNhwcMaxStages = 6;
+constexpr int kNhwcMaxStages = 12;
 constexpr int kNhwcWide = 48;       // widest footprint staged as whole rows; wider ones go in 32-column chunks
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -796,7 +797,7 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       const int scols_e = wf <= kNhwcWide ? max(8, (wf + 3) & ~3) : 32;
-      const int nst_e = min(kNhwcMaxStages, kNhwcRingCols / scols_e);
+      const int nst_e = min(p.max_stages, kNhwcRingCols / scols_e);
       const int total_e = ceil_div(wf, scols_e) * hf;
       for (int t = 0; t < min(nst_e, total_e); ++t) {
         const int xc = t / hf, r = t - xc * hf;
@@ -949,7 +950,7 @@ __device__ __forceinline__ void nhwc_roi(const FwdParams& p, int j, float* ring,
   // stage geometry: a stage holds one footprint row (chunk).  Narrow RoIs get more, smaller stages (deeper prefetch),
   // RoIs up to 48 pixels wide are still staged as whole rows, wider ones in 32-column chunks.
   const int scols = wf <= kNhwcWide ? max(8, (wf + 3) & ~3) : 32;   // >= 8: every (padded) tap stays inside its own stage
-  const int nstages = min(kNhwcMaxStages, kNhwcRingCols / scols);
+  const int nstages = min(p.max_stages, kNhwcRingCols / scols);
   const int stage_floats = scols * C;
   const int nxc = ceil_div(wf, scols);
   const int total = nxc * hf;          // (x chunk, row) tiles, chunk-major
@@ -1368,7 +1369,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
     const LevelDesc& lv = p.L.lv[level];
     const float* img_base = lv.data + (int64_t)img * lv.sN + ((int64_t)ymin * lv.sH + (int64_t)xmin * lv.sW);
     const int scols = max(8, (wf + 3) & ~3);   // FAST records are at most 48 columns wide: a stage is one whole footprint row
-    const int nstages = min(kNhwcMaxStages, kNhwcRingCols / scols);
+    const int nstages = min(p.max_stages, kNhwcRingCols / scols);
     const int stage_floats = scols * C;
     const uint32_t row_bytes = (uint32_t)(wf * C * 4);
     const int total = hf;
@@ -1478,7 +1479,7 @@ __global__ void __launch_bounds__(kThreads, 2) roi_align_fwd_nhwc_pers_kernel(co
         if (g0.x & 1) {
           const int wfn = g0.w & 0xffff, hfn = g0.w >> 16;
           const int scn = max(8, (wfn + 3) & ~3);
-          const int ne = min(min(min(kNhwcMaxStages, kNhwcRingCols / scn), hfn), fit_cols / scn);
+          const int ne = min(min(min(p.max_stages, kNhwcRingCols / scn), hfn), fit_cols / scn);
           const LevelDesc& ln = p.L.lv[g0.x >> 8];
           const float* nbase = ln.data + (int64_t)__float_as_int(rn[6]) * ln.sN + ((int64_t)g0.z * ln.sH + (int64_t)g0.y * ln.sW);
           const uint32_t nbytes = (uint32_t)(wfn * C * 4);
@@ -1674,6 +1675,7 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
   FwdParams p;
   p.counter = nullptr;
   p.pers_grid = 0;
+  p.max_stages = osr::tuning(osr::kTuneFwdVariant) == 6 ? 6 : kNhwcMaxStages;   // 6: at most 6 stages (A/B)
   p.two_rows = osr::tuning(osr::kTuneFwdVariant) == 5 ? 0 : 1;   // 5: one row per iteration (A/B: 0.506 vs 0.471 ms at cfg 2)
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);
