@@ -49,6 +49,7 @@ void osr_reset_launch_count(void);
  *                          with one staging buffer | 2 shared-memory accumulators (round-1 kernel) | 3 pixel-per-thread kernel
  *   OSR_TUNE_FWD_VARIANT   0 default | 1 opt-in TMA-tiled NCHW kernel | 2 no prep records | 4 persistent channels_last kernel
  *                          | 5 one footprint row per row-loop iteration (round-1 loop; the default folds two)
+ *                          | 6 ring cut into up to 12 row stages for narrow footprints (default 6; measured 0.5 % slower)
  *   OSR_TUNE_PLN_VARIANT   0 encoder GEMM on fp32 operands (tcgen05 kind::tf32, no cast pass; shipped) | 1 bf16 copies (kind::f16)
  *   OSR_TUNE_RPN_VARIANT   0 default | see csrc/rpn_select_decode.cu
  *   OSR_TUNE_BWD_SPLIT     0 shipped: for batches of <= 12 images the two coarsest levels launch two CTAs per 16x16 tile of

@@ -1079,7 +1079,8 @@ __device__ __forceinline__ void clr_wait_bulk(unsigned long long* bar, unsigned 
 
 // kSW > 0: compile-time pixel stride of the gradient maps in floats (= C for dense channels_last); 0: run time.  kMinB: CTAs / SM
 // the register allocation targets.  kNBuf: staging buffers per warp (RegSmemT), kInfo: footprint records kept in shared memory.
-template <int kSW, int kMinB, int kNBuf, bool kInfo>
+// kDyn: tiles are shared by several CTAs only when dense (p.clr_dyn_min; fill_bwd).
+template <int kSW, int kMinB, int kNBuf, bool kInfo, bool kDyn>
 __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = RegSmemT<kNBuf, kInfo>;
@@ -1099,8 +1100,8 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.L.C;
   const int nslab = ceil_div(C, kCWarps * 32);
-  int slab0 = (part % ps) * nslab / ps, slab1 = ((part % ps) + 1) * nslab / ps;     // my slabs
-  int st0 = (part / ps) * (kCS / pt), st1 = st0 + kCS / pt;                         // my sub-tiles
+  int slab0 = (part % ps) * nslab / ps, slab1 = ((part % ps) + 1) * nslab / ps;     // my slabs     (only ever changed
+  int st0 = (part / ps) * (kCS / pt), st1 = st0 + kCS / pt;                         // my sub-tiles  when kDyn)
   const int r0 = p.roi_off[n], r1 = p.roi_off[n + 1];
   float* const sg = S.sg[warp][0];               // buffer b at sg + b * kGBlk
   unsigned long long* const bar = S.mbar[warp];  // barrier b at bar + b
@@ -1126,12 +1127,16 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   while (true) {
     cl_collect(p, S, level, tx0, ty0, pos, r1);
     const int nb = S.nb, next = S.next_pos;
-    if (first && ps * pt > 1 && p.clr_dyn_min > 0 && nb < p.clr_dyn_min) {
-      // dynamic split: only DENSE tiles (RoIs clustered on a ground-truth box: 100+ RoIs on one coarse-level tile are
-      // one warp's 0.3 ms serial chain) are shared by the tile's CTAs; on every other tile CTA 0 does all the work and
-      // its siblings leave after this one scan (block-uniform: nb is shared)
-      if (part != 0) return;
-      slab0 = 0; slab1 = nslab; st0 = 0; st1 = kCS;
+    if constexpr (kDyn) {
+      // dynamic split: only DENSE tiles (RoIs clustered on a ground-truth box: 100+ RoIs on one coarse-level tile are one
+      // warp's 0.3 ms serial chain) are shared by the tile's CTAs; on every other tile CTA 0 does all the work and its
+      // siblings leave after this one scan (block-uniform: nb is shared).  A separate instantiation: the same lines as
+      // run-time code in the one-CTA-per-tile kernel cost it 4 - 6 % (0.582 -> 0.606 / 0.616 ms at cfg 2: register
+      // allocation and code size of a kernel that is instruction-fetch sensitive).
+      if (first && nb < p.clr_dyn_min) {
+        if (part != 0) return;
+        slab0 = 0; slab1 = nslab; st0 = 0; st1 = kCS;
+      }
     }
     if (nb > 0) {
       cl_build_tables(p, S, lv, tx0, ty0);   // (uses the staging buffers as scratch: generic-proxy accesses ...)
@@ -1280,17 +1285,17 @@ __global__ void __launch_bounds__(kCThreads, kMinB) roi_align_bwd_clr_kernel(con
   }
 }
 
-template <int kNBuf, bool kInfo>
+template <int kNBuf, bool kInfo, bool kDyn>
 int launch_clr(const BwdParams& p, dim3 grid, bool sw256, cudaStream_t s) {
   const size_t smem = sizeof(RegSmemT<kNBuf, kInfo>);
   if (sw256) {
-    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (kNBuf == 2) OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo><<<grid, kCThreads, smem, s>>>(p);
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo, kDyn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kNBuf == 2) OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo, kDyn>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    roi_align_bwd_clr_kernel<256, 3, kNBuf, kInfo, kDyn><<<grid, kCThreads, smem, s>>>(p);
   } else {
-    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (kNBuf == 2) OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo><<<grid, kCThreads, smem, s>>>(p);
+    OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo, kDyn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (kNBuf == 2) OSR_CUDA_CHECK(cudaFuncSetAttribute(roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo, kDyn>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    roi_align_bwd_clr_kernel<0, 3, kNBuf, kInfo, kDyn><<<grid, kCThreads, smem, s>>>(p);
   }
   return 0;
 }
@@ -1410,8 +1415,9 @@ static int roi_align_bwd_impl(int mode, const osr_feat_level_t* h_grad_levels, i
       for (int l = 0; l < num_levels; ++l) sw256 = sw256 && (p.L.lv[l].sW == 256);
       // 0 (shipped): two staging buffers per warp - the next pair's block is requested a whole pair ahead - and the footprint
       // records kept in shared memory by the scan (cfg 2: 0.570 -> 0.562 ms) | 1: one buffer, refilled behind the fold
-      if (variant == 1) rc = launch_clr<1, false>(p, grid, sw256, s);
-      else rc = launch_clr<2, true>(p, grid, sw256, s);
+      const bool dyn = p.clr_dyn_min > 0;
+      if (variant == 1) rc = dyn ? launch_clr<1, false, true>(p, grid, sw256, s) : launch_clr<1, false, false>(p, grid, sw256, s);
+      else rc = dyn ? launch_clr<2, true, true>(p, grid, sw256, s) : launch_clr<2, true, false>(p, grid, sw256, s);
       if (rc) return rc;
     }
     OSR_LAUNCH_CHECK();

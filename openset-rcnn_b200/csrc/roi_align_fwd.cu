@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, OSR_FWD_MINB) roi_align_fwd_kernel(c
 //   then     out[ph][pw] += Wy[ph][y] * U[pw]      for the <= 3 bins containing the row (uniform switch).
 // The per-RoI tables come from roi_fwd_prep_kernel's records in the common case (in-CTA derivation otherwise).
 // The 49 x C tile is transposed through shared memory and stored with 16-byte coalesced writes (C-major output).
-constexpr int kNhwcRingCols = 96;   // ring capacity in pixel columns (x C floats); split per RoI into 2..6 row stages
+constexpr int kNhwcRingCols = 96;   // ring capacity in pixel columns (x C floats); split per RoI into 2..6 row stages (p.max_stages)
 constexpr int kNhwcMaxStages = 12;
 constexpr int kNhwcWide = 48;       // widest footprint staged as whole rows; wider ones go in 32-column chunks
 
@@ -1675,7 +1675,9 @@ static int roi_align_fwd_impl(const osr_feat_level_t* h_levels, int num_levels, 
   FwdParams p;
   p.counter = nullptr;
   p.pers_grid = 0;
-  p.max_stages = osr::tuning(osr::kTuneFwdVariant) == 6 ? 6 : kNhwcMaxStages;   // 6: at most 6 stages (A/B)
+  // ring cut into at most 6 row stages (shipped); 6: up to 12 for narrow footprints - measured 0.5 % SLOWER (0.468 vs 0.4657 ms
+  // against the 6-stage build on the same box): the rows in flight are not what bounds narrow RoIs
+  p.max_stages = osr::tuning(osr::kTuneFwdVariant) == 6 ? kNhwcMaxStages : 6;
   p.two_rows = osr::tuning(osr::kTuneFwdVariant) == 5 ? 0 : 1;   // 5: one row per iteration (A/B: 0.506 vs 0.471 ms at cfg 2)
   int rc = osr::fill_roi_levels(p.L, h_levels, num_levels, num_images, C, P, sampling_ratio, aligned,
                                 canonical_box_size, canonical_level, min_level);
