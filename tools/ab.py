@@ -45,8 +45,9 @@ def main():
     ap.add_argument("--nchw", action="store_true")
     ap.add_argument("--topk", type=int, default=2000)
     ap.add_argument("--rois", type=int, default=512)
+    ap.add_argument("--seed", type=int, default=3234)
     a = ap.parse_args()
-    path = RoiPathStep(PathConfig(num_images=a.images, channels_last=not a.nchw, seed=3234, pre_nms_topk=a.topk,
+    path = RoiPathStep(PathConfig(num_images=a.images, channels_last=not a.nchw, seed=a.seed, pre_nms_topk=a.topk,
                                   rois_per_image=a.rois), "cuda:0")
     print(json.dumps({"setting": "defaults", **time_steps(path, a.steps)}), flush=True)
     for sw in a.sweeps:
