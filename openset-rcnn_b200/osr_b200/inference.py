@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from .nms import _MAX_SORT, _segmented
-from .structures import Boxes, Instances, cat_rows, flat_prefixes
+from .structures import Boxes, Instances, boxes_view, cat_rows, flat_prefixes, make_instances
 
 SCALE_CLAMP = math.log(1000.0 / 16)
 
@@ -111,12 +111,8 @@ def inference(predictions: Tuple[torch.Tensor, torch.Tensor], proposals: List[In
     out_kept = kept_all.split(ks)
     results, kept = [], []
     for n, p in enumerate(proposals):
-        r = Instances(p.image_size)
-        r.set("pred_boxes", Boxes(out_boxes[n]))
-        r.set("scores", out_scores[n])
-        r.set("pred_classes", out_cls[n])
-        r.set("features", out_feats[n])
-        results.append(r)
+        results.append(make_instances(p.image_size, pred_boxes=boxes_view(out_boxes[n]), scores=out_scores[n],
+                                      pred_classes=out_cls[n], features=out_feats[n]))
         kept.append(out_kept[n])
     return results, kept
 
@@ -231,9 +227,5 @@ def softmax_classifier_inference(fg_instances: List[Instances], cls_score, *, un
     oc = all_cls.index_select(0, perm).split(tot_l)
     out = []
     for n, inst in enumerate(fg_instances):
-        res = Instances(inst.image_size)
-        res.set("pred_boxes", Boxes(ob[n]))
-        res.set("scores", osc[n])
-        res.set("pred_classes", oc[n])
-        out.append(res)
+        out.append(make_instances(inst.image_size, pred_boxes=boxes_view(ob[n]), scores=osc[n], pred_classes=oc[n]))
     return out

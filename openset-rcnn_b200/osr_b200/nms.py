@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .structures import Boxes, Instances, flat_prefixes
+from .structures import Boxes, Instances, boxes_view, flat_prefixes, make_instances
 
 _MAX_SORT = 16384
 
@@ -202,10 +202,7 @@ def rpn_nominal_nms(sel, image_sizes, nms_thresh: float, post_nms_topk: int, tra
     out_scores = sel.scores.reshape(-1).index_select(0, flat).split(ks)
     results = []
     for n, image_size in enumerate(image_sizes):
-        res = Instances(tuple(image_size))
-        res.proposal_boxes = Boxes(out_boxes[n])
-        res.objectness_logits = out_scores[n]
-        results.append(res)
+        results.append(make_instances(tuple(image_size), proposal_boxes=boxes_view(out_boxes[n]), objectness_logits=out_scores[n]))
     return results
 
 

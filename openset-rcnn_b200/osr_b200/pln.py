@@ -350,12 +350,12 @@ class PLN(nn.Module):
                               reps_per_class=self.reps_per_class, unk_thr=self.unk_thr, unknown_id=unknown_id,
                               class_id=None if self.opendet_benchmark else self.class_id,
                               distance_type=self.distance_type)
-        results, o = [], 0
-        for inst, s in zip(fg_instances, sizes):
-            inst.features = rec[o:o + s]
-            inst.pred_classes = pred[o:o + s]
+        results = []
+        rec_l, pred_l = rec.split(sizes), pred.split(sizes)
+        for n, inst in enumerate(fg_instances):
+            inst._fields["features"] = rec_l[n]        # same lengths by construction: the per-field assert of set() skipped
+            inst._fields["pred_classes"] = pred_l[n]
             results.append(inst)
-            o += s
         return results
 
     def encode(self, roi_features):

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import RpnLevel
-from .structures import Boxes, Instances
+from .structures import Boxes, Instances, boxes_view, make_instances
 
 
 @dataclass
@@ -117,11 +117,9 @@ def _to_instances(sel: RpnSelection, image_sizes, training: bool, keep=None, kee
     totals = counts[:, L].tolist()
     results = []
     for n, image_size in enumerate(image_sizes):
-        res = Instances(tuple(image_size))
         c = totals[n]
-        res.proposal_boxes = Boxes(sel.boxes[n, :c])
-        res.objectness_logits = sel.scores[n, :c]
-        results.append(res)
+        results.append(make_instances(tuple(image_size), proposal_boxes=boxes_view(sel.boxes[n, :c]),
+                                      objectness_logits=sel.scores[n, :c]))
     return results
 
 

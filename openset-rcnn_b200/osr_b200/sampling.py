@@ -19,7 +19,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .structures import Boxes, Instances
+from .structures import Boxes, Instances, boxes_view, make_instances
 
 GT_LOGIT = math.log((1.0 - 1e-10) / (1e-10))
 
@@ -274,24 +274,22 @@ def _finish_batched(proposals, targets, boxes, logits, counts, offs, off, goff, 
     out = []
     for n, (p, t) in enumerate(zip(proposals, targets)):
         k = n_s[n]
-        q = Instances(p.image_size)
-        q.set("proposal_boxes", Boxes(sb[n, :k]))
-        q.set("objectness_logits", sl[n, :k])
+        f = {"proposal_boxes": boxes_view(sb[n, :k]), "objectness_logits": sl[n, :k]}   # k rows each, by construction
         if not proposal_append_gt:
             for name, value in p.get_fields().items():
                 if name not in ("proposal_boxes", "objectness_logits"):
-                    q.set(name, value[idx[n, :k].long()])
-        q.set("gt_classes", sc[n, :k])
-        q.set("ious", si[n, :k])
+                    f[name] = value[idx[n, :k].long()]
+        f["gt_classes"] = sc[n, :k]
+        f["ious"] = si[n, :k]
         for name in gt_names:
-            if q.has(name):
+            if name in f:
                 continue
             if name in batched:
                 kind, v = batched[name]
-                q.set(name, Boxes(v[n, :k]) if kind == "boxes" else v[n, :k])
+                f[name] = boxes_view(v[n, :k]) if kind == "boxes" else v[n, :k]
             else:
                 value = t.get(name)
                 st = sm_g[n, :k] - goff[n].long()
-                q.set(name, value.to(dev)[st] if hasattr(value, "to") else value[st])
-        out.append(q)
+                f[name] = value.to(dev)[st] if hasattr(value, "to") else value[st]
+        out.append(make_instances(p.image_size, **f))
     return out

@@ -189,3 +189,20 @@ def flat_prefixes(begins, counts, device) -> Tuple[torch.Tensor, torch.Tensor]:
     rep_b = np.repeat(b, c)
     both = torch.from_numpy(np.stack((rep_b + within, rep_b))).to(device, non_blocking=False)
     return both[0], both[1]
+
+
+def boxes_view(tensor: torch.Tensor) -> "Boxes":
+    """``Boxes`` around an (n, 4) fp32 tensor the caller just produced: skips the constructor's ``as_tensor`` / dtype / shape
+    handling (~4 us per object - with 32 images and four batched stages the per-image result objects are a measurable part
+    of the inference step).  Works for detectron2's ``Boxes`` as for the stand-in: both hold one attribute, ``tensor``."""
+    b = Boxes.__new__(Boxes)
+    b.tensor = tensor
+    return b
+
+
+def make_instances(image_size, **fields) -> "Instances":
+    """``Instances(image_size)`` holding ``fields`` - equally long by construction (the batched stages cut every field with
+    the same per-image counts), so the per-field length assertion of ``set`` is skipped."""
+    r = Instances(image_size)
+    r._fields.update(fields)
+    return r

@@ -114,3 +114,18 @@ def test_flat_prefixes_lists_the_first_rows_of_every_segment():
     assert P.tolist() == [0, 1, 20, 21, 22, 30] and B.tolist() == [0, 0, 20, 20, 20, 30]
     P, B = flat_prefixes([0, 5], [0, 0], "cpu")
     assert P.numel() == 0 and B.numel() == 0 and P.dtype == torch.int64
+
+
+def test_make_instances_and_boxes_view_build_the_same_objects_as_the_constructors():
+    from osr_b200.structures import Boxes, Instances, boxes_view, make_instances
+    t = torch.arange(12.0).reshape(3, 4)
+    a = Instances((5, 7))
+    a.set("proposal_boxes", Boxes(t))
+    a.set("objectness_logits", torch.ones(3))
+    b = make_instances((5, 7), proposal_boxes=boxes_view(t), objectness_logits=torch.ones(3))
+    assert type(b) is type(a) and b.image_size == a.image_size and len(b) == len(a) == 3
+    assert list(b.get_fields()) == list(a.get_fields())
+    assert type(b.proposal_boxes) is type(a.proposal_boxes) and b.proposal_boxes.tensor.data_ptr() == t.data_ptr()
+    assert torch.equal(b.proposal_boxes.tensor, a.proposal_boxes.tensor) and len(b.proposal_boxes) == 3
+    assert torch.equal(b[1:].objectness_logits, a[1:].objectness_logits)      # the result behaves like any Instances
+    assert len(make_instances((5, 7), x=torch.zeros(0))) == 0
