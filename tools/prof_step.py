@@ -12,7 +12,7 @@ from osr_b200.pipeline import PathConfig, RoiPathStep  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
-ap.add_argument("--images", type=int, default=16)
+ap.add_argument("--images", type=int, default=None, help="images per step (default: the configuration's own, 16 without --config)")
 ap.add_argument("--nchw", action="store_true")
 ap.add_argument("--config", default=None, help="cfg2 | cfg3 | cfg5 (training path shapes of that configuration)")
 ap.add_argument("--box-head", action="store_true", help="S4 on the path (bf16 pooled tile, fc1 / fc2 on tcgen05)")
@@ -30,7 +30,7 @@ elif a.config:
     from osr_b200.pipeline import make_config
     path = RoiPathStep(make_config(a.config, num_images=a.images, channels_last=not a.nchw, seed=3234), "cuda:0")
 else:
-    path = RoiPathStep(PathConfig(num_images=a.images, channels_last=not a.nchw, seed=3234, box_head=a.box_head), "cuda:0")
+    path = RoiPathStep(PathConfig(num_images=a.images or 16, channels_last=not a.nchw, seed=3234, box_head=a.box_head), "cuda:0")
 for _ in range(a.steps):
     path.step()
 torch.cuda.synchronize()
