@@ -14,12 +14,12 @@
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 
 from . import _lib
-from .structures import Boxes, Instances, boxes_view, flat_prefixes, make_instances
+from .structures import Instances, boxes_view, flat_prefixes, make_instances
 
 _MAX_SORT = 16384
 
